@@ -1,0 +1,414 @@
+// lgpu_api.cu — context lifetime, state transfer, step drivers, stage dumps (C ABI of include/lgpu.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "lgpu_neighbors.cuh"
+
+static thread_local char g_err[512] = "";
+void lgpu_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* lgpu_last_error(void) { return g_err; }
+
+extern "C" void lgpu_default_step_params(lgpu_step_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->dt = 0.01f;
+    p->gravity[0] = 0.0f; p->gravity[1] = -10.0f; p->gravity[2] = 0.0f;  // src/Simulation.hpp:162
+    p->rest_density = 24.0f; p->mass = 5.0f; p->relaxation_epsilon = 10.0f;  // :159-160,165
+    p->s_corr_dq = 0.5f; p->s_corr_k = 1.0f; p->s_corr_n = 4.0f;            // :168-170
+    p->iterations = 1;
+    p->literal_lambda_index = 1;
+    p->exact_math = 1;
+    p->sph_kernel = 0;
+    p->attract_radius = 1.5f; p->blow_radius = 2.0f; p->attract_coeff = 1000.0f; p->blow_coeff = 500.0f;  // :229-232
+    p->collision_coeff = 0.8f; p->friction_coeff = 0.7f; p->mu_s = 0.95f; p->mu_k = 0.9f;  // src/Simulate.cpp:159-163
+    p->credits = 0;
+}
+
+static const double kPi = 3.14159265358979323846;  // src/Lustrine.cpp:16
+
+static void make_geom(const lgpu_config& cfg, Geom* g) {
+    // src/Lustrine.cpp:105-107,251-266, same fp32/double operation order
+    g->domainX = (float)cfg.domain[0]; g->domainY = (float)cfg.domain[1]; g->domainZ = (float)cfg.domain[2];
+    g->idomX = (int)g->domainX; g->idomY = (int)g->domainY; g->idomZ = (int)g->domainZ;
+    g->radius = cfg.particle_radius; g->diameter = cfg.particle_diameter;
+    g->h = cfg.kernel_radius_scale * cfg.particle_radius;
+    g->h2 = g->h * g->h;
+    g->cell_size = 1.0f * g->h;
+    g->kernel_factor = 0.5f;  // src/Simulation.hpp:147
+    float h3 = (float)pow((double)g->h, 3.0);
+    g->cubic_k = (float)(8.0f / (kPi * h3));
+    g->cubic_l = (float)(48.0f / (kPi * h3));
+    g->gX = (int)(g->domainX / g->cell_size) + 1;
+    g->gY = (int)(g->domainY / g->cell_size) + 1;
+    g->gZ = (int)(g->domainZ / g->cell_size) + 1;
+    g->gXZ = g->gX * g->gZ;
+    g->C = g->gX * g->gY * g->gZ;
+}
+
+template <class T> static cudaError_t dalloc(T** p, size_t count) {
+    *p = nullptr;
+    return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+}
+
+extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
+    if (!cfg || !out) return LGPU_ERR_ARG;
+    if (cfg->domain[0] <= 0 || cfg->domain[1] <= 0 || cfg->domain[2] <= 0 || cfg->particle_radius <= 0.0f ||
+        cfg->capacity_sand < 0 || cfg->capacity_solid < 0 || cfg->kernel_radius_scale <= 0.0f) {
+        lgpu_set_error("lgpu_create: bad configuration");
+        return LGPU_ERR_ARG;
+    }
+    int device = cfg->device;
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    lgpu_ctx* c = new lgpu_ctx();
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->device = device;
+    make_geom(*cfg, &c->g);
+    c->cap = cfg->capacity_sand > 0 ? cfg->capacity_sand : 1;
+    c->cap_solid = cfg->capacity_solid;
+    c->M = cfg->max_neighbors > 0 ? cfg->max_neighbors : LGPU_DEFAULT_MAX_NEIGHBORS;
+    if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 1;
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(dalloc(&c->pos[k], cap)); CUDA_TRY(dalloc(&c->vel[k], cap));
+        CUDA_TRY(dalloc(&c->flags[k], cap)); CUDA_TRY(dalloc(&c->orig[k], cap));
+    }
+    CUDA_TRY(dalloc(&c->pstar_unsorted, cap)); CUDA_TRY(dalloc(&c->x0, cap));
+    CUDA_TRY(dalloc(&c->pa, cap)); CUDA_TRY(dalloc(&c->pb, cap));
+    CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap)); CUDA_TRY(dalloc(&c->rank_in, cap));
+    CUDA_TRY(dalloc(&c->tmp_id, cap)); CUDA_TRY(dalloc(&c->key, cap));
+    CUDA_TRY(dalloc(&c->cell_count, C1)); CUDA_TRY(dalloc(&c->cell_start, C1));
+    CUDA_TRY(dalloc(&c->scan_block_sums, C1 / 4096 + 4));
+    CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
+    CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
+    CUDA_TRY(dalloc(&c->nbr, cap * (size_t)c->M)); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
+    CUDA_TRY(dalloc(&c->lambda, cap)); CUDA_TRY(dalloc(&c->density, cap));
+    CUDA_TRY(dalloc(&c->lambda_head, (size_t)LGPU_LAMBDA_HEAD));
+    CUDA_TRY(dalloc(&c->counters, (size_t)4));
+    c->stage_bytes = sizeof(float) * 3 * cap;
+    CUDA_TRY(cudaMalloc((void**)&c->d_stage, c->stage_bytes));
+    CUDA_TRY(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * C1, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(int) * C1, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->solid_cell_start, 0, sizeof(int) * C1, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->lambda, 0, sizeof(float) * cap, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->lambda_head, 0, sizeof(float) * LGPU_LAMBDA_HEAD, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->nbr_cnt, 0, sizeof(int) * cap, c->stream));
+    for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreate(&c->ev[k]));
+    c->solids_sorted = true;  // no solids yet
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return LGPU_OK;
+}
+
+extern "C" void lgpu_destroy(lgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->flags[k]); cudaFree(c->orig[k]); }
+    cudaFree(c->pstar_unsorted); cudaFree(c->x0); cudaFree(c->pa); cudaFree(c->pb); cudaFree(c->perm);
+    cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
+    cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_block_sums);
+    cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
+    cudaFree(c->nbr); cudaFree(c->nbr_cnt); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
+    cudaFree(c->counters); cudaFree(c->d_stage);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+View lgpu_make_view(lgpu_ctx* c) {
+    View v;
+    v.g = c->g;
+    v.n = c->n; v.n_owned = c->n_owned; v.n_solid = c->n_solid; v.cap = c->cap; v.M = c->M;
+    v.pos_in = c->pos[0]; v.vel_in = c->vel[0]; v.pstar_in = c->pstar_unsorted;
+    v.flags_in = c->flags[0]; v.orig_in = c->orig[0];
+    v.pos = c->pos[1]; v.vel = c->vel[1]; v.x0 = c->x0; v.pa = c->pa; v.pb = c->pb;
+    v.flags = c->flags[1]; v.orig = c->orig[1]; v.perm = c->perm;
+    v.key_in = c->key_in; v.rank_in = c->rank_in; v.tmp_id = c->tmp_id; v.key = c->key;
+    v.cell_count = c->cell_count; v.cell_start = c->cell_start;
+    v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
+    v.nbr = c->nbr; v.nbr_cnt = c->nbr_cnt;
+    v.lambda = c->lambda; v.density = c->density; v.lambda_head = c->lambda_head;
+    v.counters = c->counters;
+    return v;
+}
+
+extern "C" int lgpu_get_grid(const lgpu_ctx* c, lgpu_grid_info* out) {
+    if (!c || !out) return LGPU_ERR_ARG;
+    out->grid[0] = c->g.gX; out->grid[1] = c->g.gY; out->grid[2] = c->g.gZ;
+    out->num_cells = c->g.C;
+    out->cell_size = c->g.cell_size; out->kernel_radius = c->g.h;
+    out->cubic_k = c->g.cubic_k; out->cubic_l = c->g.cubic_l;
+    return LGPU_OK;
+}
+
+extern "C" int lgpu_num_sand(const lgpu_ctx* c) { return c ? c->n_owned : 0; }
+extern "C" int lgpu_num_solids(const lgpu_ctx* c) { return c ? c->n_solid : 0; }
+extern "C" long lgpu_launch_count(const lgpu_ctx* c) { return c ? c->launches : 0; }
+extern "C" int lgpu_set_phase_timing(lgpu_ctx* c, int on) { if (!c) return LGPU_ERR_ARG; c->phase_timing = on != 0; return LGPU_OK; }
+extern "C" int lgpu_set_use_graph(lgpu_ctx* c, int on) {
+    if (!c) return LGPU_ERR_ARG;
+    c->use_graph = on != 0;
+    if (!on && c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return LGPU_OK;
+}
+extern "C" int lgpu_sync(lgpu_ctx* c) {
+    if (!c) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LGPU_OK;
+}
+
+// ---------------- state transfer ----------------
+__global__ void k_unpack3(const float* __restrict__ src, int n, float4* __restrict__ dst, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[offset + i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.0f);
+}
+__global__ void k_fill_meta(int n, int offset, const int* __restrict__ flags_src, int* __restrict__ flags, int* __restrict__ orig,
+                            float4* __restrict__ vel, int zero_vel) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[offset + i] = flags_src ? flags_src[i] : 0;
+    orig[offset + i] = offset + i;
+    if (zero_vel) vel[offset + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+// scatter to the reference slot: out[orig[i]] = src[i]
+__global__ void k_pack3_by_orig(const float4* __restrict__ src, const int* __restrict__ orig, int n, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = src[i];
+    int o = orig[i];
+    dst[3 * o] = a.x; dst[3 * o + 1] = a.y; dst[3 * o + 2] = a.z;
+}
+__global__ void k_pack1_by_orig(const int* __restrict__ src, const int* __restrict__ orig, int n, int* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[orig[i]] = src[i];
+}
+
+static int put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float* vel, const int* flags) {
+    if (n == 0) return LGPU_OK;
+    const int blocks = lgpu_blocks(n);
+    CUDA_TRY(cudaMemcpyAsync(c->d_stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->d_stage, n, c->pos[0], offset);
+    if (vel) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_stage, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+        k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->d_stage, n, c->vel[0], offset);
+    }
+    int* d_flags = nullptr;
+    if (flags) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        d_flags = (int*)c->d_stage;
+        CUDA_TRY(cudaMemcpyAsync(d_flags, flags, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    k_fill_meta<<<blocks, LGPU_BLOCK, 0, c->stream>>>(n, offset, d_flags, c->flags[0], c->orig[0], c->vel[0], vel ? 0 : 1);
+    c->launches += vel ? 3 : 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LGPU_OK;
+}
+
+extern "C" int lgpu_upload_sand(lgpu_ctx* c, int n, const float* pos, const float* vel, const int* flags) {
+    if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
+    if (n > c->cap) { lgpu_set_error("lgpu_upload_sand: %d particles > capacity %d", n, c->cap); return LGPU_ERR_CAPACITY; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->n = c->n_owned = n;
+    c->grid_valid = false;
+    CUDA_TRY(cudaMemsetAsync(c->lambda_head, 0, sizeof(float) * LGPU_LAMBDA_HEAD, c->stream));
+    return put_sand(c, 0, n, pos, vel, flags);
+}
+
+extern "C" int lgpu_append_sand(lgpu_ctx* c, int n, const float* pos, const float* vel, const int* flags) {
+    if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
+    if (c->n_owned + n > c->cap) { lgpu_set_error("lgpu_append_sand: capacity %d exceeded", c->cap); return LGPU_ERR_CAPACITY; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    int st = put_sand(c, c->n_owned, n, pos, vel, flags);
+    if (st) return st;
+    c->n_owned += n;
+    c->n = c->n_owned;
+    c->grid_valid = false;
+    return LGPU_OK;
+}
+
+extern "C" int lgpu_upload_solids(lgpu_ctx* c, int n, const float* pos) {
+    if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
+    if (n > c->cap_solid) { lgpu_set_error("lgpu_upload_solids: %d > capacity %d", n, c->cap_solid); return LGPU_ERR_CAPACITY; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->n_solid = n;
+    c->solids_sorted = false;
+    if (n > 0) {
+        float* stage;
+        CUDA_TRY(cudaMalloc((void**)&stage, sizeof(float) * 3 * n));
+        CUDA_TRY(cudaMemcpyAsync(stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+        k_unpack3<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(stage, n, c->solid_pos_unsorted, 0);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(stage);
+    }
+    return lgpu_sort_solids(c);
+}
+
+extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flags) {
+    if (!c) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int n = c->n_owned;
+    if (n == 0) return LGPU_OK;
+    const int blocks = lgpu_blocks(n);
+    if (pos) {
+        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->pos[0], c->orig[0], n, c->d_stage);
+        CUDA_TRY(cudaMemcpyAsync(pos, c->d_stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->launches++;
+    }
+    if (vel) {
+        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->vel[0], c->orig[0], n, c->d_stage);
+        CUDA_TRY(cudaMemcpyAsync(vel, c->d_stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->launches++;
+    }
+    if (flags) {
+        k_pack1_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->flags[0], c->orig[0], n, (int*)c->d_stage);
+        CUDA_TRY(cudaMemcpyAsync(flags, c->d_stage, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LGPU_OK;
+}
+
+// ---------------- step drivers ----------------
+static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
+    int st;
+    const bool pt = c->phase_timing;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
+    if (st) return st;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C, true);
+    if (st) return st;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    st = lgpu_launch_reorder(c, mode == 2);
+    if (st) return st;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    st = lgpu_launch_build_table(c, mode == 2);
+    if (st) return st;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
+    if (st) return st;
+    if (pt) CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+    return LGPU_OK;
+}
+
+static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
+    if (!c || !p) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->solids_sorted) { int st = lgpu_sort_solids(c); if (st) return st; }
+    c->last_params = *p;
+    c->last_mode = mode;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    int st = enqueue_step(c, *p, mode);
+    if (st) return st;
+    CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
+    c->grid_valid = true;
+    return LGPU_OK;
+}
+
+extern "C" int lgpu_step_fluid(lgpu_ctx* c, const lgpu_step_params* p) { return run_step(c, p, 1); }
+extern "C" int lgpu_step_sand(lgpu_ctx* c, const lgpu_step_params* p) { return run_step(c, p, 2); }
+
+extern "C" int lgpu_last_step_ms(lgpu_ctx* c, int phase, float* ms) {
+    if (!c || !ms || phase < 0 || phase > 5) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev[7]));
+    if (phase == 0) { CUDA_TRY(cudaEventElapsedTime(ms, c->ev[0], c->ev[7])); return LGPU_OK; }
+    if (!c->phase_timing) { *ms = 0.0f; return LGPU_OK; }
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev[phase], c->ev[phase + 1]));
+    return LGPU_OK;
+}
+
+// ---------------- stage dumps ----------------
+__global__ void k_dump_pstar(const float4* __restrict__ src, int n, float* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = src[i];
+    dst[3 * i] = a.x; dst[3 * i + 1] = a.y; dst[3 * i + 2] = a.z;
+}
+
+template <bool SAND>
+__global__ void k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n_owned) return;
+    long t = offsets[i];
+    for_each_neighbor<SAND>(v, i, [&](int j) { flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j]; });
+}
+
+extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
+    if (!c || !out) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->n_owned;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case LGPU_DUMP_KEYS: src = c->key; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_PERM: src = c->perm; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_ORIG: src = c->orig[0]; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_NBR_COUNT: src = c->nbr_cnt; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_DENSITY: src = c->density; bytes = sizeof(float) * n; break;
+        case LGPU_DUMP_LAMBDA: src = c->lambda; bytes = sizeof(float) * n; break;
+        case LGPU_DUMP_CELL_START: src = c->cell_start; bytes = sizeof(int) * ((size_t)c->g.C + 1); break;
+        case LGPU_DUMP_COUNTERS: src = c->counters; bytes = sizeof(unsigned long long) * 4; break;
+        case LGPU_DUMP_PSTAR: {
+            bytes = sizeof(float) * 3 * n;
+            if (out_bytes < bytes) return LGPU_ERR_ARG;
+            if (n == 0) return LGPU_OK;
+            if (!c->pstar_final) return LGPU_ERR_ARG;
+            k_dump_pstar<<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(c->pstar_final, (int)n, c->d_stage);
+            CUDA_TRY(cudaMemcpyAsync(out, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            return LGPU_OK;
+        }
+        case LGPU_DUMP_NBR: {
+            if (n == 0) return LGPU_OK;
+            std::vector<int> cnt(n);
+            CUDA_TRY(cudaMemcpy(cnt.data(), c->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost));
+            std::vector<long> off(n + 1);
+            off[0] = 0;
+            for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
+            bytes = sizeof(int) * (size_t)off[n];
+            if (out_bytes < bytes) return LGPU_ERR_ARG;
+            if (off[n] == 0) return LGPU_OK;
+            long* d_off; int* d_flat;
+            CUDA_TRY(cudaMalloc((void**)&d_off, sizeof(long) * (n + 1)));
+            CUDA_TRY(cudaMalloc((void**)&d_flat, bytes));
+            CUDA_TRY(cudaMemcpy(d_off, off.data(), sizeof(long) * (n + 1), cudaMemcpyHostToDevice));
+            View v = lgpu_make_view(c);
+            if (c->last_mode == 2) k_dump_nbr<true><<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(v, d_off, d_flat);
+            else k_dump_nbr<false><<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(v, d_off, d_flat);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(out, d_flat, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(d_off); cudaFree(d_flat);
+            return LGPU_OK;
+        }
+        default: return LGPU_ERR_ARG;
+    }
+    if (out_bytes < bytes) { lgpu_set_error("lgpu_dump: buffer too small (%zu < %zu)", out_bytes, bytes); return LGPU_ERR_ARG; }
+    if (bytes) CUDA_TRY(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return LGPU_OK;
+}

@@ -1,0 +1,249 @@
+// lgpu_internal.cuh — shared declarations of liblgpu.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "lgpu.h"
+
+#define LGPU_DEFAULT_MAX_NEIGHBORS 32
+#define LGPU_LAMBDA_HEAD 4096  // lambdas[loop counter] table: first slots in reference order
+#define LGPU_BLOCK 128
+
+// ---------------------------------------------------------------------------------------
+// Device-side view of a context.  Passed BY VALUE to every kernel (lives in the constant
+// bank), so scalar parameters are re-read on every launch like the reference re-reads its
+// public struct on every call.
+// ---------------------------------------------------------------------------------------
+struct Geom {
+    float domainX, domainY, domainZ;  // float copies of the int domain (src/Lustrine.cpp:105-107)
+    int idomX, idomY, idomZ;          // int X = simulation->domainX truncation (src/Simulate.cpp:35-37)
+    float radius, diameter;
+    float h, h2;                      // kernelRadius and its fp32 square (src/neighbors/Neighbors.cpp:349)
+    float cell_size, kernel_factor;
+    float cubic_k, cubic_l;
+    int gX, gY, gZ, gXZ, C;
+};
+
+struct View {
+    Geom g;
+    int n;        // sand particles resident (owned + ghosts)
+    int n_owned;  // sand particles this context updates
+    int n_solid;
+    int cap;      // row stride of the neighbour table
+    int M;        // neighbour table width
+    // unsorted (pre-reorder) buffers, indexed by the storage slot of the previous step
+    float4 *pos_in, *vel_in, *pstar_in;
+    int *flags_in, *orig_in;
+    // sorted buffers of this step
+    float4 *pos, *vel, *x0;  // x0 = predicted positions at grid-build time (frozen)
+    float4 *pa, *pb;         // ping-pong predicted positions of the solver iterations
+    int *flags, *orig, *perm;
+    int *key_in, *rank_in, *tmp_id, *key;
+    int *cell_count, *cell_start;
+    // solids, sorted by cell once (src/neighbors/Neighbors.cpp:266-272)
+    float4* solid_pos;
+    int *solid_orig, *solid_cell_start;
+    // neighbour table (column-major: entry k of particle i at nbr[k * cap + i]); sand = slot,
+    // solid = ~sorted_solid_slot
+    int *nbr, *nbr_cnt;
+    float *lambda, *density, *lambda_head;
+    unsigned long long* counters;  // [0] key violations, [1] table overflows
+};
+
+struct lgpu_ctx {
+    lgpu_config cfg;
+    Geom g;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int n, n_owned, n_solid, cap, cap_solid, M;
+    bool grid_valid;      // cell_start/key describe the current storage
+    bool solids_sorted;
+    // device buffers (see View)
+    float4 *pos[2], *vel[2], *pstar_unsorted, *x0, *pa, *pb;
+    int *flags[2], *orig[2], *perm;
+    int cur;  // which of the [2] buffers holds the current storage
+    int *key_in, *rank_in, *tmp_id, *key;
+    int *cell_count, *cell_start, *scan_block_sums;
+    float4 *solid_pos, *solid_pos_unsorted;
+    int *solid_orig, *solid_cell_start;
+    int *nbr, *nbr_cnt;
+    float *lambda, *density, *lambda_head;
+    unsigned long long* counters;
+    float4* pstar_final;  // where the last step left x* (for dumps)
+    // staging
+    float *h_stage, *d_stage;
+    size_t stage_bytes;
+    // timing
+    cudaEvent_t ev[8];
+    bool phase_timing;
+    float phase_ms[6];
+    long launches;
+    // graphs
+    bool use_graph;
+    cudaGraphExec_t graph_exec;
+    int graph_sig[4];
+    lgpu_step_params last_params;
+    int last_mode;  // 0 none, 1 fluid, 2 sand
+};
+
+void lgpu_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            lgpu_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return LGPU_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+static inline int lgpu_blocks(long n, int block = LGPU_BLOCK) { return (int)((n + block - 1) / block); }
+
+View lgpu_make_view(lgpu_ctx* c);
+
+// ---- launch wrappers, one per translation unit ----
+int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p);
+int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p);
+int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts);
+int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig);
+int lgpu_sort_solids(lgpu_ctx* c);
+int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order);
+int lgpu_launch_fluid_solver(lgpu_ctx* c, const lgpu_step_params& p);
+int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p);
+
+// ---------------------------------------------------------------------------------------
+// Arithmetic policies.
+//   Exact: every operation is a separately rounded IEEE fp32 operation in the reference's
+//          order (the __f*_rn intrinsics are never contracted into FMAs), matching the
+//          reference compiled with -O2 -ffp-contract=off.
+//   Fast:  plain operators (nvcc contracts to FMA) and approximate reciprocal / rsqrt.
+// Keys, the neighbour predicate and the contact predicate ALWAYS use Exact.
+// ---------------------------------------------------------------------------------------
+struct Exact {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static constexpr bool exact = true;
+};
+struct Fast {
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static constexpr bool exact = false;
+};
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 f3(float4 a) { return f3(a.x, a.y, a.z); }
+__device__ __forceinline__ float4 f4(F3 a, float w = 0.0f) { return make_float4(a.x, a.y, a.z, w); }
+
+// glm 0.9.9.8 semantics: dot = (x*x + y*y) + z*z on separately rounded products, length = sqrt(dot),
+// normalize = v * (1/sqrt(dot)) (thirdparty/glm-0.9.9.8/glm/detail/func_geometric.inl:8-14,48-55,82-90).
+template <class P> __device__ __forceinline__ F3 vadd(F3 a, F3 b) { return f3(P::add(a.x, b.x), P::add(a.y, b.y), P::add(a.z, b.z)); }
+template <class P> __device__ __forceinline__ F3 vsub(F3 a, F3 b) { return f3(P::sub(a.x, b.x), P::sub(a.y, b.y), P::sub(a.z, b.z)); }
+template <class P> __device__ __forceinline__ F3 vscale(F3 a, float s) { return f3(P::mul(a.x, s), P::mul(a.y, s), P::mul(a.z, s)); }
+template <class P> __device__ __forceinline__ F3 vdiv(F3 a, float s) { return f3(P::div(a.x, s), P::div(a.y, s), P::div(a.z, s)); }
+template <class P> __device__ __forceinline__ float vdot(F3 a, F3 b) {
+    return P::add(P::add(P::mul(a.x, b.x), P::mul(a.y, b.y)), P::mul(a.z, b.z));
+}
+template <class P> __device__ __forceinline__ float vlen(F3 a) { return P::sqrt(vdot<P>(a, a)); }
+template <class P> __device__ __forceinline__ F3 vnormalize(F3 a) { return vscale<P>(a, P::div(1.0f, P::sqrt(vdot<P>(a, a)))); }
+__device__ __forceinline__ F3 vneg(F3 a) { return f3(-a.x, -a.y, -a.z); }
+
+// get_cell_id, src/neighbors/Utils.hpp:24-33: IEEE division, truncation toward zero, no clamp.
+// Ids outside [0, C) (undefined behaviour in the reference) are clamped and counted.
+__device__ __forceinline__ int cell_id_raw(const Geom& g, F3 p) {
+    int cx = __float2int_rz(__fdiv_rn(p.x, g.cell_size));
+    int cy = __float2int_rz(__fdiv_rn(p.y, g.cell_size));
+    int cz = __float2int_rz(__fdiv_rn(p.z, g.cell_size));
+    return cy * g.gXZ + cx * g.gZ + cz;
+}
+__device__ __forceinline__ int cell_id_checked(const Geom& g, F3 p, unsigned long long* counters) {
+    int id = cell_id_raw(g, p);
+    if (id < 0 || id >= g.C) {
+        atomicAdd(&counters[0], 1ULL);
+        id = id < 0 ? 0 : g.C - 1;
+    }
+    return id;
+}
+
+// neighbour predicate, src/neighbors/Neighbors.cpp:347-349,433-435: dot(t,t) <= h*h, t = self - other
+__device__ __forceinline__ bool within_h(const Geom& g, F3 self, F3 other) {
+    F3 t = vsub<Exact>(self, other);
+    return vdot<Exact>(t, t) <= g.h2;
+}
+
+// cubic_kernel, src/Kernels.cpp:6-19
+template <class P> __device__ __forceinline__ float cubic_W(const Geom& g, float r) {
+    float q = P::div(P::mul(r, g.kernel_factor), g.h);
+    float result = 0.0f;
+    if (q <= 1.0f) {
+        if (q <= 0.5f) {
+            float q2 = P::mul(q, q);
+            float q3 = P::mul(q2, q);
+            result = P::mul(g.cubic_k, P::add(P::sub(P::mul(6.0f, q3), P::mul(6.0f, q2)), 1.0f));
+        } else {
+            float f = P::sub(1.0f, q);
+            result = P::mul(g.cubic_k, P::mul(2.0f, (float)pow((double)f, 3.0)));
+        }
+    }
+    return result;
+}
+
+// cubic_kernel_grad, src/Kernels.cpp:26-41
+template <class P> __device__ __forceinline__ F3 cubic_gradW(const Geom& g, F3 r) {
+    F3 result = f3(0.0f, 0.0f, 0.0f);
+    float rl = P::mul(vlen<P>(r), g.kernel_factor);
+    float q = P::div(rl, g.h);
+    if (rl > 1.0e-5f && q <= 1.0f) {
+        F3 grad_q = vscale<P>(r, P::div(1.0f, P::mul(rl, g.h)));
+        if (q <= 0.5f) {
+            result = vscale<P>(grad_q, P::mul(P::mul(g.cubic_l, q), P::sub(P::mul(3.0f, q), 2.0f)));
+        } else {
+            float f = P::sub(1.0f, q);
+            result = vscale<P>(grad_q, P::mul(g.cubic_l, P::mul(-f, f)));
+        }
+    }
+    return result;
+}
+
+// poly6_kernel(float), src/Kernels.cpp:43-51 — std::pow(float,int) promotes: evaluated in double
+__device__ __forceinline__ float poly6_W(const Geom& g, float r) {
+    float result = 0.0f;
+    float hf = __fmul_rn(g.h, g.kernel_factor);
+    if (r <= g.h) {
+        double a = 315.0f / ((double)__fmul_rn(64.0f, 3.14f) * pow((double)hf, 9.0));
+        double kr = (double)__fmul_rn(g.kernel_factor, r);
+        double d = (double)hf * (double)hf - kr * kr;
+        result = (float)(a * (d * d * d));
+    }
+    return result;
+}
+
+// spiky_kernel, src/Kernels.cpp:57-67
+__device__ __forceinline__ F3 spiky_gradW(const Geom& g, F3 r) {
+    F3 result = f3(0.0f, 0.0f, 0.0f);
+    float rl = vlen<Exact>(r);
+    if (rl > 0.0f && rl <= g.h) {
+        float hf = __fmul_rn(g.h, g.kernel_factor);
+        double e = (double)__fsub_rn(hf, __fmul_rn(rl, g.kernel_factor));
+        float temp = (float)((15.0f / ((double)3.14f * pow((double)hf, 6.0))) * (e * e));
+        result = vscale<Exact>(vdiv<Exact>(r, __fmul_rn(rl, g.kernel_factor)), temp);
+    }
+    return result;
+}
+
+// std::pow(float,float) of s_coor (src/Simulate.cpp:8).  glibc's powf evaluates in double and
+// rounds once; the device equivalent is a double pow rounded to float (n == 4: two exact-ish
+// double multiplies).
+__device__ __forceinline__ float powf_like_libm(float x, float n) {
+    if (n == 4.0f) { double x2 = (double)x * (double)x; return (float)(x2 * x2); }
+    return (float)pow((double)x, (double)n);
+}

@@ -1,0 +1,158 @@
+// lgpu_sand.cu — position-based-dynamics contact + Coulomb friction iterations for sand.
+// Replaces the solver loop of Lustrine::simulate_sand, src/Simulate.cpp:226-311, and the
+// velocity/position commit :316-319 (simulate_sand_credits: :401-502, different mu and the
+// "no gravity" bit).
+//
+// One fused kernel per Jacobi iteration: contact push-out + friction + box clamp (+ commit on
+// the last iteration).  Reads the current x* and the OLD positions of the neighbours, writes the
+// next x* to the other ping-pong buffer (the reference's positions_tmp copy, :310).
+#include "lgpu_neighbors.cuh"
+#include <math.h>
+
+struct SandParams {
+    float dt, mass, diameter;
+    float collision_coeff, friction_coeff, mu_s, mu_k;
+    float d2_contact_max;  // largest fp32 d2 with sqrt_rn(d2) <= diameter: `len > diameter` <=> d2 > this
+    float cc_half;         // collision_coeff * m / (m + m), evaluated in the reference's order
+    int credits;
+};
+
+__device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
+
+template <class P, bool LAST>
+__global__ void __launch_bounds__(LGPU_BLOCK) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n_owned) return;
+    const Geom& g = v.g;
+    const F3 pi = f3(cur[i]);
+    const F3 xi_old = f3(v.pos[i]);
+    F3 deltap = f3(0.0f, 0.0f, 0.0f);
+    bool touched = false;
+    for_each_neighbor<true>(v, i, [&](int j) {
+        const bool is_sand = j >= 0;
+        F3 pj = is_sand ? f3(cur[j]) : f3(v.solid_pos[~j]);
+        // :235-240 — contact predicate, always Exact
+        F3 ij = vsub<Exact>(pi, pj);
+        float d2 = vdot<Exact>(ij, ij);
+        if (d2 == 0.0f) {  // glm::length(ij) == 0.0f
+            ij = f3(0.0f, 0.00001f, 0.0f);
+            d2 = vdot<Exact>(ij, ij);
+        }
+        if (d2 > sp.d2_contact_max) return;  // len > particleDiameter
+        touched = true;
+        if (P::exact) {
+            float len = __fsqrt_rn(d2);
+            F3 tmp, xjdelta, nrm;
+            if (is_sand) {  // :242-255
+                float sc = P::mul(sp.cc_half, P::sub(len, sp.diameter));
+                tmp = vdiv<P>(vscale<P>(ij, sc), len);
+                xjdelta = vsub<P>(vadd<P>(pj, tmp), f3(v.pos[j]));
+                nrm = vsub<P>(vsub<P>(pi, tmp), vadd<P>(pj, tmp));
+            } else {        // :268-276
+                float sc = P::mul(sp.collision_coeff, P::sub(len, sp.diameter));
+                tmp = vdiv<P>(vscale<P>(ij, sc), len);
+                xjdelta = f3(0.0f, 0.0f, 0.0f);
+                nrm = vsub<P>(vsub<P>(pi, tmp), pj);
+            }
+            deltap = vsub<P>(deltap, tmp);
+            float d = vlen<P>(tmp);
+            F3 xidelta = vsub<P>(vsub<P>(pi, tmp), xi_old);
+            nrm = vnormalize<P>(nrm);
+            F3 rel = vsub<P>(xidelta, xjdelta);
+            F3 xtan = vsub<P>(rel, vscale<P>(nrm, vdot<P>(rel, nrm)));
+            float lt = P::add(vlen<P>(xtan), 1e-9f);  // avoid0, :134
+            if (P::mul(d, sp.mu_s) > lt) {
+                deltap = vsub<P>(deltap, vscale<P>(xtan, sp.friction_coeff));
+            } else {
+                float ratio = P::div(P::mul(sp.mu_k, d), lt);
+                ratio = ratio < 1.0f ? ratio : 1.0f;
+                deltap = vsub<P>(deltap, vscale<P>(vscale<P>(xtan, sp.friction_coeff), ratio));
+            }
+        } else {
+            // Fast policy: same algebra with FMA contraction and approximate rsqrt.
+            float rinv = rsqrt_approx(d2);
+            float len = d2 * rinv;
+            float sc = (is_sand ? sp.cc_half : sp.collision_coeff) * (len - sp.diameter) * rinv;
+            F3 tmp = f3(ij.x * sc, ij.y * sc, ij.z * sc);
+            deltap.x -= tmp.x; deltap.y -= tmp.y; deltap.z -= tmp.z;
+            float d = fabsf(sc) * len;  // |tmp|
+            F3 a = f3(pi.x - tmp.x, pi.y - tmp.y, pi.z - tmp.z);
+            F3 rel = f3(a.x - xi_old.x, a.y - xi_old.y, a.z - xi_old.z);
+            F3 nrm;
+            if (is_sand) {
+                F3 b = f3(pj.x + tmp.x, pj.y + tmp.y, pj.z + tmp.z);
+                F3 xo = f3(v.pos[j]);
+                rel.x -= b.x - xo.x; rel.y -= b.y - xo.y; rel.z -= b.z - xo.z;
+                nrm = f3(a.x - b.x, a.y - b.y, a.z - b.z);
+            } else {
+                nrm = f3(a.x - pj.x, a.y - pj.y, a.z - pj.z);
+            }
+            float ninv = rsqrt_approx(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+            nrm.x *= ninv; nrm.y *= ninv; nrm.z *= ninv;
+            float dn = rel.x * nrm.x + rel.y * nrm.y + rel.z * nrm.z;
+            F3 xtan = f3(rel.x - dn * nrm.x, rel.y - dn * nrm.y, rel.z - dn * nrm.z);
+            float lt = sqrtf(xtan.x * xtan.x + xtan.y * xtan.y + xtan.z * xtan.z) + 1e-9f;
+            float s = sp.friction_coeff;
+            if (!(d * sp.mu_s > lt)) s *= fminf(__fdividef(sp.mu_k * d, lt), 1.0f);
+            deltap.x -= s * xtan.x; deltap.y -= s * xtan.y; deltap.z -= s * xtan.z;
+        }
+    });
+    F3 ps = P::exact ? vadd<Exact>(pi, deltap) : f3(pi.x + deltap.x, pi.y + deltap.y, pi.z + deltap.z);  // :288
+    const float r = g.radius;
+    ps.x = fminf(fmaxf(ps.x, r), __fsub_rn(g.domainX, r));  // :307
+    ps.y = fminf(fmaxf(ps.y, r), __fsub_rn(g.domainY, r));
+    ps.z = fminf(fmaxf(ps.z, r), __fsub_rn(g.domainZ, r));
+    next[i] = f4(ps);
+    if (sp.credits && touched) {  // :463-470: the "no gravity" bit drops at the first contact
+        int a = v.flags[i];
+        if (a & 2) v.flags[i] = a & ~2;
+    }
+    if (LAST) {  // :316-319, always Exact
+        // Written to the step-boundary storage (the pre-reorder buffers, free since k_reorder):
+        // other threads still read the OLD sorted positions v.pos[j] in this launch.
+        v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(ps, xi_old), sp.dt));
+        v.pos_in[i] = f4(ps);
+        v.flags_in[i] = v.flags[i];
+        v.orig_in[i] = v.orig[i];
+    }
+}
+
+// largest fp32 x with sqrt_rn(x) <= d  (so that `sqrt(d2) > d` <=> `d2 > x`, bit-exactly)
+static float contact_threshold(float d) {
+    float x = d * d;
+    while (sqrtf(x) > d) x = nextafterf(x, 0.0f);
+    while (sqrtf(nextafterf(x, INFINITY)) <= d) x = nextafterf(x, INFINITY);
+    return x;
+}
+
+int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
+    if (c->n_owned == 0) return LGPU_OK;
+    View v = lgpu_make_view(c);
+    SandParams sp;
+    sp.dt = p.dt; sp.mass = p.mass; sp.diameter = c->g.diameter;
+    sp.collision_coeff = p.collision_coeff; sp.friction_coeff = p.friction_coeff;
+    sp.mu_s = p.mu_s; sp.mu_k = p.mu_k;
+    sp.d2_contact_max = contact_threshold(c->g.diameter);
+    sp.cc_half = p.collision_coeff * p.mass / (p.mass + p.mass);  // src/Simulate.cpp:246, left to right
+    sp.credits = p.credits;
+    const int K = p.iterations < 1 ? 1 : p.iterations;
+    const int blocks = lgpu_blocks(c->n_owned);
+    const float4* cur = c->x0;
+    float4* bufs[2] = {c->pa, c->pb};
+    for (int it = 0; it < K; it++) {
+        float4* next = bufs[it & 1];
+        const bool last = it == K - 1;
+        if (p.exact_math) {
+            if (last) k_sand_iteration<Exact, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+            else k_sand_iteration<Exact, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+        } else {
+            if (last) k_sand_iteration<Fast, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+            else k_sand_iteration<Fast, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+        }
+        c->launches++;
+        cur = next;
+    }
+    c->pstar_final = (float4*)cur;
+    CUDA_TRY(cudaGetLastError());
+    return LGPU_OK;
+}

@@ -1,0 +1,376 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/lgpu.h), against the oracle.
+
+Contract: cell keys, sort permutation and neighbour lists (order included) are
+bit-exact; densities, lambdas, positions and velocities agree within REL_TOL = 1e-5 relative
+(ABS_TOL = 1e-5 absolute floor) per teacher-forced substep.  With exact_math=1 the device
+performs the reference's fp32 operations one by one, so most arrays are in fact bit-identical;
+the tests print the observed maximum error next to the asserted tolerance.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as O
+import scenes
+from lustrine_b200 import lgpu
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+ABS_TOL = 1e-5
+
+
+def close(a, b, what, rtol=REL_TOL, atol=ABS_TOL):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    bound = atol + rtol * np.abs(b)
+    worst = float((err / bound).max()) if err.size else 0.0
+    exact = float((a == b).mean()) if err.size else 1.0
+    print("  %-10s max|err| %.3e  worst err/bound %.3f  bit-exact %.4f" % (what, err.max() if err.size else 0.0, worst, exact))
+    assert worst <= 1.0, "%s outside tolerance: max|err| %.3e" % (what, err.max())
+
+
+def make_pair(domain, sand, solids=None, **ctx_kw):
+    n_solid = 0 if solids is None else len(solids)
+    P = O.PortSim(*domain, capacity=len(sand) + 64, n_solid=n_solid)
+    P.set_sand(sand)
+    G = lgpu.Context(domain, capacity_sand=len(sand) + 64, capacity_solid=n_solid, **ctx_kw)
+    G.upload_sand(sand)
+    if n_solid:
+        P.set_solid(solids)
+        G.upload_solids(solids)
+    return P, G
+
+
+def force_state(P, G):
+    """Teacher forcing: the GPU state is reset to the oracle's state before a compared substep."""
+    G.upload_sand(P.positions.copy(), P.velocities.copy(), P.attracted.copy())
+
+
+# ----------------------------------------------------------------------------------------------
+def test_counting_sort_known_answer():
+    # restated from the reference's only unit test, experiments/unit_tests/main.cpp:46-89
+    rng = np.random.default_rng(2022)
+    keys = rng.integers(0, 1987, 20000).astype(np.int32)
+    got = lgpu.counting_sort(keys, 1987)
+    assert np.array_equal(got, np.argsort(keys, kind="stable").astype(np.int32))
+    assert np.array_equal(got, O.counting_sort_port(keys, 1987))
+    assert np.array_equal(keys[got], np.sort(keys))
+    # edge cases: empty, single, all-equal, maximum key
+    assert lgpu.counting_sort(np.zeros(0, np.int32), 5).shape == (0,)
+    assert np.array_equal(lgpu.counting_sort(np.array([3], np.int32), 5), [0])
+    assert np.array_equal(lgpu.counting_sort(np.full(1000, 4, np.int32), 5), np.arange(1000))
+    big = rng.integers(0, 3_000_000, 100000).astype(np.int32)
+    assert np.array_equal(lgpu.counting_sort(big, 3_000_000), np.argsort(big, kind="stable"))
+
+
+def test_kernel_tables():
+    P = O.PortSim(60, 40, 40, capacity=1)
+    with lgpu.Context((60, 40, 40), capacity_sand=1) as G:
+        h = G.kernel_radius
+        assert (G.grid, G.num_cells) == ((P.s.gridX, P.s.gridY, P.s.gridZ), P.s.num_grid_cells)
+        assert (G.kernel_radius, G.cubic_k, G.cubic_l) == (P.s.kernelRadius, P.s.cubic_kernel_k, P.s.cubic_kernel_l)
+        r = np.linspace(0.0, 2.0 * h, 4096).astype(np.float32)
+        rng = np.random.default_rng(5)
+        d = rng.normal(size=(4096, 3)).astype(np.float32)
+        d *= (r / np.linalg.norm(d, axis=1))[:, None].astype(np.float32)
+        d[0] = 0.0
+        L = P.L
+        W = np.array([L.lo_cubic_kernel(P.p, float(x)) for x in r], np.float32)
+        p6 = np.array([L.lo_poly6_kernel(P.p, float(x)) for x in r], np.float32)
+        sc = np.array([L.lo_s_coor(P.p, float(x)) for x in r], np.float32)
+        gW = np.zeros_like(d); sp = np.zeros_like(d)
+        for i in range(len(d)):
+            L.lo_cubic_kernel_grad(P.p, d[i].ctypes.data, gW[i].ctypes.data)
+            L.lo_spiky_kernel(P.p, d[i].ctypes.data, sp[i].ctypes.data)
+
+        def ulps(a, b):
+            a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+            spacing = np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
+            return float((np.abs(a.astype(np.float64) - b) / np.maximum(spacing, np.float32(1e-45))).max())
+
+        for name, which, ref, arg, tol in (("W", 0, W, r, 0), ("gradW", 1, gW, d, 0), ("poly6", 2, p6, r, 4),
+                                           ("spiky", 3, sp, d, 4), ("s_coor", 4, sc, r, 4)):
+            got = G.eval_kernel(which, arg, exact=True)
+            u = ulps(got, ref)
+            print("  %-6s exact: %.1f ulp (tolerance %d)" % (name, u, tol))
+            assert u <= tol, name
+        for name, which, ref, arg in (("W", 0, W, r), ("gradW", 1, gW, d), ("s_coor", 4, sc, r)):
+            got = G.eval_kernel(which, arg, exact=False)
+            scale = np.abs(ref).max()
+            err = np.abs(got.astype(np.float64) - ref).max() / scale
+            print("  %-6s fast: max err / max|ref| = %.2e" % (name, err))
+            assert err <= 1e-5, name
+
+
+# ----------------------------------------------------------------------------------------------
+def compare_fluid_substep(P, G, iterations, literal, exact, check_lists=True):
+    n = P.n
+    force_state(P, G)
+    P.L.lo_step_fluid(P.p, 0.01, iterations, 1, int(literal))
+    G.step_fluid(dt=0.01, iterations=iterations, literal_lambda_index=int(literal), exact_math=int(exact))
+    orig = G.dump(lgpu.DUMP_ORIG)
+    assert np.array_equal(np.sort(orig), np.arange(n))
+    # keys and sort order: bit-exact
+    assert np.array_equal(G.dump(lgpu.DUMP_KEYS), P.keys[orig]), "cell keys"
+    assert np.array_equal(G.dump(lgpu.DUMP_PERM), orig)
+    keys = G.dump(lgpu.DUMP_KEYS)
+    assert np.all(np.diff(keys) >= 0), "storage sorted by cell"
+    same = np.diff(keys) == 0
+    assert np.all(np.diff(orig)[same] > 0), "stable: ascending reference slot inside a cell"
+    if check_lists:
+        # neighbour lists: bit-exact, list order included (sand slots mapped back to reference slots)
+        goff, gflat = G.neighbors()
+        poff, pflat = P.neighbors()
+        gmap = np.where(gflat < n, orig[np.minimum(gflat, n - 1)], gflat)
+        assert np.array_equal(goff[1:] - goff[:-1], (poff[1:] - poff[:-1])[orig]), "neighbour counts"
+        order = np.concatenate([np.arange(poff[o], poff[o + 1]) for o in orig]) if n else np.zeros(0, np.int64)
+        assert np.array_equal(gmap, pflat[order]), "neighbour lists (order included)"
+    close(G.dump(lgpu.DUMP_DENSITY), P.densities[orig], "density")
+    close(G.dump(lgpu.DUMP_LAMBDA), P.lambdas[orig], "lambda", atol=1e-7)
+    pos, vel, _ = G.download()
+    close(pos, P.positions, "position")
+    close(vel, P.velocities, "velocity", atol=1e-3)  # v = dx/dt amplifies the position tolerance by 1/dt
+
+
+@pytest.mark.parametrize("n_side,with_solids", [(12, False), (20, True), (40, False)])
+def test_fluid_teacher_forced(n_side, with_solids):
+    domain, sand = scenes.dam_break(n_side)
+    solids = scenes.floor_plate(min(3 * n_side, 40), min(2 * n_side, 30)) if with_solids else None
+    P, G = make_pair(domain, sand, solids)
+    for step in range(4):
+        print("substep", step)
+        compare_fluid_substep(P, G, iterations=1, literal=True, exact=True)
+    c = G.dump(lgpu.DUMP_COUNTERS)
+    assert c[0] == 0 and P.s.violations == 0
+    G.close(); P.close()
+
+
+@pytest.mark.parametrize("iterations,literal,exact", [(4, False, True), (4, True, True), (1, True, False), (4, False, False)])
+def test_fluid_modes(iterations, literal, exact):
+    domain, sand = scenes.dam_break(16)
+    P, G = make_pair(domain, sand, scenes.floor_plate(30, 20))
+    for step in range(3):
+        print("substep", step)
+        compare_fluid_substep(P, G, iterations, literal, exact)
+    G.close(); P.close()
+
+
+def test_fluid_table_overflow_falls_back_to_walk():
+    domain, sand = scenes.dam_break(12)
+    P, G = make_pair(domain, sand, max_neighbors=6)
+    for step in range(2):
+        compare_fluid_substep(P, G, 2, True, True)
+    assert G.dump(lgpu.DUMP_COUNTERS)[1] > 0, "the narrow table must have overflowed"
+    G.close(); P.close()
+
+
+def test_fluid_free_running_horizon():
+    # 10 free-running substeps (no teacher forcing), K=1 literal vs the Jacobi oracle
+    domain, sand = scenes.dam_break(20)
+    P, G = make_pair(domain, sand)
+    for step in range(10):
+        P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
+        G.step_fluid(dt=0.01, iterations=1, literal_lambda_index=1, exact_math=1)
+    pos, vel, _ = G.download()
+    d = np.abs(pos - P.positions)
+    print("  horizon 10: max|dx| %.3e mean|dx| %.3e" % (d.max(), d.mean()))
+    assert d.mean() <= 1e-3 * 1.0  # 1e-3 * diameter
+    # neighbour sets of the last grid build
+    orig = G.dump(lgpu.DUMP_ORIG)
+    goff, gflat = G.neighbors()
+    poff, pflat = P.neighbors()
+    n = P.n
+    gmap = np.where(gflat < n, orig[np.minimum(gflat, n - 1)], gflat)
+    gi = np.repeat(orig, np.diff(goff))
+    pi = np.repeat(np.arange(n), np.diff(poff))
+    gset = set(zip(gi.tolist(), gmap.tolist()))
+    pset = set(zip(pi.tolist(), pflat.tolist()))
+    jac = len(gset & pset) / max(len(gset | pset), 1)
+    print("  neighbour-set Jaccard %.6f" % jac)
+    assert jac >= 0.999
+    G.close(); P.close()
+
+
+# ----------------------------------------------------------------------------------------------
+def compare_sand_substep(P, G, iterations, exact, credits=False, dt=0.016, player=None, attract=False, blow=False):
+    n = P.n
+    force_state(P, G)
+    prev = P.s.prev_attract_flag
+    if player is not None:
+        for a in range(3):
+            P.s.player_position[a] = float(player[a])
+    P.s.attract_flag, P.s.blow_flag = int(attract), int(blow)
+    before_pos = P.positions.copy()
+    P.L.lo_step_sand(P.p, dt, iterations, int(credits))
+    kw = dict(dt=dt, iterations=iterations, exact_math=int(exact), credits=int(credits), attract_flag=int(attract),
+              blow_flag=int(blow), prev_attract_flag=int(prev))
+    if credits:
+        kw.update(mu_s=0.8, mu_k=0.7)
+    if player is not None:
+        kw["player_position"] = player
+    G.step_sand(**kw)
+    # sort permutation: bit-exact against Sorting::counting_sort
+    assert np.array_equal(G.dump(lgpu.DUMP_PERM), P.sorted_index), "sort permutation"
+    assert np.array_equal(G.dump(lgpu.DUMP_KEYS), P.keys), "cell keys"
+    assert np.array_equal(G.dump(lgpu.DUMP_ORIG), np.arange(n))
+    # neighbour lists: the oracle keeps the reference's two self entries (F7); the device drops them
+    goff, gflat = G.neighbors()
+    poff, pflat = P.neighbors()
+    owner = np.repeat(np.arange(n), np.diff(poff))
+    keep = pflat != owner
+    pcount = np.bincount(owner[keep], minlength=n)
+    assert np.array_equal(np.diff(goff), pcount), "neighbour counts"
+    assert np.array_equal(gflat, pflat[keep]), "neighbour lists (order included)"
+    pos, vel, flags = G.download()
+    close(pos, P.positions, "position")
+    close(vel, P.velocities, "velocity", atol=1e-3)
+    assert np.array_equal(flags, P.attracted), "attracted flags"
+    return before_pos
+
+
+@pytest.mark.parametrize("n_side", [8, 16])
+def test_sand_teacher_forced(n_side):
+    domain, sand, solids = scenes.sand_pile(n_side)
+    P, G = make_pair(domain, sand, solids)
+    for step in range(6):
+        print("step", step)
+        compare_sand_substep(P, G, 4, True)
+    assert G.dump(lgpu.DUMP_COUNTERS)[0] == 0
+    G.close(); P.close()
+
+
+@pytest.mark.parametrize("iterations,exact", [(1, True), (2, True), (3, True), (4, False)])
+def test_sand_iterations_and_fast_math(iterations, exact):
+    domain, sand, solids = scenes.sand_pile(12, drop=1.0)
+    P, G = make_pair(domain, sand, solids)
+    for step in range(4):
+        print("step", step)
+        compare_sand_substep(P, G, iterations, exact)
+    G.close(); P.close()
+
+
+def test_sand_attract_blow_and_credits():
+    domain, sand, solids = scenes.sand_pile(10, drop=1.0)
+    player = (15.0, 4.0, 15.0)
+    P, G = make_pair(domain, sand, solids)
+    P.s.attract_radius, P.s.blow_radius = 6.0, 5.0
+    schedule = [(False, False), (True, False), (True, False), (False, False), (False, True), (False, False)]
+    for step, (att, blow) in enumerate(schedule):
+        print("step", step, att, blow)
+        force_state(P, G)
+        prev = P.s.prev_attract_flag
+        for a in range(3):
+            P.s.player_position[a] = player[a]
+        P.s.attract_flag, P.s.blow_flag = int(att), int(blow)
+        P.L.lo_step_sand(P.p, 0.016, 4, 0)
+        G.step_sand(dt=0.016, iterations=4, exact_math=1, attract_flag=int(att), blow_flag=int(blow),
+                    prev_attract_flag=int(prev), player_position=player, attract_radius=6.0, blow_radius=5.0)
+        pos, vel, flags = G.download()
+        close(pos, P.positions, "position")
+        close(vel, P.velocities, "velocity", atol=1e-3)
+        assert np.array_equal(flags, P.attracted)
+        if att:
+            assert flags.sum() > 0, "somebody must be attracted in this scene"
+    G.close(); P.close()
+    # credits: bit 1 = no gravity until first contact/attraction/blow (src/Simulate.cpp:362-364,463-470)
+    P, G = make_pair(domain, sand, solids)
+    flags0 = np.full(len(sand), 2, np.int32)
+    P.set_sand(sand, None, flags0)
+    for step in range(4):
+        print("credits step", step)
+        compare_sand_substep(P, G, 4, True, credits=True)
+    G.close(); P.close()
+
+
+def test_sand_free_running_horizon():
+    domain, sand, solids = scenes.sand_pile(14, drop=2.0)
+    P, G = make_pair(domain, sand, solids)
+    for step in range(10):
+        P.L.lo_step_sand(P.p, 0.016, 4, 0)
+        G.step_sand(dt=0.016, iterations=4, exact_math=1)
+    pos, vel, _ = G.download()
+    d = np.abs(pos - P.positions)
+    print("  horizon 10: max|dx| %.3e mean|dx| %.3e bit-exact %.4f" % (d.max(), d.mean(), (pos == P.positions).mean()))
+    assert d.mean() <= 1e-3
+    G.close(); P.close()
+
+
+# ----------------------------------------------------------------------------------------------
+def test_edge_cases():
+    # empty, single particle, ragged block, particles on the domain faces, coincident particles
+    with lgpu.Context((20, 20, 20), capacity_sand=16) as G:
+        G.upload_sand(np.zeros((0, 3), np.float32))
+        G.step_fluid(dt=0.01)
+        G.step_sand()
+        assert G.download()[0].shape == (0, 3)
+    for mode in ("fluid", "sand"):
+        pts = np.array([[10.0, 10.0, 10.0]], np.float32)
+        P, G = make_pair((20, 20, 20), pts)
+        if mode == "fluid":
+            compare_fluid_substep(P, G, 1, True, True)
+        else:
+            compare_sand_substep(P, G, 4, True)
+        G.close(); P.close()
+    ragged = scenes.lattice(7, 3, 11, origin=(0.5, 0.5, 0.5))
+    corners = np.array([[0.5, 0.5, 0.5], [19.5, 19.5, 19.5], [0.5, 19.5, 0.5], [19.4, 0.6, 19.4]], np.float32)
+    coincident = np.array([[5.0, 9.0, 5.0], [5.0, 9.0, 5.0], [5.0, 9.0, 5.0]], np.float32)
+    pts = np.concatenate([ragged, corners, coincident]).astype(np.float32)
+    for mode in ("fluid", "sand"):
+        P, G = make_pair((20, 20, 20), pts)
+        for step in range(3):
+            if mode == "fluid":
+                compare_fluid_substep(P, G, 1, True, True)
+            else:
+                compare_sand_substep(P, G, 4, True)
+        G.close(); P.close()
+
+
+def test_against_compiled_reference_if_present():
+    """Same comparison straight against the unmodified reference (oracle/_ref, built where
+    /root/reference exists and shipped to the GPU box as a binary)."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    domain, sand = scenes.dam_break(14)
+    solids = scenes.floor_plate(20, 20)
+    # fluid: keys / lists / lambdas vs the literal reference, positions vs O-jac
+    R = O.RefSim(*domain, n_sand=len(sand), n_solid=len(solids))
+    R.set_sand(sand); R.set_solid(solids)
+    R.set_fun(R.FLUID_JACOBI, 1, True)
+    with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
+        G.upload_sand(sand); G.upload_solids(solids)
+        for step in range(3):
+            rp, _, rv, ra = R.get_sand()
+            G.upload_sand(rp, rv, ra)
+            R.step(0.01)
+            G.step_fluid(dt=0.01, iterations=1, literal_lambda_index=1, exact_math=1)
+            orig = G.dump(lgpu.DUMP_ORIG)
+            close(G.dump(lgpu.DUMP_LAMBDA), R.lambdas()[orig], "lambda", atol=1e-7)
+            roff, rflat = R.neighbors()
+            goff, gflat = G.neighbors()
+            n = len(sand)
+            gmap = np.where(gflat < n, orig[np.minimum(gflat, n - 1)], gflat)
+            order = np.concatenate([np.arange(roff[o], roff[o + 1]) for o in orig])
+            assert np.array_equal(gmap, rflat[order])
+            rp, _, rv, _ = R.get_sand()
+            pos, vel, _ = G.download()
+            close(pos, rp, "position")
+    R.close()
+    # sand vs the unmodified simulate_sand
+    domain, sand, solids = scenes.sand_pile(10, drop=1.0)
+    R = O.RefSim(*domain, n_sand=len(sand), n_solid=len(solids))
+    R.set_sand(sand); R.set_solid(solids)
+    R.set_fun(R.SAND)
+    with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
+        G.upload_solids(solids)
+        for step in range(4):
+            rp, _, rv, ra = R.get_sand()
+            G.upload_sand(rp, rv, ra)
+            R.step(0.016)
+            G.step_sand(dt=0.016, iterations=4, exact_math=1)
+            assert np.array_equal(G.dump(lgpu.DUMP_KEYS), R.sorted_cell_ids())
+            rp, _, rv, _ = R.get_sand()
+            pos, vel, _ = G.download()
+            close(pos, rp, "position")
+            close(vel, rv, "velocity", atol=1e-3)
+    R.close()
