@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the Lustrine particle step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one substep (predict + grid build + `iterations` solver iterations + commit) of the
+synthetic scene named in config.workload.  Prints ONE JSON line (rank 0).
+
+  value     whole-job particle-substeps/s with the state resident in HBM, timed on the device with
+            CUDA events around every substep (max over ranks), L2 flushed between substeps.
+  e2e       the same metric through the drop-in boundary with HOST buffers: per step the
+            positions/velocities/flags are copied host->device from pinned memory, the substep runs,
+            and the new positions/velocities/flags are copied device->host (what
+            Lustrine::Simulation::simulate_fun does when the caller owns the arrays).
+  roofline  achieved algorithmic HBM bytes/s of the dominant kernel vs MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own CPU step (oracle/_ref, unmodified sources, Release flags) timed on
+            this box's host cores on a bounded sample (rank 0, N=1 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+# algorithmic bytes per particle-substep (SURVEY §8d / DESIGN.md §Roofline)
+def fluid_bytes_per_particle(K, cells_per_particle):
+    return 116 + 44 * K + (12 + 8 * K) * cells_per_particle
+
+def sand_bytes_per_particle(K, cells_per_particle):
+    return 48 + 60 + 36 * K + 24 + (12 + 8 * K) * cells_per_particle
+
+# per-kernel algorithmic bytes per particle
+KERNEL_BYTES = {"fluid_lambda": 16.0, "fluid_deltap": 28.0, "sand_iteration": 36.0}
+
+WORKLOADS = {
+    # name: (kind, cube side, iterations, dt)
+    "dam_break_1m": ("fluid", 100, 4, 0.01),    # BASELINE.json configs[1]
+    "dam_break_64k": ("fluid", 40, 4, 0.01),
+    "dam_break_2m": ("fluid", 126, 4, 0.01),    # per-GPU load of the 16M weak-scaling config
+    "sand_pile_4m": ("sand", 160, 4, 0.016),    # BASELINE.json configs[2]
+    "sand_pile_262k": ("sand", 64, 4, 0.016),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_scene(kind, side):
+    import scenes
+    if kind == "fluid":
+        domain, sand = scenes.dam_break(side)
+        return domain, sand, None
+    # sand pile: side^3 block dropped on a solid voxel floor with obstacle boxes
+    D = (3 * side, side + side // 2, 3 * side)
+    sand = scenes.lattice(side, side, side, origin=(side + 0.5, 8.5, side + 0.5), jitter=0.05, seed=777)
+    floor = scenes.lattice(3 * side, 2, 3 * side, origin=(0.5, 0.5, 0.5), jitter=0.0)
+    boxes = [scenes.lattice(side // 4, 4, side // 4, origin=(side + 0.5 + k * side // 2, 2.5, side + 0.5 + k * side // 3), jitter=0.0)
+             for k in range(2)]
+    return D, sand, np.concatenate([floor] + boxes).astype(np.float32)
+
+
+def step_kwargs(kind, K, dt, exact):
+    kw = dict(dt=dt, iterations=K, exact_math=int(exact))
+    if kind == "fluid":
+        kw["literal_lambda_index"] = 1
+    return kw
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
+    """Times the reference's own CPU step on a bounded sample of the workload.  Uses the compiled
+    unmodified reference (oracle/_ref/libref_time.so, the reference's Release flags) when present,
+    else the plain-C port.  Single-threaded: the reference has no threading."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    # K=4 fluid: ~2.5e5 particle-substeps/s on one core; sand: ~5e5
+    est = 2.0e5 if kind == "fluid" else 4.5e5
+    n_target = int(est * budget_s / max(steps + warmup, 1))
+    sample_side = int(max(8, min(side, round(n_target ** (1.0 / 3.0)))))
+    domain, sand, solids = make_scene(kind, sample_side)
+    if kind == "sand" and solids is not None and len(solids) > 60000:
+        # one Bullet box per solid voxel is created by the reference's init: keep the floor modest
+        solids = solids[:60000]
+    n = len(sand)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)  # the reference prints banners on stdout
+    try:
+        if O.have_ref("time"):
+            kind_name = "reference"
+            R = O.RefSim(*domain, n_sand=n, n_solid=0 if solids is None else len(solids), which="time")
+            R.set_sand(sand)
+            if solids is not None:
+                R.set_solid(solids)
+            if kind == "fluid":
+                R.set_fun(R.FLUID_JACOBI if K != 1 else R.FLUID, K, True)
+            else:
+                R.set_fun(R.SAND)
+            R.step(dt, warmup)
+            seconds = R.step(dt, steps)
+            R.close()
+        else:
+            kind_name = "port"
+            P = O.PortSim(*domain, capacity=n, n_solid=0 if solids is None else len(solids))
+            P.set_sand(sand)
+            if solids is not None:
+                P.set_solid(solids)
+            def one():
+                if kind == "fluid":
+                    P.L.lo_step_fluid(P.p, dt, K, 1 if K != 1 else 0, 1)
+                else:
+                    P.L.lo_step_sand(P.p, dt, K, 0)
+            for _ in range(warmup):
+                one()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                one()
+            seconds = time.perf_counter() - t0
+            P.close()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+    value = n * steps / seconds
+    sample = ("%s scene, %d^3 = %d particles, %d substeps (%d warm-up), %d solver iterations, dt=%g; %s"
+              % (kind, sample_side, n, steps, warmup, K, dt,
+                 "unmodified reference sources, -O3 -mavx2 -ffast-math -mfma -march=skylake"
+                 + ("; K>1 loop = oracle/ref_harness.cpp simulate_fluid_jacobi over the reference's own neighbour search and kernels" if (kind == "fluid" and K != 1) else "")
+                 if kind_name == "reference" else "plain-C port of the reference, -O2"))
+    return {"value": value, "unit": "particle-substeps/s", "cores": 1, "kind": kind_name, "sample": sample,
+            "seconds": seconds, "host_cores_available": os.cpu_count()}, n, seconds
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--exact", type=int, default=0, help="1 = parity arithmetic (every fp32 op separately rounded)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    workload = args.workload or ("dam_break_1m" if args.gpus == 1 else "dam_break_2m")
+    kind, side, K, dt = WORKLOADS[workload]
+    metric = "particle-substeps/s"
+
+    # ---------------- reference arm: the reference's own CPU step ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, n, seconds = run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s=max(args.cpu_budget * 6.0, 60.0))
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "particle-substeps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * seconds / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "kind": kind, "solver_iterations": K, "dt": dt,
+                           "note": "CPU reference on a bounded sample of the workload: " + cb["sample"]},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- B200 arm ----------------
+    import torch
+    import torch.distributed as dist
+    from lustrine_b200 import lgpu
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the particle step has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    hbm_gbs, peak_src = load_peaks()
+    domain, sand, solids = make_scene(kind, side)
+    n = len(sand)
+    if world > 1:
+        from lustrine_b200 import slabs  # spatial slabs with halo exchange
+        result = slabs.bench(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src)
+        if rank == 0:
+            print(json.dumps(result), flush=True)
+        dist.destroy_process_group()
+        return 0
+
+    G = lgpu.Context(domain, capacity_sand=n, capacity_solid=0 if solids is None else len(solids), device=local_rank)
+    G.upload_sand(sand)
+    if solids is not None:
+        G.upload_solids(solids)
+    kw = step_kwargs(kind, K, dt, args.exact)
+    params = lgpu.default_step_params(**kw)
+    step = G.step_fluid if kind == "fluid" else G.step_sand
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(params)
+    G.sync()
+
+    # timed region: K substeps, each bracketed by CUDA events on the launching stream, L2 flushed
+    # (outside the event bracket) between substeps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = G.launch_count()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(steps):
+        flush_l2()
+        step(params)
+        G.sync()
+        dev_ms += G.last_step_ms(0)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = G.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    ms_per_step = dev_ms / steps
+    value = n / (ms_per_step * 1e-3)
+
+    # back-to-back throughput without the flush (what a game loop sees); reported, not the headline
+    G.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(params)
+    G.sync()
+    pipelined_ms = (time.perf_counter() - t0) * 1e3 / steps
+
+    # per-kernel timing pass (phase timing adds event records, so it is a separate short pass)
+    G.set_phase_timing(True)
+    phase = np.zeros(8)
+    PH = 20
+    for _ in range(PH):
+        flush_l2()
+        step(params)
+        G.sync()
+        for ph in range(8):
+            phase[ph] += G.last_step_ms(ph)
+    phase /= PH
+    G.set_phase_timing(False)
+    counters = G.dump(lgpu.DUMP_COUNTERS)
+
+    cells_per_particle = G.num_cells / n
+    if kind == "fluid":
+        step_bytes = fluid_bytes_per_particle(K, cells_per_particle)
+        cand = {"fluid_lambda": phase[6] / K, "fluid_deltap": phase[7] / K}
+    else:
+        step_bytes = sand_bytes_per_particle(K, cells_per_particle)
+        cand = {"sand_iteration": phase[7] / K}
+    dom = max(cand, key=lambda k: cand[k])
+    dom_ms = cand[dom]
+    dom_bytes = KERNEL_BYTES[dom] * n
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                "note": "sparse stencil: ~%d neighbour interactions per particle per launch are served from L1/L2; "
+                        "the kernel is issue/latency bound, not HBM bound (DESIGN.md §Roofline)" % 19}
+    step_achieved = step_bytes * n / (ms_per_step * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": step_achieved / hbm_gbs,
+                     "algorithmic_bytes_per_particle_substep": step_bytes,
+                     "phases_ms": {"predict_key_hist": phase[1], "scan": phase[2], "scatter_reorder": phase[3],
+                                   "neighbour_table": phase[4], "lambda_total": phase[6], "deltap_or_contact_total": phase[7],
+                                   "sum": float(phase[1:5].sum() + phase[6] + phase[7])}}
+
+    # ---------------- e2e through the C ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        pos_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        vel_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        flg_h = torch.empty((n,), dtype=torch.int32).pin_memory()
+        G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
+        e_steps = min(steps, 50)
+        for _ in range(3):
+            G.upload_from(n, pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
+            step(params)
+            G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            G.upload_from(n, pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
+            step(params)
+            G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        checksum = float(pos_h.double().sum())
+        e2e = {"value": n / (e_ms * 1e-3), "unit": "particle-substeps/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n * 28, "steps": e_steps,
+               "position_checksum": checksum,
+               "path": "lgpu_upload_sand + lgpu_step + lgpu_download_sand on pinned host buffers"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline, _, _ = run_cpu_reference(kind, side, K, dt, steps=3, warmup=1, budget_s=args.cpu_budget)
+
+    line = {"metric": metric, "value": value, "unit": "particle-substeps/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "kind": kind, "particles": n, "solid_particles": 0 if solids is None else len(solids),
+                       "domain": list(domain), "grid_cells": G.num_cells, "solver_iterations": K, "dt": dt,
+                       "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
+                       "literal_lambda_index": 1 if kind == "fluid" else None,
+                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
+                       "timing": "CUDA events on the launching stream around every substep, summed",
+                       "wall_ms_per_step_incl_flush": t_wall * 1e3 / steps, "pipelined_ms_per_step_no_flush": pipelined_ms,
+                       "table_overflows": int(counters[1]), "key_violations": int(counters[0])},
+            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": sampler.result()}
+    print(json.dumps(line), flush=True)
+    G.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -130,8 +130,10 @@ LGPU_API int lgpu_step_fluid(lgpu_ctx* ctx, const lgpu_step_params* p);
 LGPU_API int lgpu_step_sand(lgpu_ctx* ctx, const lgpu_step_params* p);
 LGPU_API int lgpu_sync(lgpu_ctx* ctx);
 
-/* Device time of the last `lgpu_step_*` call (CUDA events on the context's stream), and of
- * its phases: 0 whole step, 1 predict+key, 2 scan, 3 reorder, 4 neighbour table, 5 solver. */
+/* Device time of the last `lgpu_step_*` call (CUDA events on the context's stream).  phase 0 =
+ * the whole step (always available).  With phase timing on, also the sum over the launches of
+ * one kind: 1 predict+key+histogram, 2 cell prefix sum, 3 scatter+stable reorder, 4 neighbour
+ * table, 6 density/lambda kernels, 7 delta-p (fluid) / contact (sand) kernels, 5 = 6 + 7. */
 LGPU_API int lgpu_last_step_ms(lgpu_ctx* ctx, int phase, float* ms);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 LGPU_API long lgpu_launch_count(const lgpu_ctx* ctx);

@@ -104,7 +104,8 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     CUDA_TRY(cudaMemsetAsync(c->lambda_head, 0, sizeof(float) * LGPU_LAMBDA_HEAD, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->nbr_cnt, 0, sizeof(int) * cap, c->stream));
-    for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreate(&c->ev[k]));
+    for (int k = 0; k < 2; k++) CUDA_TRY(cudaEventCreate(&c->ev[k]));
+    for (int k = 0; k < LGPU_MAX_MARKS; k++) CUDA_TRY(cudaEventCreate(&c->ev_pool[k]));
     c->solids_sorted = true;  // no solids yet
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -123,7 +124,8 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->nbr); cudaFree(c->nbr_cnt); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    for (int k = 0; k < 8; k++) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < LGPU_MAX_MARKS; k++) cudaEventDestroy(c->ev_pool[k]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -294,23 +296,21 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
 // ---------------- step drivers ----------------
 static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     int st;
-    const bool pt = c->phase_timing;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    lgpu_mark(c, 1);
     st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
     if (st) return st;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    lgpu_mark(c, 2);
     st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C, true);
     if (st) return st;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, mode == 2);
     if (st) return st;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    lgpu_mark(c, 4);
     st = lgpu_launch_build_table(c, mode == 2);
     if (st) return st;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
+    st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);  // marks 6 / 7 per launch
     if (st) return st;
-    if (pt) CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+    lgpu_mark(c, -1);
     return LGPU_OK;
 }
 
@@ -320,10 +320,11 @@ static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
     if (!c->solids_sorted) { int st = lgpu_sort_solids(c); if (st) return st; }
     c->last_params = *p;
     c->last_mode = mode;
+    c->n_marks = 0;
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     int st = enqueue_step(c, *p, mode);
     if (st) return st;
-    CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     c->grid_valid = true;
     return LGPU_OK;
 }
@@ -332,12 +333,19 @@ extern "C" int lgpu_step_fluid(lgpu_ctx* c, const lgpu_step_params* p) { return 
 extern "C" int lgpu_step_sand(lgpu_ctx* c, const lgpu_step_params* p) { return run_step(c, p, 2); }
 
 extern "C" int lgpu_last_step_ms(lgpu_ctx* c, int phase, float* ms) {
-    if (!c || !ms || phase < 0 || phase > 5) return LGPU_ERR_ARG;
+    if (!c || !ms || phase < 0 || phase > 7) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaEventSynchronize(c->ev[7]));
-    if (phase == 0) { CUDA_TRY(cudaEventElapsedTime(ms, c->ev[0], c->ev[7])); return LGPU_OK; }
-    if (!c->phase_timing) { *ms = 0.0f; return LGPU_OK; }
-    CUDA_TRY(cudaEventElapsedTime(ms, c->ev[phase], c->ev[phase + 1]));
+    CUDA_TRY(cudaEventSynchronize(c->ev[1]));
+    *ms = 0.0f;
+    if (phase == 0) { CUDA_TRY(cudaEventElapsedTime(ms, c->ev[0], c->ev[1])); return LGPU_OK; }
+    for (int k = 0; k + 1 < c->n_marks; k++) {
+        int ph = c->ev_phase[k];
+        if (ph == phase || (phase == 5 && (ph == 6 || ph == 7))) {
+            float t = 0.0f;
+            CUDA_TRY(cudaEventElapsedTime(&t, c->ev_pool[k], c->ev_pool[k + 1]));
+            *ms += t;
+        }
+    }
     return LGPU_OK;
 }
 

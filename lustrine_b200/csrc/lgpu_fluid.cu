@@ -177,7 +177,9 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
     float4* bufs[2] = {c->pa, c->pb};
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
+        lgpu_mark(c, 6);
         k_fluid_lambda<P, POLY6><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur);
+        lgpu_mark(c, 7);
         if (it == iterations - 1) k_fluid_deltap<P, POLY6, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur, next);
         else k_fluid_deltap<P, POLY6, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur, next);
         c->launches += 2;

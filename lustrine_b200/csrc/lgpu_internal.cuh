@@ -10,6 +10,7 @@
 #define LGPU_DEFAULT_MAX_NEIGHBORS 32
 #define LGPU_LAMBDA_HEAD 4096  // lambdas[loop counter] table: first slots in reference order
 #define LGPU_BLOCK 128
+#define LGPU_MAX_MARKS 96
 
 // ---------------------------------------------------------------------------------------
 // Device-side view of a context.  Passed BY VALUE to every kernel (lives in the constant
@@ -77,9 +78,11 @@ struct lgpu_ctx {
     float *h_stage, *d_stage;
     size_t stage_bytes;
     // timing
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[2];          // whole-step bracket (always recorded)
+    cudaEvent_t ev_pool[LGPU_MAX_MARKS];  // per-launch marks (only with phase timing on)
+    int ev_phase[LGPU_MAX_MARKS];
+    int n_marks;
     bool phase_timing;
-    float phase_ms[6];
     long launches;
     // graphs
     bool use_graph;
@@ -103,6 +106,15 @@ void lgpu_set_error(const char* fmt, ...);
 static inline int lgpu_blocks(long n, int block = LGPU_BLOCK) { return (int)((n + block - 1) / block); }
 
 View lgpu_make_view(lgpu_ctx* c);
+
+// Phase ids of lgpu_last_step_ms: 1 predict+key+histogram, 2 scan, 3 scatter+reorder, 4 neighbour
+// table, 6 density/lambda kernels, 7 delta-p (fluid) or contact (sand) kernels; 5 = 6 + 7; 0 = whole step.
+static inline void lgpu_mark(lgpu_ctx* c, int phase) {
+    if (!c->phase_timing || c->n_marks >= LGPU_MAX_MARKS) return;
+    cudaEventRecord(c->ev_pool[c->n_marks], c->stream);
+    c->ev_phase[c->n_marks] = phase;
+    c->n_marks++;
+}
 
 // ---- launch wrappers, one per translation unit ----
 int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p);

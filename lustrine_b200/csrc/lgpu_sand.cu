@@ -142,6 +142,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
+        lgpu_mark(c, 7);
         if (p.exact_math) {
             if (last) k_sand_iteration<Exact, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
             else k_sand_iteration<Exact, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);

@@ -89,12 +89,25 @@ def test_kernel_tables():
             spacing = np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32))
             return float((np.abs(a.astype(np.float64) - b) / np.maximum(spacing, np.float32(1e-45))).max())
 
-        for name, which, ref, arg, tol in (("W", 0, W, r, 0), ("gradW", 1, gW, d, 0), ("poly6", 2, p6, r, 4),
-                                           ("spiky", 3, sp, d, 4), ("s_coor", 4, sc, r, 4)):
+        # On the hot path neighbours are cut at r <= h, i.e. q <= 0.5: that branch of W and
+        # the whole of gradW contain no libm call and must be bit-exact.  The outer branch of W
+        # (std::pow(1-q, 3.0f)), poly6/spiky (std::pow in double) and s_coor (powf) go through libm,
+        # where the device's pow may round differently: <= 4 ulp.
+        inner = r <= h
+        got = G.eval_kernel(0, r, exact=True)
+        print("  W      exact: inner %.1f ulp (tolerance 0), outer %.1f ulp (tolerance 4)" % (ulps(got[inner], W[inner]), ulps(got[~inner], W[~inner])))
+        assert np.array_equal(got[inner], W[inner]) and ulps(got[~inner], W[~inner]) <= 4
+        for name, which, ref, arg, tol in (("gradW", 1, gW, d, 0), ("poly6", 2, p6, r, 4), ("spiky", 3, sp, d, 4)):
             got = G.eval_kernel(which, arg, exact=True)
             u = ulps(got, ref)
-            print("  %-6s exact: %.1f ulp (tolerance %d)" % (name, u, tol))
+            print("  %-6s exact: %.1f ulp (tolerance %d), bit-exact fraction %.4f" % (name, u, tol, (got == ref).mean()))
             assert u <= tol, name
+        # s_coor = -k (W(r)/W(dq))^4: powf on the hot path (<= 4 ulp); beyond r > h the 1-ulp
+        # difference of W's outer branch is amplified by the 4th power (<= 16 ulp, off the hot path)
+        got = G.eval_kernel(4, r, exact=True)
+        print("  s_coor exact: inner %.1f ulp (tolerance 4), outer %.1f ulp (tolerance 16), bit-exact fraction %.4f"
+              % (ulps(got[inner], sc[inner]), ulps(got[~inner], sc[~inner]), (got == sc).mean()))
+        assert ulps(got[inner], sc[inner]) <= 4 and ulps(got[~inner], sc[~inner]) <= 16
         for name, which, ref, arg in (("W", 0, W, r), ("gradW", 1, gW, d), ("s_coor", 4, sc, r)):
             got = G.eval_kernel(which, arg, exact=False)
             scale = np.abs(ref).max()
