@@ -1,0 +1,169 @@
+"""CPU tests (-m "not gpu"): the oracle port against the committed golden vectors (outputs of the
+unmodified reference, tests/golden/make_golden.py) and, where oracle/_ref is built, against the
+compiled reference itself.  Everything is required to be BIT-identical: the port restates the
+reference's fp32 operation order and is compiled with -O2 -ffp-contract=off like oracle/_ref."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import scenes
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_counting_sort_golden_and_known_answer():
+    g = gold("counting_sort.npz")
+    got = O.counting_sort_port(g["keys"], 1987)
+    assert np.array_equal(got, g["sorted"])
+    assert np.array_equal(got, np.argsort(g["keys"], kind="stable"))
+    assert np.array_equal(g["keys"][got], np.sort(g["keys"]))  # the reference's own check (unit_tests/main.cpp:80-88)
+
+
+def test_kernel_tables_golden():
+    g = gold("kernel_tables.npz")
+    P = O.PortSim(60, 40, 40, capacity=1)
+    assert np.array_equal(np.array([P.s.kernelRadius, P.s.cell_size, P.s.cubic_kernel_k, P.s.cubic_kernel_l], np.float32), g["consts"])
+    assert [P.s.gridX, P.s.gridY, P.s.gridZ, P.s.num_grid_cells] == list(g["grid"])
+    r, d = g["r"], g["d"]
+    W = np.array([P.L.lo_cubic_kernel(P.p, float(x)) for x in r], np.float32)
+    p6 = np.array([P.L.lo_poly6_kernel(P.p, float(x)) for x in r], np.float32)
+    sc = np.array([P.L.lo_s_coor(P.p, float(x)) for x in r], np.float32)
+    gW = np.zeros_like(d); sp = np.zeros_like(d)
+    for i in range(len(d)):
+        P.L.lo_cubic_kernel_grad(P.p, d[i].ctypes.data, gW[i].ctypes.data)
+        P.L.lo_spiky_kernel(P.p, d[i].ctypes.data, sp[i].ctypes.data)
+    for name, got in (("W", W), ("poly6", p6), ("s_coor", sc), ("gradW", gW), ("spiky", sp)):
+        assert np.array_equal(got, g[name]), name
+    P.close()
+
+
+@pytest.mark.parametrize("name,jacobi", [("fluid_literal_8.npz", 0), ("fluid_jacobi_8.npz", 1)])
+def test_fluid_golden(name, jacobi):
+    g = gold(name)
+    P = O.PortSim(*[int(x) for x in g["domain"]], capacity=len(g["sand"]), n_solid=len(g["solids"]))
+    P.set_sand(g["sand"]); P.set_solid(g["solids"])
+    for s in range(3):
+        P.L.lo_step_fluid(P.p, 0.01, 1, jacobi, 1)
+        off, flat = P.neighbors()
+        assert np.array_equal(P.keys, g["keys_%d" % s])
+        assert np.array_equal(off, g["nbr_off_%d" % s]) and np.array_equal(flat, g["nbr_%d" % s])
+        assert np.array_equal(P.lambdas, g["lambda_%d" % s])
+        assert np.array_equal(P.positions, g["pos_%d" % s]) and np.array_equal(P.velocities, g["vel_%d" % s])
+    P.close()
+
+
+def test_sand_golden():
+    g = gold("sand_8.npz")
+    P = O.PortSim(*[int(x) for x in g["domain"]], capacity=len(g["sand"]), n_solid=len(g["solids"]))
+    P.set_sand(g["sand"]); P.set_solid(g["solids"])
+    for s in range(3):
+        P.L.lo_step_sand(P.p, 0.016, 4, 0)
+        off, flat = P.neighbors()
+        assert np.array_equal(P.keys, g["keys_%d" % s])
+        assert np.array_equal(off, g["nbr_off_%d" % s]) and np.array_equal(flat, g["nbr_%d" % s])
+        assert np.array_equal(P.positions, g["pos_%d" % s]) and np.array_equal(P.velocities, g["vel_%d" % s])
+    P.close()
+
+
+def test_jacobi_vs_gauss_seidel_divergence_is_as_surveyed():
+    # the literal reference is sequential Gauss-Seidel; Jacobi differs by ~1e-3 per substep.
+    a, b = gold("fluid_literal_8.npz"), gold("fluid_jacobi_8.npz")
+    d = np.abs(a["pos_0"] - b["pos_0"]).max()
+    assert 1e-6 < d < 5e-2
+    assert np.array_equal(a["lambda_0"], b["lambda_0"])  # the density/lambda pass is pure
+
+
+def test_edge_cases_port():
+    # empty, single particle, out-of-grid key is clamped and counted (undefined behaviour in the reference, F10)
+    P = O.PortSim(20, 20, 20, capacity=8)
+    P.set_sand(np.zeros((0, 3), np.float32))
+    P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
+    P.L.lo_step_sand(P.p, 0.016, 4, 0)
+    P.set_sand(np.array([[10, 10, 10]], np.float32))
+    P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
+    off, flat = P.neighbors()
+    assert list(off) == [0, 1] and list(flat) == [0]  # fluid lists contain self once (F7)
+    P.L.lo_step_sand(P.p, 0.016, 4, 0)
+    off, flat = P.neighbors()
+    assert list(flat) == [0, 0]  # sand lists contain self twice (F7)
+    P.set_sand(np.array([[10, -100, 10]], np.float32))
+    P.L.lo_find_neighbors_v0(P.p)
+    assert P.s.violations == 1
+    P.close()
+
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", ["fluid_lit", "fluid_jac", "fluid_jac4_fixed", "sand", "credits"])
+def test_port_vs_compiled_reference(mode):
+    n_side = 12
+    if mode in ("sand", "credits"):
+        domain, sand, solids = scenes.sand_pile(n_side, drop=1.0)
+    else:
+        domain, sand = scenes.dam_break(n_side)
+        solids = scenes.floor_plate(20, 20)
+    R = O.RefSim(*domain, n_sand=len(sand), n_solid=len(solids))
+    P = O.PortSim(*domain, capacity=len(sand), n_solid=len(solids))
+    flags = np.full(len(sand), 2, np.int32) if mode == "credits" else None
+    R.set_sand(sand, None, flags); R.set_solid(solids)
+    P.set_sand(sand, None, flags); P.set_solid(solids)
+    for step in range(4):
+        if mode == "fluid_lit":
+            R.set_fun(R.FLUID); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 1, 0, 1)
+        elif mode == "fluid_jac":
+            R.set_fun(R.FLUID_JACOBI, 1, True); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
+        elif mode == "fluid_jac4_fixed":
+            R.set_fun(R.FLUID_JACOBI, 4, False); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 4, 1, 0)
+        elif mode == "sand":
+            R.set_fun(R.SAND); R.step(0.016); P.L.lo_step_sand(P.p, 0.016, 4, 0)
+        else:
+            R.set_fun(R.SAND_CREDITS); R.step(0.016); P.L.lo_step_sand(P.p, 0.016, 4, 1)
+        rp, rs, rv, ra = R.get_sand()
+        ro, rf = R.neighbors(); po, pf = P.neighbors()
+        assert np.array_equal(ro, po) and np.array_equal(rf, pf), "neighbour lists"
+        if mode.startswith("fluid"):
+            assert np.array_equal(R.lambdas(), P.lambdas)
+        else:
+            assert np.array_equal(R.sorted_cell_ids(), P.keys)
+        assert np.array_equal(rp, P.positions) and np.array_equal(rv, P.velocities)
+        assert np.array_equal(ra, P.attracted)
+    R.close(); P.close()
+
+
+@needs_ref
+def test_port_vs_reference_attract_blow():
+    domain, sand, solids = scenes.sand_pile(8, drop=1.0)
+    player = np.array([12.0, 4.0, 12.0], np.float32)
+    R = O.RefSim(*domain, n_sand=len(sand), n_solid=len(solids))
+    P = O.PortSim(*domain, capacity=len(sand), n_solid=len(solids))
+    R.set_sand(sand); R.set_solid(solids); P.set_sand(sand); P.set_solid(solids)
+    R.set_fun(R.SAND)
+    R.set_player(player, False, False, 6.0, 5.0, 1000.0, 500.0)
+    P.s.attract_radius, P.s.blow_radius = 6.0, 5.0
+    for a in range(3):
+        P.s.player_position[a] = float(player[a])
+    for att, blow in [(False, False), (True, False), (True, False), (False, False), (False, True), (False, False)]:
+        R.set_player(None, att, blow, 6.0, 5.0, 1000.0, 500.0)
+        P.s.attract_flag, P.s.blow_flag = int(att), int(blow)
+        R.step(0.016)
+        P.L.lo_step_sand(P.p, 0.016, 4, 0)
+        rp, _, rv, ra = R.get_sand()
+        assert np.allclose(R.player_position, player)
+        assert np.array_equal(ra, P.attracted)
+        assert np.array_equal(rp, P.positions) and np.array_equal(rv, P.velocities)
+    R.close(); P.close()
+
+
+@needs_ref
+def test_counting_sort_vs_reference():
+    rng = np.random.default_rng(7)
+    keys = rng.integers(0, 5000, 50000).astype(np.int32)
+    assert np.array_equal(O.counting_sort_ref(keys, 5000), O.counting_sort_port(keys, 5000))
