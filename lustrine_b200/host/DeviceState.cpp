@@ -1,0 +1,132 @@
+// DeviceState.cpp — glue between the Lustrine::Simulation host struct and the lgpu C ABI.
+#include "DeviceState.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "lustrine/Profiling.hpp"
+
+namespace Lustrine {
+namespace B200 {
+
+namespace {
+void die(const char* what, int status) {
+    // The particle step has no CPU fallback: a failing device call is fatal and loud.
+    std::cerr << "lustrine_b200: " << what << " failed (status " << status << "): " << lgpu_last_error() << std::endl;
+    std::abort();
+}
+#define LGPU_MUST(call) do { int _s = (call); if (_s != LGPU_OK) die(#call, _s); } while (0)
+}  // namespace
+
+DeviceState* DeviceState::create(Simulation* s, float kernel_radius_scale) {
+    DeviceState* d = new DeviceState();
+    lgpu_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.domain[0] = s->parameters_copy.X; cfg.domain[1] = s->parameters_copy.Y; cfg.domain[2] = s->parameters_copy.Z;
+    cfg.particle_radius = s->parameters_copy.particleRadius;
+    cfg.particle_diameter = s->parameters_copy.particleDiameter;
+    cfg.kernel_radius_scale = kernel_radius_scale;
+    // every slot below the solid tail can become sand through the particle sources (src/Lustrine.cpp:237-239)
+    cfg.capacity_sand = s->ptr_solid_ordered_end + 1 > 0 ? s->ptr_solid_ordered_end + 1 : 1;
+    const char* cap_env = std::getenv("LUSTRINE_B200_MAX_SAND");
+    if (cap_env) {
+        int cap = std::atoi(cap_env);
+        if (cap >= s->num_sand_particles && cap < cfg.capacity_sand) cfg.capacity_sand = cap;
+    }
+    cfg.capacity_solid = s->num_solid_particles;
+    cfg.device = -1;
+    LGPU_MUST(lgpu_create(&cfg, &d->ctx));
+    lgpu_grid_info gi;
+    LGPU_MUST(lgpu_get_grid(d->ctx, &gi));
+    if (gi.grid[0] != s->gridX || gi.grid[1] != s->gridY || gi.grid[2] != s->gridZ || gi.kernel_radius != s->kernelRadius ||
+        gi.cubic_k != s->cubic_kernel_k || gi.cubic_l != s->cubic_kernel_l) {
+        std::cerr << "lustrine_b200: device grid constants differ from the host's" << std::endl;
+        std::abort();
+    }
+    if (s->num_solid_particles > 0)
+        LGPU_MUST(lgpu_upload_solids(d->ctx, s->num_solid_particles, reinterpret_cast<const float*>(s->positions + s->ptr_solid_start)));
+    d->upload(s);
+    return d;
+}
+
+void DeviceState::destroy(DeviceState* d) {
+    if (!d) return;
+    lgpu_destroy(d->ctx);
+    delete d;
+}
+
+void DeviceState::upload(Simulation* s) {
+    const int n = s->ptr_sand_end - s->ptr_sand_start;
+    LGPU_MUST(lgpu_upload_sand(ctx, n, reinterpret_cast<const float*>(s->positions + s->ptr_sand_start),
+                               reinterpret_cast<const float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
+    device_sand = n;
+}
+
+void DeviceState::download(Simulation* s) {
+    LGPU_MUST(lgpu_download_sand(ctx, reinterpret_cast<float*>(s->positions + s->ptr_sand_start),
+                                 reinterpret_cast<float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
+    // the reference leaves positions_star == positions after a step (src/Simulate.cpp:111,318)
+    std::memcpy(s->positions_star + s->ptr_sand_start, s->positions + s->ptr_sand_start, sizeof(glm::vec3) * (size_t)lgpu_num_sand(ctx));
+}
+
+void DeviceState::download_positions_into(float* dst) { LGPU_MUST(lgpu_download_sand(ctx, dst, nullptr, nullptr)); }
+
+void DeviceState::append_from_host(Simulation* s, int first, int count) {
+    if (sync_mode == SYNC_FULL) return;  // the next step uploads everything anyway
+    LGPU_MUST(lgpu_append_sand(ctx, count, reinterpret_cast<const float*>(s->positions + first),
+                               reinterpret_cast<const float*>(s->velocities + first), s->attracted + first));
+    device_sand += count;
+}
+
+int DeviceState::remove_in_cells(Simulation* s, const std::vector<int>& cells) {
+    int removed = 0;
+    LGPU_MUST(lgpu_remove_in_cells(ctx, cells.data(), (int)cells.size(), &removed));
+    device_sand -= removed;
+    if (removed > 0 && sync_mode != SYNC_LAZY) download(s);
+    return removed;
+}
+
+int DeviceState::cell_count(const int lo[3], const int hi[3], bool include_solid) {
+    int count = 0;
+    LGPU_MUST(lgpu_cell_count(ctx, lo, hi, include_solid ? 1 : 0, &count));
+    return count;
+}
+
+void DeviceState::step(Simulation* s, float dt, int mode) {
+    if (sync_mode == SYNC_FULL) upload(s);
+    lgpu_step_params p;
+    lgpu_default_step_params(&p);
+    p.dt = dt;
+    p.gravity[0] = s->gravity.x; p.gravity[1] = s->gravity.y; p.gravity[2] = s->gravity.z;
+    p.rest_density = s->rest_density; p.mass = s->mass; p.relaxation_epsilon = s->relaxation_epsilon;
+    p.s_corr_dq = s->s_corr_dq; p.s_corr_k = s->s_corr_k; p.s_corr_n = s->s_corr_n;
+    p.exact_math = exact_math ? 1 : 0;
+    p.sph_kernel = (s->W == static_cast<W_fun>(poly6_kernel)) ? 1 : 0;  // which kernel the caller wired
+    if (mode == 1) {
+        p.iterations = fluid_iterations;
+        p.literal_lambda_index = literal_lambda_index ? 1 : 0;
+        LGPU_MUST(lgpu_step_fluid(ctx, &p));
+        s->time_step = dt < 0.001f ? 0.001f : (dt > 0.01f ? 0.01f : dt);  // src/Simulate.cpp:31-32
+    } else {
+        const glm::vec3& pp = s->bullet_physics_simulation.player_position;
+        p.iterations = 4;  // src/Simulate.cpp:226
+        p.player_position[0] = pp.x; p.player_position[1] = pp.y; p.player_position[2] = pp.z;
+        p.attract_flag = s->attract_flag; p.blow_flag = s->blow_flag; p.prev_attract_flag = prev_attract_flag;
+        p.attract_radius = s->attract_radius; p.blow_radius = s->blow_radius;
+        p.attract_coeff = s->attract_coeff; p.blow_coeff = s->blow_coeff;
+        p.credits = mode == 3;
+        if (mode == 3) { p.mu_s = 0.8f; p.mu_k = 0.7f; }  // src/Simulate.cpp:333-334
+        LGPU_MUST(lgpu_step_sand(ctx, &p));
+        s->time_step = dt;  // :168
+        prev_attract_flag = s->attract_flag;  // :323
+        s->first_iteration = false;
+    }
+    if (sync_mode != SYNC_LAZY) download(s);
+    else LGPU_MUST(lgpu_sync(ctx));
+    LGPU_MUST(lgpu_last_step_ms(ctx, 0, &last_ms));
+    Profiling::record(2, last_ms * 1e-3);
+}
+
+}  // namespace B200
+}  // namespace Lustrine

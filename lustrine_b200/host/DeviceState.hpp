@@ -1,0 +1,37 @@
+// DeviceState.hpp — the GPU side of one Lustrine::Simulation: an lgpu context (include/lgpu.h) plus
+// the host<->device synchronisation policy.  Internal to liblustrine_b200.so.
+#pragma once
+
+#include <vector>
+
+#include "lgpu.h"
+#include "lustrine/Lustrine.hpp"
+
+namespace Lustrine {
+namespace B200 {
+
+struct DeviceState {
+    lgpu_ctx* ctx = nullptr;
+    HostSync sync_mode = SYNC_FULL;
+    int fluid_iterations = 1;          // the reference's simulate_fluid does one iteration per call
+    bool literal_lambda_index = true;  // reference behaviour
+    bool exact_math = true;
+    bool prev_attract_flag = false;    // the reference keeps this in a function-local static (src/Simulate.cpp:185)
+    bool host_pinned = false;
+    float last_ms = 0.0f;
+    int device_sand = 0;               // particles resident on the device
+
+    static DeviceState* create(Simulation* s, float kernel_radius_scale);
+    static void destroy(DeviceState* d);
+
+    void upload(Simulation* s);                                  // host arrays -> device (positions, velocities, attracted)
+    void download(Simulation* s);                                // device -> host arrays
+    void download_positions_into(float* dst);
+    void append_from_host(Simulation* s, int first, int count);  // particle sources
+    int remove_in_cells(Simulation* s, const std::vector<int>& cells);
+    int cell_count(const int lo[3], const int hi[3], bool include_solid);
+    void step(Simulation* s, float dt, int mode /*1 fluid, 2 sand, 3 sand_credits*/);
+};
+
+}  // namespace B200
+}  // namespace Lustrine

@@ -1,0 +1,74 @@
+"""Drop-in test of the kept API: the same LustrineWrapper C calls are driven against the reference's
+own compiled library and against liblustrine_b200.so; particle counts, positions and grid queries must
+agree (sand steps in parity arithmetic are bit-identical)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from wrapper_driver import WRAPPER_SYMBOLS, Wrapper
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "lustrine_b200", "lib", "liblustrine_b200.so")
+
+
+def test_wrapper_symbols_exported():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", OURS]).decode()
+    exported = set(re.findall(r" T (\w+)", out))
+    missing = [s for s in WRAPPER_SYMBOLS if s not in exported]
+    assert not missing, "liblustrine_b200.so lacks C entry points of the reference wrapper: %s" % missing
+    assert len(WRAPPER_SYMBOLS) >= 56  # the wrapper entry points + 3 profiling getters
+    hdr = "/root/reference/src/LustrineWrapper.hpp"
+    if os.path.exists(hdr):  # only in the build container
+        ref = set(re.findall(r'^\s*extern "C" LUSTRINE_WRAPPER_EXPORT [\w:]+\s+(\w+)\(', open(hdr).read(), re.M))
+        assert ref <= exported, sorted(ref - exported)
+    for cxx in ("init_simulation", "init_simulation_extra_parameters", "clean_simulation", "init_chunk_from_grid", "init_grid_box",
+                "init_grid_box_random", "init_grid_from_magika_voxel", "add_particle_source", "add_particle_sink",
+                "query_cell_num_particles", "simulate", "simulate_fluid", "simulate_sand", "simulate_sand_credits", "simulate_sand_v3"):
+        assert re.search(r"_ZN8Lustrine\d+%s" % cxx, out), "C++ API function %s not exported" % cxx
+
+
+def run_scenario(w, steps, flags=None, with_source_sink=False):
+    data = w.init((30, 30, 30), 0.5, sand=[((10, 10, 10), (5.0, 8.0, 5.0))],
+                  solids=[((24, 1, 24), (0.0, 0.0, 0.0), 2), ((4, 3, 4), (8.0, 1.0, 8.0), 2)], subdivision=1)
+    trace = {"n0": (data.num_sand_particles, data.num_solid_particles, data.start_solid_index, data.end_solid_index), "pos": [], "n": [], "q": []}
+    if with_source_sink:
+        w.add_source((2, 2, 2), (14.0, 22.0, 14.0), (0.0, -1.0, 0.0), 0.05, 48)
+        w.add_sink((0.0, 0.0, 0.0), (30.0, 2.5, 12.0), 0.0)
+    w.L.set_attract_blow_parameters(12.0, 9.0, 1000.0, 500.0)
+    for s in range(steps):
+        att, blow = flags[s] if flags else (False, False)
+        w.L.simulate(0.016, att, blow)
+        trace["pos"].append(w.positions())
+        trace["n"].append(w.L.get_num_sand_particles())
+        trace["q"].append((w.query((4.0, 0.0, 4.0), (16.0, 12.0, 16.0), False), w.query((0.0, 0.0, 0.0), (30.0, 4.0, 30.0), True)))
+    w.L.cleanup_simulation()
+    return trace
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scenario", ["sand", "attract_blow", "source_sink"])
+def test_wrapper_matches_reference(scenario):
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    steps = 24
+    flags = None
+    if scenario == "attract_blow":
+        flags = [(False, False)] * 4 + [(True, False)] * 6 + [(False, False)] * 4 + [(False, True)] * 4 + [(False, False)] * 6
+    kw = dict(steps=steps, flags=flags, with_source_sink=scenario == "source_sink")
+    ref = run_scenario(Wrapper(O.REF_LIT_SO), **kw)
+    got = run_scenario(Wrapper(OURS), **kw)
+    assert got["n0"] == ref["n0"]
+    assert got["n"] == ref["n"], "particle counts per step"
+    assert got["q"] == ref["q"], "query_cell_num_particles per step"
+    worst = 0.0
+    for a, b in zip(got["pos"], ref["pos"]):
+        assert a.shape == b.shape
+        worst = max(worst, float(np.abs(a - b).max()) if a.size else 0.0)
+    print("  %s: max|dx| over %d steps = %.3e" % (scenario, steps, worst))
+    assert worst <= 1e-5
+    if scenario == "source_sink":
+        assert ref["n"][-1] != ref["n0"][0], "sources/sinks must have changed the particle count"
