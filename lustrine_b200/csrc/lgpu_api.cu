@@ -76,6 +76,7 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     c->cap = cfg->capacity_sand > 0 ? cfg->capacity_sand : 1;
     c->cap_solid = cfg->capacity_solid;
     c->M = cfg->max_neighbors > 0 ? cfg->max_neighbors : LGPU_DEFAULT_MAX_NEIGHBORS;
+    c->M = (c->M + 3) & ~3;  // the table stores groups of four 16-bit codes
     if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 1;
@@ -88,10 +89,11 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap)); CUDA_TRY(dalloc(&c->rank_in, cap));
     CUDA_TRY(dalloc(&c->tmp_id, cap)); CUDA_TRY(dalloc(&c->key, cap));
     CUDA_TRY(dalloc(&c->cell_count, C1)); CUDA_TRY(dalloc(&c->cell_start, C1));
-    CUDA_TRY(dalloc(&c->scan_block_sums, C1 / 4096 + 4));
+    CUDA_TRY(dalloc(&c->scan_state, C1 / 4096 + 4));
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
-    CUDA_TRY(dalloc(&c->nbr, cap * (size_t)c->M)); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
+    CUDA_TRY(dalloc(&c->nbr16, cap * (size_t)(c->M / 4))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
+    CUDA_TRY(dalloc(&c->blk, cap / LGPU_TILE + 2));
     CUDA_TRY(dalloc(&c->lambda, cap)); CUDA_TRY(dalloc(&c->density, cap));
     CUDA_TRY(dalloc(&c->lambda_head, (size_t)LGPU_LAMBDA_HEAD));
     CUDA_TRY(dalloc(&c->counters, (size_t)4));
@@ -119,9 +121,9 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     for (int k = 0; k < 2; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->flags[k]); cudaFree(c->orig[k]); }
     cudaFree(c->pstar_unsorted); cudaFree(c->x0); cudaFree(c->pa); cudaFree(c->pb); cudaFree(c->perm);
     cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
-    cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_block_sums);
+    cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_state);
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
-    cudaFree(c->nbr); cudaFree(c->nbr_cnt); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
+    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->blk); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev[k]);
@@ -141,7 +143,7 @@ View lgpu_make_view(lgpu_ctx* c) {
     v.key_in = c->key_in; v.rank_in = c->rank_in; v.tmp_id = c->tmp_id; v.key = c->key;
     v.cell_count = c->cell_count; v.cell_start = c->cell_start;
     v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
-    v.nbr = c->nbr; v.nbr_cnt = c->nbr_cnt;
+    v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt; v.blk = c->blk;
     v.lambda = c->lambda; v.density = c->density; v.lambda_head = c->lambda_head;
     v.counters = c->counters;
     return v;
@@ -357,12 +359,33 @@ __global__ void k_dump_pstar(const float4* __restrict__ src, int n, float* __res
     dst[3 * i] = a.x; dst[3 * i + 1] = a.y; dst[3 * i + 2] = a.z;
 }
 
+// neighbour lists as the solver passes see them: decoded from the 16-bit table where the row is
+// valid, re-walked otherwise
 template <bool SAND>
-__global__ void k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(LGPU_TILE) k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
+    __shared__ BlkDesc d;
+    int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    if (threadIdx.x < (int)(sizeof(BlkDesc) / sizeof(int))) ((int*)&d)[threadIdx.x] = ((const int*)&v.blk[blockIdx.x])[threadIdx.x];
+    __syncthreads();
     if (i >= v.n_owned) return;
     long t = offsets[i];
-    for_each_neighbor<SAND>(v, i, [&](int j) { flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j]; });
+    const int word = v.nbr_cnt[i];
+    if (!(word & LGPU_CNT_WALK)) {
+        const int cnt = word & LGPU_CNT_MASK;
+        for (int k = 0; k < cnt; k++) {
+            uint2 w = v.nbr16[(size_t)(k >> 2) * v.cap + i];
+            uint32_t pair = (k & 2) ? w.y : w.x;
+            uint32_t code = (k & 1) ? pair >> 16 : pair & 0xffffu;
+            int j = decode_code(d, code);
+            flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j];
+        }
+    } else {
+        walk<SAND>(v, i, f3(v.x0[i]), [&](int j, int) { flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j]; });
+    }
+}
+__global__ void k_dump_cnt(const int* __restrict__ word, int n, int* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = word[i] & LGPU_CNT_MASK;
 }
 
 extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
@@ -376,7 +399,15 @@ extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
         case LGPU_DUMP_KEYS: src = c->key; bytes = sizeof(int) * n; break;
         case LGPU_DUMP_PERM: src = c->perm; bytes = sizeof(int) * n; break;
         case LGPU_DUMP_ORIG: src = c->orig[0]; bytes = sizeof(int) * n; break;
-        case LGPU_DUMP_NBR_COUNT: src = c->nbr_cnt; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_NBR_COUNT: {
+            bytes = sizeof(int) * n;
+            if (out_bytes < bytes) return LGPU_ERR_ARG;
+            if (n == 0) return LGPU_OK;
+            k_dump_cnt<<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(c->nbr_cnt, (int)n, (int*)c->d_stage);
+            CUDA_TRY(cudaMemcpyAsync(out, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            return LGPU_OK;
+        }
         case LGPU_DUMP_DENSITY: src = c->density; bytes = sizeof(float) * n; break;
         case LGPU_DUMP_LAMBDA: src = c->lambda; bytes = sizeof(float) * n; break;
         case LGPU_DUMP_CELL_START: src = c->cell_start; bytes = sizeof(int) * ((size_t)c->g.C + 1); break;
@@ -397,7 +428,7 @@ extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
             CUDA_TRY(cudaMemcpy(cnt.data(), c->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost));
             std::vector<long> off(n + 1);
             off[0] = 0;
-            for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
+            for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + (cnt[i] & LGPU_CNT_MASK);
             bytes = sizeof(int) * (size_t)off[n];
             if (out_bytes < bytes) return LGPU_ERR_ARG;
             if (off[n] == 0) return LGPU_OK;
@@ -406,8 +437,9 @@ extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
             CUDA_TRY(cudaMalloc((void**)&d_flat, bytes));
             CUDA_TRY(cudaMemcpy(d_off, off.data(), sizeof(long) * (n + 1), cudaMemcpyHostToDevice));
             View v = lgpu_make_view(c);
-            if (c->last_mode == 2) k_dump_nbr<true><<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(v, d_off, d_flat);
-            else k_dump_nbr<false><<<lgpu_blocks((long)n), LGPU_BLOCK, 0, c->stream>>>(v, d_off, d_flat);
+            const int nblk = (int)((n + LGPU_TILE - 1) / LGPU_TILE);
+            if (c->last_mode == 2) k_dump_nbr<true><<<nblk, LGPU_TILE, 0, c->stream>>>(v, d_off, d_flat);
+            else k_dump_nbr<false><<<nblk, LGPU_TILE, 0, c->stream>>>(v, d_off, d_flat);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(out, d_flat, bytes, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));

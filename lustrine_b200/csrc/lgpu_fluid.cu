@@ -22,6 +22,10 @@ struct FluidParams {
     float l_h2;       // cubic_l / (h*h)
     float l_kfh;      // cubic_l / (kernelFactor * h)
     float inv_W_dq, inv_rho0, inv_dt;
+    float gA, gB;     // Fast lambda pass: -(m/rho0) * gradW coefficient = gA*q + gB   (q <= 0.5)
+    float cA, cB;     // Fast delta-p pass: gradW coefficient = cA*q + cB             (q <= 0.5)
+    float kx;         // cubic_k / W(s_corr_dq)
+    float mk;         // mass * cubic_k
     int literal_lambda_index;
 };
 
@@ -59,50 +63,25 @@ __device__ __forceinline__ void cubic_pair_fast(const Geom& g, const FluidParams
     }
 }
 
-template <class P, bool POLY6>
-__global__ void __launch_bounds__(LGPU_BLOCK) k_fluid_lambda(View v, FluidParams fp, const float4* __restrict__ cur) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n_owned) return;
-    const Geom& g = v.g;
-    F3 xi = f3(cur[i]);
-    float rho = 0.0f, sum = 0.0f;
-    F3 gi = f3(0.0f, 0.0f, 0.0f);
-    for_each_neighbor<false>(v, i, [&](int j) {
-        F3 xj = j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]);
-        if (P::exact || POLY6) {
-            F3 d = vsub<P>(xi, xj);
-            float len = vlen<P>(d);
-            rho = P::add(rho, P::mul(fp.mass, W_of<POLY6, P>(g, len)));           // :62-64
-            F3 gr = vscale<P>(gradW_of<POLY6, P>(g, d), fp.neg_mr);                // :76
-            sum = P::add(sum, vdot<P>(gr, gr));                                    // :77
-            gi = vsub<P>(gi, gr);                                                  // :78
-        } else {
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r2 = dx * dx + dy * dy + dz * dz;
-            float Wv, coef;
-            cubic_pair_fast(g, fp, r2, Wv, coef);
-            rho += fp.mass * Wv;
-            float gs = fp.neg_mr * coef;
-            sum += gs * gs * r2;
-            gi.x -= gs * dx; gi.y -= gs * dy; gi.z -= gs * dz;
+// Fast-policy pair evaluation used by the solver passes: wp = W(|d|)/cubic_k and cf = A*q + B on
+// the inner branch q <= 0.5 (the only one list neighbours reach at build time); the
+// outer branch and the cut-off are handled out of line.  A, B = the pass's pre-scaled gradient
+// constants, outer = its scale of the outer-branch gradient (-l/(kf*h) times the same factor).
+__device__ __forceinline__ void cubic_pair_inner(const FluidParams& fp, float r2, float A, float B, float outer, float& wp, float& cf) {
+    const float len = sqrt_approx(r2);
+    const float q = len * fp.c_q;
+    const float t = fmaf(q, 6.0f, -6.0f);
+    wp = fmaf(q * q, t, 1.0f);
+    cf = fmaf(q, A, B);
+    if (q > 0.5f) {
+        wp = 0.0f; cf = 0.0f;
+        if (q <= 1.0f) {
+            const float f = 1.0f - q;
+            wp = 2.0f * f * f * f;
+            cf = outer * f * f * rsqrtf(r2);
         }
-    });
-    float lam = 0.0f;
-    if (P::exact || POLY6) {
-        rho = P::add(rho, P::mul(fp.mass, fp.W_zero));                             // :66
-        float Ci = P::sub(P::div(rho, fp.rest_density), 1.0f);                     // :69
-        sum = P::add(sum, vdot<P>(gi, gi));                                        // :81
-        if (sum > 0.0f) lam = P::div(-Ci, P::add(sum, fp.eps));                    // :83-86
-    } else {
-        rho += fp.mass * fp.W_zero;
-        float Ci = rho * fp.inv_rho0 - 1.0f;
-        sum += gi.x * gi.x + gi.y * gi.y + gi.z * gi.z;
-        if (sum > 0.0f) lam = __fdividef(-Ci, sum + fp.eps);
     }
-    v.density[i] = rho;
-    v.lambda[i] = lam;
-    int o = v.orig[i];
-    if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
+    cf = r2 > 4.0e-10f ? cf : 0.0f;  // rl = |d|*kernelFactor > 1e-5 (src/Kernels.cpp:32)
 }
 
 // resolve_collision, src/Simulate.cpp:13-24 (returns 0.01, not min)
@@ -112,41 +91,136 @@ __device__ __forceinline__ float resolve_collision(float value, float lo, float 
     return value;
 }
 
-template <class P, bool POLY6, bool LAST>
-__global__ void __launch_bounds__(LGPU_BLOCK) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n_owned) return;
-    const Geom& g = v.g;
-    F3 xi = f3(cur[i]);
-    const float li = v.lambda[i];
-    F3 f = f3(0.0f, 0.0f, 0.0f);
-    int t = 0;
-    for_each_neighbor<false>(v, i, [&](int j) {
-        F3 xj = j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]);
-        // :97 — the reference indexes lambdas with the LOOP COUNTER
-        float lj;
-        if (fp.literal_lambda_index) lj = t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f;
-        else lj = j >= 0 ? v.lambda[j] : 0.0f;
-        t++;
+// ---- density + lambda: src/Simulate.cpp:58-88 ----
+template <class P, bool POLY6>
+struct LambdaAcc {
+    float rho, sum;
+    F3 gi;
+    __device__ __forceinline__ void init() { rho = 0.0f; sum = 0.0f; gi = f3(0.0f, 0.0f, 0.0f); }
+    __device__ __forceinline__ void pair(const Geom& g, const FluidParams& fp, F3 xi, F3 xj) {
         if (P::exact || POLY6) {
             F3 d = vsub<P>(xi, xj);
             float len = vlen<P>(d);
-            float x = P::div(W_of<POLY6, P>(g, len), fp.W_dq);
-            float sc = P::mul(-fp.s_corr_k, powf_like_libm(x, fp.s_corr_n));     // :7-9
-            float w = P::add(P::add(li, lj), sc);
-            f = vadd<P>(f, vscale<P>(gradW_of<POLY6, P>(g, d), w));               // :97
+            rho = P::add(rho, P::mul(fp.mass, W_of<POLY6, P>(g, len)));           // :62-64
+            F3 gr = vscale<P>(gradW_of<POLY6, P>(g, d), fp.neg_mr);                // :76
+            sum = P::add(sum, vdot<P>(gr, gr));                                    // :77
+            gi = vsub<P>(gi, gr);                                                  // :78
         } else {
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r2 = dx * dx + dy * dy + dz * dz;
-            float Wv, coef;
-            cubic_pair_fast(g, fp, r2, Wv, coef);
-            float x = Wv * fp.inv_W_dq;
-            float x2 = x * x;
-            float pw = fp.s_corr_n == 4.0f ? x2 * x2 : __powf(x, fp.s_corr_n);
-            float w = (li + lj - fp.s_corr_k * pw) * coef;
-            f.x += w * dx; f.y += w * dy; f.z += w * dz;
+            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float wp, gs;
+            cubic_pair_inner(fp, r2, fp.gA, fp.gB, -fp.neg_mr * fp.l_kfh, wp, gs);
+            rho += wp;  // scaled by mass * cubic_k in finish()
+            sum = fmaf(gs * gs, r2, sum);
+            gi.x = fmaf(-gs, dx, gi.x); gi.y = fmaf(-gs, dy, gi.y); gi.z = fmaf(-gs, dz, gi.z);
         }
-    });
+    }
+    __device__ __forceinline__ float finish(const FluidParams& fp) {
+        float lam = 0.0f;
+        if (P::exact || POLY6) {
+            rho = P::add(rho, P::mul(fp.mass, fp.W_zero));                             // :66
+            float Ci = P::sub(P::div(rho, fp.rest_density), 1.0f);                     // :69
+            sum = P::add(sum, vdot<P>(gi, gi));                                        // :81
+            if (sum > 0.0f) lam = P::div(-Ci, P::add(sum, fp.eps));                    // :83-86
+        } else {
+            rho = fmaf(rho, fp.mk, fp.mass * fp.W_zero);
+            float Ci = rho * fp.inv_rho0 - 1.0f;
+            sum += gi.x * gi.x + gi.y * gi.y + gi.z * gi.z;
+            if (sum > 0.0f) lam = __fdividef(-Ci, sum + fp.eps);
+        }
+        return lam;
+    }
+};
+
+// Reads x* of the neighbours from the stage, writes rho_i, lambda_i and also lambda_i into the w
+// lane of the particle's own x* so that the delta-p pass gets (x*_j, lambda_j) in one LDS.128.
+template <class P, bool POLY6, bool SOLIDS>
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams fp, float4* __restrict__ cur) {
+    extern __shared__ float4 stage[];
+    __shared__ BlkDesc d;
+    __shared__ uint64_t bar;
+    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    stage_begin(v, cur, d, &bar, stage);
+    if (i >= v.n) return;
+    const int word = v.nbr_cnt[i];
+    if (word & LGPU_CNT_GHOST) return;
+    const Geom& g = v.g;
+    const F3 xi = f3(cur[i]);
+    LambdaAcc<P, POLY6> acc;
+    acc.init();
+    if (!(word & LGPU_CNT_WALK)) {
+        stage_wait(d, &bar);
+        replay_table<SOLIDS, !(P::exact || POLY6)>(v, d, stage, cur, i, word & LGPU_CNT_MASK,
+                                                   [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
+    } else {
+        walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { acc.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
+    }
+    const float lam = acc.finish(fp);
+    v.density[i] = acc.rho;
+    v.lambda[i] = lam;
+    reinterpret_cast<float*>(cur + i)[3] = lam;
+    int o = v.orig[i];
+    if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
+}
+
+// ---- delta-p + box collision (+ commit): src/Simulate.cpp:90-113 ----
+template <class P, bool POLY6>
+__device__ __forceinline__ void deltap_pair(const Geom& g, const FluidParams& fp, F3 xi, F3 xj, float li, float lj, F3& f) {
+    if (P::exact || POLY6) {
+        F3 d = vsub<P>(xi, xj);
+        float len = vlen<P>(d);
+        float x = P::div(W_of<POLY6, P>(g, len), fp.W_dq);
+        float sc = P::mul(-fp.s_corr_k, powf_like_libm(x, fp.s_corr_n));     // :7-9
+        float w = P::add(P::add(li, lj), sc);
+        f = vadd<P>(f, vscale<P>(gradW_of<POLY6, P>(g, d), w));               // :97
+    } else {
+        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        float wp, cf;
+        cubic_pair_inner(fp, r2, fp.cA, fp.cB, -fp.l_kfh, wp, cf);
+        const float x = wp * fp.kx;
+        const float x2 = x * x;
+        const float pw = fp.s_corr_n == 4.0f ? x2 * x2 : __powf(x, fp.s_corr_n);
+        const float w = fmaf(-fp.s_corr_k, pw, li + lj) * cf;
+        f.x = fmaf(w, dx, f.x); f.y = fmaf(w, dy, f.y); f.z = fmaf(w, dz, f.z);
+    }
+}
+
+template <class P, bool POLY6, bool SOLIDS, bool LAST>
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next) {
+    extern __shared__ float4 stage[];
+    __shared__ BlkDesc d;
+    __shared__ uint64_t bar;
+    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    stage_begin(v, cur, d, &bar, stage);
+    if (i >= v.n) return;
+    const int word = v.nbr_cnt[i];
+    const float4 ci = cur[i];
+    if (word & LGPU_CNT_GHOST) { next[i] = ci; return; }
+    const Geom& g = v.g;
+    const F3 xi = f3(ci);
+    const float li = ci.w;
+    const bool literal = fp.literal_lambda_index != 0;
+    F3 f = f3(0.0f, 0.0f, 0.0f);
+    if (!(word & LGPU_CNT_WALK)) {
+        stage_wait(d, &bar);
+        replay_table<SOLIDS, !(P::exact || POLY6)>(v, d, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int t) {
+            // :97 — the reference indexes lambdas with the LOOP COUNTER
+            float lj;
+            if (literal) lj = t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f;
+            else lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
+            deltap_pair<P, POLY6>(g, fp, xi, f3(pj), li, lj, f);
+        });
+    } else {
+        int t = 0;
+        walk<false>(v, i, f3(v.x0[i]), [&](int j, int) {
+            float lj;
+            if (literal) lj = t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f;
+            else lj = j >= 0 ? v.lambda[j] : 0.0f;
+            t++;
+            deltap_pair<P, POLY6>(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]), li, lj, f);
+        });
+    }
     F3 p;
     if (P::exact || POLY6) {
         f = vdiv<P>(f, fp.rest_density);                                           // :100
@@ -170,22 +244,30 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_fluid_deltap(View v, FluidParams
     }
 }
 
-template <class P, bool POLY6>
+template <class P, bool POLY6, bool SOLIDS>
 static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
-    const int blocks = lgpu_blocks(c->n_owned);
-    const float4* cur = c->x0;
+    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE;
+    const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda<P, POLY6, SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        k_fluid_lambda<P, POLY6><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur);
+        k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
         lgpu_mark(c, 7);
-        if (it == iterations - 1) k_fluid_deltap<P, POLY6, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur, next);
-        else k_fluid_deltap<P, POLY6, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, fp, cur, next);
+        if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
         c->launches += 2;
         cur = next;
     }
-    c->pstar_final = (float4*)cur;
+    c->pstar_final = cur;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }
@@ -232,6 +314,10 @@ FluidParams lgpu_make_fluid_params(const Geom& g, const lgpu_step_params& p) {
     fp.inv_W_dq = 1.0f / fp.W_dq;
     fp.inv_rho0 = 1.0f / p.rest_density;
     fp.inv_dt = 1.0f / fp.dt;
+    fp.cA = 3.0f * fp.l_h2; fp.cB = -2.0f * fp.l_h2;
+    fp.gA = fp.neg_mr * fp.cA; fp.gB = fp.neg_mr * fp.cB;
+    fp.kx = g.cubic_k / fp.W_dq;
+    fp.mk = p.mass * g.cubic_k;
     fp.literal_lambda_index = p.literal_lambda_index;
     return fp;
 }
@@ -241,9 +327,10 @@ int lgpu_launch_fluid_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     View v = lgpu_make_view(c);
     FluidParams fp = lgpu_make_fluid_params(c->g, p);
     const int K = p.iterations < 1 ? 1 : p.iterations;
-    if (p.sph_kernel == 1) return run_fluid<Exact, true>(c, v, fp, K);
-    if (p.exact_math) return run_fluid<Exact, false>(c, v, fp, K);
-    return run_fluid<Fast, false>(c, v, fp, K);
+    const bool solids = c->n_solid > 0;
+    if (p.sph_kernel == 1) return solids ? run_fluid<Exact, true, true>(c, v, fp, K) : run_fluid<Exact, true, false>(c, v, fp, K);
+    if (p.exact_math) return solids ? run_fluid<Exact, false, true>(c, v, fp, K) : run_fluid<Exact, false, false>(c, v, fp, K);
+    return solids ? run_fluid<Fast, false, true>(c, v, fp, K) : run_fluid<Fast, false, false>(c, v, fp, K);
 }
 
 // ---- function tables for the kernel parity tests ----

@@ -124,11 +124,13 @@ int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// exclusive prefix sum over the cell histogram: three phases, 4096 cells per block
+// exclusive prefix sum over the cell histogram (inclusive scan of Sorting::counting_sort,
+// src/neighbors/Sorting.cpp:22-24, as cell offsets): ONE pass over the grid, decoupled look-back
+// between 4096-cell tiles.  Reads the histogram once (int4, coalesced), writes the offsets once and
+// zeroes the histogram for the next substep in the same pass: 12 bytes per cell.
 // ------------------------------------------------------------------------------------------
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 16
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_TILE 4096  // 4 sub-tiles of 256 threads x int4
 
 __device__ __forceinline__ int warp_incl_scan(int x) {
 #pragma unroll
@@ -139,86 +141,108 @@ __device__ __forceinline__ int warp_incl_scan(int x) {
     return x;
 }
 
-// block-wide exclusive scan of one int per thread; returns the exclusive prefix, total in *total
-__device__ __forceinline__ int block_excl_scan(int x, int* total) {
+// tile status word: bits 62..63 = 0 not ready, 1 tile aggregate, 2 inclusive prefix; low 32 bits = value
+#define SCAN_AGG (1ULL << 62)
+#define SCAN_PFX (2ULL << 62)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ counts, int n, int* __restrict__ starts,
+                                                             unsigned long long* __restrict__ state, int zero_counts) {
     __shared__ int warp_sums[SCAN_THREADS / 32];
-    __shared__ int block_total;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = warp_incl_scan(x);
-    if (lane == 31) warp_sums[w] = inc;
+    __shared__ int s_tile, s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nb = gridDim.x;
+    if (tid == 0) s_tile = (int)atomicAdd(&state[nb], 1ULL);  // ticket: tiles start in look-back order
+    __syncthreads();
+    const int tile = s_tile;
+    const long base = (long)tile * SCAN_TILE;
+    int4 vals[4];
+    int tsum[4];
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        long idx = base + (long)k * 1024 + tid * 4;
+        int4 a = make_int4(0, 0, 0, 0);
+        if (idx + 3 < n) a = *reinterpret_cast<const int4*>(counts + idx);
+        else {
+            if (idx < n) a.x = counts[idx];
+            if (idx + 1 < n) a.y = counts[idx + 1];
+            if (idx + 2 < n) a.z = counts[idx + 2];
+        }
+        vals[k] = a;
+        tsum[k] = a.x + a.y + a.z + a.w;
+        total += tsum[k];
+    }
+    // block aggregate
+    int wt = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+    if (lane == 0) warp_sums[w] = wt;
     __syncthreads();
     if (w == 0) {
-        int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
-        int si = warp_incl_scan(s);
-        if (lane < SCAN_THREADS / 32) warp_sums[lane] = si - s;
-        if (lane == SCAN_THREADS / 32 - 1) block_total = si;
-    }
-    __syncthreads();
-    int r = inc - x + warp_sums[w];
-    *total = block_total;
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int* __restrict__ counts, int n, int* __restrict__ block_sums) {
-    long base = (long)blockIdx.x * SCAN_TILE;
-    int s = 0;
+        int agg = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        long idx = base + (long)k * SCAN_THREADS + threadIdx.x;
-        if (idx < n) s += counts[idx];
-    }
-    int total;
-    block_excl_scan(s, &total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of the block sums (any count, looped)
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(int* block_sums, int nb) {
-    int carry = 0;
-    for (int base = 0; base < nb; base += SCAN_THREADS) {
-        int idx = base + threadIdx.x;
-        int x = idx < nb ? block_sums[idx] : 0;
-        int total;
-        int ex = block_excl_scan(x, &total);
-        if (idx < nb) block_sums[idx] = ex + carry;
-        carry += total;
-    }
-    if (threadIdx.x == 0) block_sums[nb] = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* __restrict__ counts, int n, const int* __restrict__ block_sums,
-                                                             int* __restrict__ starts, int zero_counts) {
-    // each thread owns SCAN_ITEMS consecutive cells -> one serial scan + one block scan
-    long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
-    int vals[SCAN_ITEMS];
-    int s = 0;
+        for (int o = 16; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
+        volatile unsigned long long* vs = state;
+        if (tile == 0) {
+            if (lane == 0) { vs[0] = SCAN_PFX | (unsigned int)agg; s_prefix = 0; }
+        } else {
+            if (lane == 0) vs[tile] = SCAN_AGG | (unsigned int)agg;
+            int running = 0;
+            int look = tile - 1 - lane;
+            while (true) {
+                unsigned long long st = look >= 0 ? vs[look] : SCAN_PFX;
+                while (__any_sync(0xffffffffu, (st >> 62) == 0)) st = look >= 0 ? vs[look] : SCAN_PFX;
+                unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                int first = pm ? __ffs(pm) - 1 : 32;
+                int contrib = lane <= first ? (int)(unsigned int)st : 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        long idx = base + k;
-        vals[k] = idx < n ? counts[idx] : 0;
-        s += vals[k];
-    }
-    int total;
-    int ex = block_excl_scan(s, &total) + block_sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        long idx = base + k;
-        if (idx < n) {
-            starts[idx] = ex;
-            if (zero_counts) counts[idx] = 0;
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                running += contrib;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) { vs[tile] = SCAN_PFX | (unsigned int)(running + agg); s_prefix = running; }
         }
-        ex += vals[k];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) starts[n] = block_sums[gridDim.x];
+    __syncthreads();
+    int carry = s_prefix;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // exclusive scan of the per-thread sums of this sub-tile
+        int inc = warp_incl_scan(tsum[k]);
+        __syncthreads();
+        if (lane == 31) warp_sums[w] = inc;
+        __syncthreads();
+        int woff = 0, sub_total = 0;
+#pragma unroll
+        for (int q = 0; q < SCAN_THREADS / 32; q++) {
+            int sv = warp_sums[q];
+            if (q < w) woff += sv;
+            sub_total += sv;
+        }
+        int ex = carry + woff + inc - tsum[k];
+        long idx = base + (long)k * 1024 + tid * 4;
+        int4 a = vals[k];
+        int4 o4 = make_int4(ex, ex + a.x, ex + a.x + a.y, ex + a.x + a.y + a.z);
+        if (idx + 3 < n) {
+            *reinterpret_cast<int4*>(starts + idx) = o4;
+            if (zero_counts) *reinterpret_cast<int4*>(counts + idx) = make_int4(0, 0, 0, 0);
+        } else {
+            if (idx < n) { starts[idx] = o4.x; if (zero_counts) counts[idx] = 0; }
+            if (idx + 1 < n) { starts[idx + 1] = o4.y; if (zero_counts) counts[idx + 1] = 0; }
+            if (idx + 2 < n) { starts[idx + 2] = o4.z; if (zero_counts) counts[idx + 2] = 0; }
+        }
+        // starts[n] = grand total: written by the thread that owns element n-1
+        if (n - 1 >= idx && n - 1 <= idx + 3) starts[n] = ex + tsum[k];
+        carry += sub_total;
+    }
 }
 
 int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts) {
     int nb = (num_cells + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<nb, SCAN_THREADS, 0, c->stream>>>(counts, num_cells, c->scan_block_sums);
-    k_scan_block_sums<<<1, SCAN_THREADS, 0, c->stream>>>(c->scan_block_sums, nb);
-    k_scan_apply<<<nb, SCAN_THREADS, 0, c->stream>>>(counts, num_cells, c->scan_block_sums, starts, zero_counts ? 1 : 0);
-    c->launches += 3;
+    CUDA_TRY(cudaMemsetAsync(c->scan_state, 0, sizeof(unsigned long long) * ((size_t)nb + 1), c->stream));
+    k_scan_cells<<<nb, SCAN_THREADS, 0, c->stream>>>(counts, num_cells, starts, c->scan_state, zero_counts ? 1 : 0);
+    c->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }
@@ -351,7 +375,7 @@ int lgpu_counting_sort(const int* keys, int n, int num_cells, int* sorted, int d
     CUDA_TRY(cudaMalloc(&d_sorted, sizeof(int) * n));
     CUDA_TRY(cudaMalloc(&d_counts, sizeof(int) * ((size_t)num_cells + 1)));
     CUDA_TRY(cudaMalloc(&d_starts, sizeof(int) * ((size_t)num_cells + 1)));
-    CUDA_TRY(cudaMalloc(&tmpctx.scan_block_sums, sizeof(int) * ((size_t)nb + 1)));
+    CUDA_TRY(cudaMalloc(&tmpctx.scan_state, sizeof(unsigned long long) * ((size_t)nb + 2)));
     CUDA_TRY(cudaMemcpyAsync(d_keys, keys, sizeof(int) * n, cudaMemcpyHostToDevice, tmpctx.stream));
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * ((size_t)num_cells + 1), tmpctx.stream));
     k_cs_hist<<<lgpu_blocks(n), LGPU_BLOCK, 0, tmpctx.stream>>>(d_keys, n, d_ranks, d_counts);
@@ -363,7 +387,7 @@ int lgpu_counting_sort(const int* keys, int n, int num_cells, int* sorted, int d
     CUDA_TRY(cudaMemcpyAsync(sorted, d_sorted, sizeof(int) * n, cudaMemcpyDeviceToHost, tmpctx.stream));
     CUDA_TRY(cudaStreamSynchronize(tmpctx.stream));
     cudaFree(d_keys); cudaFree(d_ranks); cudaFree(d_tmp); cudaFree(d_sorted); cudaFree(d_counts); cudaFree(d_starts);
-    cudaFree(tmpctx.scan_block_sums);
+    cudaFree(tmpctx.scan_state);
     cudaStreamDestroy(tmpctx.stream);
     return LGPU_OK;
 }

@@ -12,6 +12,33 @@
 #define LGPU_BLOCK 128
 #define LGPU_MAX_MARKS 96
 
+// ---- staged neighbour table (lgpu_stage.cuh) ----
+#ifndef LGPU_TILE
+#define LGPU_TILE 512            // particles per thread block of the table / solver kernels
+#endif
+#ifndef LGPU_STAGE_SLOTS
+#define LGPU_STAGE_SLOTS 5120    // float4 slots of the shared-memory stage (80 KB); slot 0 = far-away dummy
+#endif
+#define LGPU_VIRTUAL_SLOTS 65535 // a neighbourhood larger than the stage is addressed with the same codes, read from L1/L2
+#define LGPU_SOLID_CODE 0x8000u  // table code of a solid neighbour: 0x8000 | run << 11 | offset in the run's window
+#define LGPU_SOLID_WINDOW 2048
+#define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
+#define LGPU_CNT_GHOST (1 << 29)  // nbr_cnt flag: ghost particle of a neighbouring slab (not updated here)
+#define LGPU_CNT_MASK 0x0fffffff
+
+// Per thread block of LGPU_TILE consecutive sorted particles: the (merged) contiguous ranges of the
+// sorted storage that cover the 27-cell neighbourhoods of all its particles.  Cell ids are linear
+// (y-major, z fastest) and the storage is sorted by cell id, so for each of the 9 (dy,dx) stencil
+// columns the cells [key_first + off - 1, key_last + off + 1] are ONE contiguous particle range.
+struct BlkDesc {
+    int nr;            // number of copy ranges (<= 9)
+    int mode;          // 0 = staged in shared memory; 1 = virtual slots (too large for the stage: same codes,
+                       // neighbours read through L1/L2); 2 = re-walk the stencil
+    int g0[9], len[9], s0[9];  // copy m: sorted slots [g0, g0+len) -> stage slots [s0, s0+len)
+    int slotbase[9];   // stage slot of sorted particle j reached through stencil column r = slotbase[r] + j
+    int sbase[9];      // first sorted solid slot of stencil column r's window
+};
+
 // ---------------------------------------------------------------------------------------
 // Device-side view of a context.  Passed BY VALUE to every kernel (lives in the constant
 // bank), so scalar parameters are re-read on every launch like the reference re-reads its
@@ -46,9 +73,12 @@ struct View {
     // solids, sorted by cell once (src/neighbors/Neighbors.cpp:266-272)
     float4* solid_pos;
     int *solid_orig, *solid_cell_start;
-    // neighbour table (column-major: entry k of particle i at nbr[k * cap + i]); sand = slot,
-    // solid = ~sorted_solid_slot
-    int *nbr, *nbr_cnt;
+    // neighbour table: 16-bit codes in list order, four per uint2, group-major: codes 4g..4g+3 of
+    // particle i at nbr16[g * cap + i].  code < 0x8000: stage slot of the block (0 = dummy);
+    // code >= 0x8000: solid, see LGPU_SOLID_CODE.
+    uint2* nbr16;
+    int* nbr_cnt;      // list length | LGPU_CNT_* flags
+    BlkDesc* blk;
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;  // [0] key violations, [1] table overflows
 };
@@ -67,10 +97,13 @@ struct lgpu_ctx {
     int *flags[2], *orig[2], *perm;
     int cur;  // which of the [2] buffers holds the current storage
     int *key_in, *rank_in, *tmp_id, *key;
-    int *cell_count, *cell_start, *scan_block_sums;
+    int *cell_count, *cell_start;
+    unsigned long long* scan_state;
     float4 *solid_pos, *solid_pos_unsorted;
     int *solid_orig, *solid_cell_start;
-    int *nbr, *nbr_cnt;
+    uint2* nbr16;
+    int* nbr_cnt;
+    BlkDesc* blk;
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;
     float4* pstar_final;  // where the last step left x* (for dumps)

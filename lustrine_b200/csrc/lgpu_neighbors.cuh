@@ -1,14 +1,17 @@
-// lgpu_neighbors.cuh — neighbour enumeration in the reference's list order.
+// lgpu_neighbors.cuh — neighbour enumeration in the reference's list order, and the staged
+// neighbour table the solver passes replay.
 //
 // The reference materialises std::vector<int> lists (src/neighbors/Neighbors.cpp:306-361 for
-// sand "v1", :386-448 for fluid "v0") and the solver loops accumulate over them in list order.
-// Here the same ORDER is produced by a per-particle stencil walk over the cell-sorted storage;
-// k_build_table stores it in a fixed-width column-major table once per substep and the solver
-// passes replay the table (or re-walk the stencil with the frozen build-time predicate when a
-// list is longer than the table).
-//
-// Encoding of an entry: sand neighbour = its sorted slot (>= 0); solid neighbour = ~(sorted
-// solid slot) (< 0).
+// sand "v1", :386-448 for fluid "v0") once per step and every solver loop accumulates over them
+// in list order.  Here the same lists, in the same order, are produced once per substep by
+// k_build_table (lgpu_neighbors.cu) and stored as 16-bit codes; each solver pass then
+//   1. stages the block's neighbourhood of the CURRENT predicted positions in shared memory with
+//      a handful of 1-D bulk (TMA) copies — the storage is cell-sorted, so the 27-cell
+//      neighbourhood of 256 consecutive particles is at most 9 contiguous ranges (BlkDesc), and
+//   2. replays its list: one coalesced 8-byte load per four neighbours, one LDS.128 per neighbour.
+// Lists that do not fit (more than M entries, a neighbourhood larger than the stage, more than
+// 2048 solids in a window) fall back to a stencil re-walk with the frozen build-time predicate
+//  — always correct, only slower.
 #pragma once
 #include "lgpu_internal.cuh"
 
@@ -22,6 +25,11 @@ __device__ __forceinline__ CellCoord decode_cell(const Geom& g, int id) {
     c.z = rem - c.x * g.gZ;
     return c;
 }
+
+// ------------------------------------------------------------------------------------------
+// Stencil walks over the global (cell-sorted) storage.  f(j, r): j >= 0 sorted sand slot,
+// j < 0: ~(sorted solid slot); r = 3*(dy+1) + (dx+1) is the stencil column the entry was found in.
+// ------------------------------------------------------------------------------------------
 
 // Fluid order (v0): stencil y-outer, x, z-inner (ascending cell id); in each cell the sand
 // particles in ascending reference slot (= ascending sorted slot, the sort is stable) and then
@@ -37,17 +45,18 @@ __device__ __forceinline__ void walk_fluid(const View& v, int i, F3 xi0, F&& f) 
         for (int dx = -1; dx <= 1; dx++) {
             int x = c.x + dx;
             if (x < 0 || x >= g.gX) continue;
+            const int r = 3 * (dy + 1) + (dx + 1);
             int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
             int base = y * g.gXZ + x * g.gZ;
             for (int z = zlo; z <= zhi; z++) {
                 int cc = base + z;
                 int b = v.cell_start[cc], e = v.cell_start[cc + 1];
                 for (int u = b; u < e; u++)
-                    if (within_h(g, xi0, f3(v.x0[u]))) f(u);
+                    if (within_h(g, xi0, f3(v.x0[u]))) f(u, r);
                 if (v.n_solid) {
                     int sb = v.solid_cell_start[cc], se = v.solid_cell_start[cc + 1];
                     for (int k = sb; k < se; k++)
-                        if (within_h(g, xi0, f3(v.solid_pos[k]))) f(~k);
+                        if (within_h(g, xi0, f3(v.solid_pos[k]))) f(~k, r);
                 }
             }
         }
@@ -70,11 +79,12 @@ __device__ __forceinline__ void walk_sand(const View& v, int i, F3 xi0, F&& f) {
         for (int dx = -1; dx <= 1; dx++) {
             int x = c.x + dx;
             if (x < 0 || x >= g.gX) continue;
+            const int r = 3 * (dy + 1) + (dx + 1);
             int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
             int base = y * g.gXZ + x * g.gZ;
             int b = v.cell_start[base + zlo], e = min(v.cell_start[base + zhi + 1], i);
             for (int u = b; u < e; u++)
-                if (within_h(g, xi0, f3(v.x0[u]))) f(u);
+                if (within_h(g, xi0, f3(v.x0[u]))) f(u, r);
         }
     }
     // phase B: per cell, solids then sand with a larger slot
@@ -84,6 +94,7 @@ __device__ __forceinline__ void walk_sand(const View& v, int i, F3 xi0, F&& f) {
         for (int dx = -1; dx <= 1; dx++) {
             int x = c.x + dx;
             if (x < 0 || x >= g.gX) continue;
+            const int r = 3 * (dy + 1) + (dx + 1);
             int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
             int base = y * g.gXZ + x * g.gZ;
             for (int z = zlo; z <= zhi; z++) {
@@ -91,11 +102,11 @@ __device__ __forceinline__ void walk_sand(const View& v, int i, F3 xi0, F&& f) {
                 if (v.n_solid) {
                     int sb = v.solid_cell_start[cc], se = v.solid_cell_start[cc + 1];
                     for (int k = sb; k < se; k++)
-                        if (within_h(g, xi0, f3(v.solid_pos[k]))) f(~k);
+                        if (within_h(g, xi0, f3(v.solid_pos[k]))) f(~k, r);
                 }
                 int b = max(v.cell_start[cc], i + 1), e = v.cell_start[cc + 1];
                 for (int u = b; u < e; u++)
-                    if (within_h(g, xi0, f3(v.x0[u]))) f(u);
+                    if (within_h(g, xi0, f3(v.x0[u]))) f(u, r);
             }
         }
     }
@@ -107,14 +118,93 @@ __device__ __forceinline__ void walk(const View& v, int i, F3 xi0, F&& f) {
     else walk_fluid(v, i, xi0, f);
 }
 
-// Replays the neighbour table, or re-walks the stencil when the list did not fit.
-template <bool SAND, class F>
-__device__ __forceinline__ void for_each_neighbor(const View& v, int i, F&& f) {
-    int cnt = v.nbr_cnt[i];
-    if (cnt <= v.M) {
-        const int* col = v.nbr + i;
-        for (int k = 0; k < cnt; k++) f(col[(size_t)k * v.cap]);
+// ------------------------------------------------------------------------------------------
+// Shared-memory stage: mbarrier + 1-D bulk copies (cp.async.bulk, the TMA engine; SASS UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// Block prologue of every staged kernel: loads the block descriptor, starts the bulk copies of
+// `src` (the array the neighbours are read from) and returns; stage_wait() blocks until they landed.
+// Must be called by all threads of the block (contains __syncthreads).
+__device__ __forceinline__ void stage_begin(const View& v, const float4* __restrict__ src, BlkDesc& d, uint64_t* bar, float4* stage) {
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(BlkDesc) / sizeof(int))) ((int*)&d)[tid] = ((const int*)&v.blk[blockIdx.x])[tid];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        stage[0] = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.0f);  // dummy: farther than any support radius
+    }
+    __syncthreads();
+    if (tid == 0 && d.mode == 0 && d.nr > 0) {
+        uint32_t bytes = 0;
+        for (int m = 0; m < d.nr; m++) bytes += (uint32_t)d.len[m] * 16u;
+        mbar_expect_tx(bar, bytes);
+        for (int m = 0; m < d.nr; m++) bulk_g2s(stage + d.s0[m], src + d.g0[m], (uint32_t)d.len[m] * 16u, bar);
+    }
+}
+__device__ __forceinline__ void stage_wait(const BlkDesc& d, uint64_t* bar) {
+    if (d.mode == 0 && d.nr > 0) mbar_wait(bar, 0);
+}
+
+// sorted sand slot (>= 0) or ~solid slot (< 0) of a table code
+__device__ __forceinline__ int decode_code(const BlkDesc& d, uint32_t code) {
+    if (code & LGPU_SOLID_CODE) return ~(d.sbase[(code >> 11) & 15] + (int)(code & (LGPU_SOLID_WINDOW - 1)));
+    for (int m = 0; m < d.nr; m++)
+        if ((int)code >= d.s0[m] && (int)code < d.s0[m] + d.len[m]) return d.g0[m] + (int)code - d.s0[m];
+    return 0;
+}
+
+// Replays the table row of particle i (cnt entries).  body(pj, code, k): pj = position (and .w payload)
+// of the k-th neighbour, read from the stage (sand; from `src` through L1/L2 when the block is in
+// virtual-slot mode) or from the sorted solid array.
+// PAD = true: the row is processed in whole groups of four; the padding codes are 0 = the far-away
+// dummy, which every fast-arithmetic body maps to a zero contribution.
+template <bool SOLIDS, bool PAD, class Body>
+__device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, const float4* __restrict__ stage,
+                                             const float4* __restrict__ src, int i, int cnt, Body&& body) {
+    const uint2* __restrict__ col = v.nbr16 + i;
+    const int ng = (cnt + 3) >> 2;
+    uint2 w = ng > 0 ? col[0] : make_uint2(0u, 0u);
+    if (d.mode == 0) {
+        for (int g = 0; g < ng; g++) {
+            uint2 wn = make_uint2(0u, 0u);
+            if (g + 1 < ng) wn = col[(size_t)(g + 1) * v.cap];
+            uint32_t code[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int k = 4 * g + q;
+                if (!PAD && k >= cnt) break;
+                float4 pj;
+                if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
+                else pj = stage[code[q]];
+                body(pj, code[q], k);
+            }
+            w = wn;
+        }
     } else {
-        walk<SAND>(v, i, f3(v.x0[i]), f);
+        for (int k = 0; k < cnt; k++) {
+            if ((k & 3) == 0 && k) w = col[(size_t)(k >> 2) * v.cap];
+            const uint32_t pair = (k & 2) ? w.y : w.x;
+            const uint32_t code = (k & 1) ? pair >> 16 : pair & 0xffffu;
+            const int j = decode_code(d, code);
+            body(j >= 0 ? src[j] : v.solid_pos[~j], code, k);
+        }
     }
 }

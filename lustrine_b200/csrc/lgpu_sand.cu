@@ -19,84 +19,105 @@ struct SandParams {
 
 __device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
 
-template <class P, bool LAST>
-__global__ void __launch_bounds__(LGPU_BLOCK) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n_owned) return;
+// One neighbour of the contact loop, src/Simulate.cpp:231-286.  pj = current x* of the neighbour,
+// old_j() = its position at the start of the step (only evaluated for sand neighbours in contact).
+template <class P, class OldJ>
+__device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old, F3 pj, bool is_sand, OldJ&& old_j, F3& deltap, bool& touched) {
+    // :235-240 — contact predicate, always Exact
+    F3 ij = vsub<Exact>(pi, pj);
+    float d2 = vdot<Exact>(ij, ij);
+    if (d2 == 0.0f) {  // glm::length(ij) == 0.0f
+        ij = f3(0.0f, 0.00001f, 0.0f);
+        d2 = vdot<Exact>(ij, ij);
+    }
+    if (d2 > sp.d2_contact_max) return;  // len > particleDiameter
+    touched = true;
+    if (P::exact) {
+        float len = __fsqrt_rn(d2);
+        F3 tmp, xjdelta, nrm;
+        if (is_sand) {  // :242-255
+            float sc = P::mul(sp.cc_half, P::sub(len, sp.diameter));
+            tmp = vdiv<P>(vscale<P>(ij, sc), len);
+            xjdelta = vsub<P>(vadd<P>(pj, tmp), old_j());
+            nrm = vsub<P>(vsub<P>(pi, tmp), vadd<P>(pj, tmp));
+        } else {        // :268-276
+            float sc = P::mul(sp.collision_coeff, P::sub(len, sp.diameter));
+            tmp = vdiv<P>(vscale<P>(ij, sc), len);
+            xjdelta = f3(0.0f, 0.0f, 0.0f);
+            nrm = vsub<P>(vsub<P>(pi, tmp), pj);
+        }
+        deltap = vsub<P>(deltap, tmp);
+        float d = vlen<P>(tmp);
+        F3 xidelta = vsub<P>(vsub<P>(pi, tmp), xi_old);
+        nrm = vnormalize<P>(nrm);
+        F3 rel = vsub<P>(xidelta, xjdelta);
+        F3 xtan = vsub<P>(rel, vscale<P>(nrm, vdot<P>(rel, nrm)));
+        float lt = P::add(vlen<P>(xtan), 1e-9f);  // avoid0, :134
+        if (P::mul(d, sp.mu_s) > lt) {
+            deltap = vsub<P>(deltap, vscale<P>(xtan, sp.friction_coeff));
+        } else {
+            float ratio = P::div(P::mul(sp.mu_k, d), lt);
+            ratio = ratio < 1.0f ? ratio : 1.0f;
+            deltap = vsub<P>(deltap, vscale<P>(vscale<P>(xtan, sp.friction_coeff), ratio));
+        }
+    } else {
+        // Fast policy: same algebra with FMA contraction and approximate rsqrt.
+        float rinv = rsqrt_approx(d2);
+        float len = d2 * rinv;
+        float sc = (is_sand ? sp.cc_half : sp.collision_coeff) * (len - sp.diameter) * rinv;
+        F3 tmp = f3(ij.x * sc, ij.y * sc, ij.z * sc);
+        deltap.x -= tmp.x; deltap.y -= tmp.y; deltap.z -= tmp.z;
+        float d = fabsf(sc) * len;  // |tmp|
+        F3 a = f3(pi.x - tmp.x, pi.y - tmp.y, pi.z - tmp.z);
+        F3 rel = f3(a.x - xi_old.x, a.y - xi_old.y, a.z - xi_old.z);
+        F3 nrm;
+        if (is_sand) {
+            F3 b = f3(pj.x + tmp.x, pj.y + tmp.y, pj.z + tmp.z);
+            F3 xo = old_j();
+            rel.x -= b.x - xo.x; rel.y -= b.y - xo.y; rel.z -= b.z - xo.z;
+            nrm = f3(a.x - b.x, a.y - b.y, a.z - b.z);
+        } else {
+            nrm = f3(a.x - pj.x, a.y - pj.y, a.z - pj.z);
+        }
+        float ninv = rsqrt_approx(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        nrm.x *= ninv; nrm.y *= ninv; nrm.z *= ninv;
+        float dn = rel.x * nrm.x + rel.y * nrm.y + rel.z * nrm.z;
+        F3 xtan = f3(rel.x - dn * nrm.x, rel.y - dn * nrm.y, rel.z - dn * nrm.z);
+        float lt = sqrtf(xtan.x * xtan.x + xtan.y * xtan.y + xtan.z * xtan.z) + 1e-9f;
+        float s = sp.friction_coeff;
+        if (!(d * sp.mu_s > lt)) s *= fminf(__fdividef(sp.mu_k * d, lt), 1.0f);
+        deltap.x -= s * xtan.x; deltap.y -= s * xtan.y; deltap.z -= s * xtan.z;
+    }
+}
+
+template <class P, bool SOLIDS, bool LAST>
+__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
+    extern __shared__ float4 stage[];
+    __shared__ BlkDesc d;
+    __shared__ uint64_t bar;
+    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    stage_begin(v, cur, d, &bar, stage);
+    if (i >= v.n) return;
+    const int word = v.nbr_cnt[i];
+    const float4 ci = cur[i];
+    if (word & LGPU_CNT_GHOST) { next[i] = ci; return; }
     const Geom& g = v.g;
-    const F3 pi = f3(cur[i]);
+    const F3 pi = f3(ci);
     const F3 xi_old = f3(v.pos[i]);
     F3 deltap = f3(0.0f, 0.0f, 0.0f);
     bool touched = false;
-    for_each_neighbor<true>(v, i, [&](int j) {
-        const bool is_sand = j >= 0;
-        F3 pj = is_sand ? f3(cur[j]) : f3(v.solid_pos[~j]);
-        // :235-240 — contact predicate, always Exact
-        F3 ij = vsub<Exact>(pi, pj);
-        float d2 = vdot<Exact>(ij, ij);
-        if (d2 == 0.0f) {  // glm::length(ij) == 0.0f
-            ij = f3(0.0f, 0.00001f, 0.0f);
-            d2 = vdot<Exact>(ij, ij);
-        }
-        if (d2 > sp.d2_contact_max) return;  // len > particleDiameter
-        touched = true;
-        if (P::exact) {
-            float len = __fsqrt_rn(d2);
-            F3 tmp, xjdelta, nrm;
-            if (is_sand) {  // :242-255
-                float sc = P::mul(sp.cc_half, P::sub(len, sp.diameter));
-                tmp = vdiv<P>(vscale<P>(ij, sc), len);
-                xjdelta = vsub<P>(vadd<P>(pj, tmp), f3(v.pos[j]));
-                nrm = vsub<P>(vsub<P>(pi, tmp), vadd<P>(pj, tmp));
-            } else {        // :268-276
-                float sc = P::mul(sp.collision_coeff, P::sub(len, sp.diameter));
-                tmp = vdiv<P>(vscale<P>(ij, sc), len);
-                xjdelta = f3(0.0f, 0.0f, 0.0f);
-                nrm = vsub<P>(vsub<P>(pi, tmp), pj);
-            }
-            deltap = vsub<P>(deltap, tmp);
-            float d = vlen<P>(tmp);
-            F3 xidelta = vsub<P>(vsub<P>(pi, tmp), xi_old);
-            nrm = vnormalize<P>(nrm);
-            F3 rel = vsub<P>(xidelta, xjdelta);
-            F3 xtan = vsub<P>(rel, vscale<P>(nrm, vdot<P>(rel, nrm)));
-            float lt = P::add(vlen<P>(xtan), 1e-9f);  // avoid0, :134
-            if (P::mul(d, sp.mu_s) > lt) {
-                deltap = vsub<P>(deltap, vscale<P>(xtan, sp.friction_coeff));
-            } else {
-                float ratio = P::div(P::mul(sp.mu_k, d), lt);
-                ratio = ratio < 1.0f ? ratio : 1.0f;
-                deltap = vsub<P>(deltap, vscale<P>(vscale<P>(xtan, sp.friction_coeff), ratio));
-            }
-        } else {
-            // Fast policy: same algebra with FMA contraction and approximate rsqrt.
-            float rinv = rsqrt_approx(d2);
-            float len = d2 * rinv;
-            float sc = (is_sand ? sp.cc_half : sp.collision_coeff) * (len - sp.diameter) * rinv;
-            F3 tmp = f3(ij.x * sc, ij.y * sc, ij.z * sc);
-            deltap.x -= tmp.x; deltap.y -= tmp.y; deltap.z -= tmp.z;
-            float d = fabsf(sc) * len;  // |tmp|
-            F3 a = f3(pi.x - tmp.x, pi.y - tmp.y, pi.z - tmp.z);
-            F3 rel = f3(a.x - xi_old.x, a.y - xi_old.y, a.z - xi_old.z);
-            F3 nrm;
-            if (is_sand) {
-                F3 b = f3(pj.x + tmp.x, pj.y + tmp.y, pj.z + tmp.z);
-                F3 xo = f3(v.pos[j]);
-                rel.x -= b.x - xo.x; rel.y -= b.y - xo.y; rel.z -= b.z - xo.z;
-                nrm = f3(a.x - b.x, a.y - b.y, a.z - b.z);
-            } else {
-                nrm = f3(a.x - pj.x, a.y - pj.y, a.z - pj.z);
-            }
-            float ninv = rsqrt_approx(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
-            nrm.x *= ninv; nrm.y *= ninv; nrm.z *= ninv;
-            float dn = rel.x * nrm.x + rel.y * nrm.y + rel.z * nrm.z;
-            F3 xtan = f3(rel.x - dn * nrm.x, rel.y - dn * nrm.y, rel.z - dn * nrm.z);
-            float lt = sqrtf(xtan.x * xtan.x + xtan.y * xtan.y + xtan.z * xtan.z) + 1e-9f;
-            float s = sp.friction_coeff;
-            if (!(d * sp.mu_s > lt)) s *= fminf(__fdividef(sp.mu_k * d, lt), 1.0f);
-            deltap.x -= s * xtan.x; deltap.y -= s * xtan.y; deltap.z -= s * xtan.z;
-        }
-    });
+    if (!(word & LGPU_CNT_WALK)) {
+        stage_wait(d, &bar);
+        replay_table<SOLIDS, true>(v, d, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+            const bool is_sand = !(SOLIDS && (code & LGPU_SOLID_CODE));
+            sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[decode_code(d, code)]); }, deltap, touched);
+        });
+    } else {
+        walk<true>(v, i, f3(v.x0[i]), [&](int j, int) {
+            const bool is_sand = j >= 0;
+            sand_pair<P>(sp, pi, xi_old, is_sand ? f3(cur[j]) : f3(v.solid_pos[~j]), is_sand, [&]() { return f3(v.pos[j]); }, deltap, touched);
+        });
+    }
     F3 ps = P::exact ? vadd<Exact>(pi, deltap) : f3(pi.x + deltap.x, pi.y + deltap.y, pi.z + deltap.z);  // :288
     const float r = g.radius;
     ps.x = fminf(fmaxf(ps.x, r), __fsub_rn(g.domainX, r));  // :307
@@ -136,20 +157,32 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     sp.cc_half = p.collision_coeff * p.mass / (p.mass + p.mass);  // src/Simulate.cpp:246, left to right
     sp.credits = p.credits;
     const int K = p.iterations < 1 ? 1 : p.iterations;
-    const int blocks = lgpu_blocks(c->n_owned);
+    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE;
+    const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
+    const bool solids = c->n_solid > 0;
     const float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
         lgpu_mark(c, 7);
+#define LGPU_SAND_LAUNCH(PP, SS, LL)                                                                                    \
+    do {                                                                                                                \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);                         \
+    } while (0)
         if (p.exact_math) {
-            if (last) k_sand_iteration<Exact, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
-            else k_sand_iteration<Exact, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+            if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
+            else { if (last) LGPU_SAND_LAUNCH(Exact, false, true); else LGPU_SAND_LAUNCH(Exact, false, false); }
         } else {
-            if (last) k_sand_iteration<Fast, true><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
-            else k_sand_iteration<Fast, false><<<blocks, LGPU_BLOCK, 0, c->stream>>>(v, sp, cur, next);
+            if (solids) { if (last) LGPU_SAND_LAUNCH(Fast, true, true); else LGPU_SAND_LAUNCH(Fast, true, false); }
+            else { if (last) LGPU_SAND_LAUNCH(Fast, false, true); else LGPU_SAND_LAUNCH(Fast, false, false); }
         }
+#undef LGPU_SAND_LAUNCH
         c->launches++;
         cur = next;
     }

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblgpu.so")
+LIB_PATH = os.environ.get("LGPU_LIB") or os.path.join(_HERE, "lib", "liblgpu.so")  # LGPU_LIB: tuning builds only
 
 c_f, c_i = C.c_float, C.c_int
 
