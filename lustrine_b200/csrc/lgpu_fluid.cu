@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     LambdaAcc<P, POLY6> acc;
     acc.init();
     if (!(word & LGPU_CNT_WALK)) {
-        stage_wait(d, &bar);
-        replay_table<SOLIDS, !(P::exact || POLY6)>(v, d, stage, cur, i, word & LGPU_CNT_MASK,
+        replay_neighbors<SOLIDS, !(P::exact || POLY6)>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK,
                                                    [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
     } else {
         walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { acc.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
@@ -203,8 +202,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     const bool literal = fp.literal_lambda_index != 0;
     F3 f = f3(0.0f, 0.0f, 0.0f);
     if (!(word & LGPU_CNT_WALK)) {
-        stage_wait(d, &bar);
-        replay_table<SOLIDS, !(P::exact || POLY6)>(v, d, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int t) {
+        replay_neighbors<SOLIDS, !(P::exact || POLY6)>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int t) {
             // :97 — the reference indexes lambdas with the LOOP COUNTER
             float lj;
             if (literal) lj = t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f;

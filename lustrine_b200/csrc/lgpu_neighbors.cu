@@ -58,25 +58,26 @@ __global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks) {
 // Appends 16-bit codes to a table row: four consecutive codes share one 8-byte group, groups are
 // strided by the capacity (nbr16 layout in lgpu_internal.cuh).
 struct RowWriter {
-    unsigned short* p;   // next code
-    int stride16;        // distance between two groups of the same particle, in codes
+    unsigned short* base;  // code 0 of this particle's row
+    uint32_t idx;          // offset of the next code
+    uint32_t jump;         // distance between two groups of the same particle, in codes, minus 3
     int M, cnt;
     bool bad;
     __device__ __forceinline__ void init(const View& v, int i) {
-        p = reinterpret_cast<unsigned short*>(v.nbr16 + i);
-        stride16 = v.cap * 4;
+        base = reinterpret_cast<unsigned short*>(v.nbr16 + i);
+        idx = 0;
+        jump = (uint32_t)v.cap * 4u - 3u;
         M = v.M; cnt = 0; bad = false;
     }
     __device__ __forceinline__ void emit(uint32_t code) {
         if (cnt < M) {
-            *p = (unsigned short)code;
-            p++;
-            if ((cnt & 3) == 3) p += stride16 - 4;
+            base[idx] = (unsigned short)code;
+            idx += (cnt & 3) == 3 ? jump : 1u;
         }
         cnt++;
     }
     __device__ __forceinline__ void finish() {  // pad the last group with the dummy code
-        if (cnt < M) for (int k = cnt & 3; k != 0 && k < 4; k++) *p++ = 0;
+        if (cnt < M) for (int k = cnt & 3; k != 0 && k < 4; k++) base[idx++] = 0;
     }
 };
 
@@ -132,12 +133,29 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
         // columns (fluid: self included; sand: self skipped — SURVEY F7).
         // Phase 1: one flattened loop over the thread's own candidate ranges (lanes with different
         // range lengths do not idle); the hits of a column are collected in a 32-bit mask.
-        const bool staged = d.mode == 0;
-        {
+        if (d.mode == 0) {
+            const uint32_t stage_addr = smem_u32(stage);
+            int r = 0;
+            uint32_t s = seg[0][tid];
+            uint32_t a = stage_addr + (s & 0xffffu) * 16u, aend = stage_addr + (s >> 16) * 16u, hits = 0, bit = 1;
+            while (true) {
+                while (a >= aend) {
+                    seg[r][tid] = hits;
+                    if (++r == 9) goto emit_phase;
+                    s = seg[r][tid];
+                    a = stage_addr + (s & 0xffffu) * 16u; aend = stage_addr + (s >> 16) * 16u; hits = 0; bit = 1;
+                }
+                const float4 pj = lds128(a);
+                if (within_h(g, xi, f3(pj))) hits |= bit;
+                bit += bit;
+                a += 16u;
+            }
+        } else {
+            // virtual-slot mode: same codes, candidates read from the global storage
             int r = 0;
             uint32_t s = seg[0][tid];
             uint32_t u = s & 0xffffu, end = s >> 16, u0 = u, hits = 0;
-            const float4* vsrc = v.x0 - d.slotbase[0];  // virtual-slot mode: slot -> sorted particle of column r
+            const float4* vsrc = v.x0 - d.slotbase[0];  // slot -> sorted particle of column r
             while (true) {
                 while (u >= end) {
                     seg[r][tid] = hits;
@@ -146,8 +164,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
                     u = s & 0xffffu; end = s >> 16; u0 = u; hits = 0;
                     vsrc = v.x0 - d.slotbase[r];
                 }
-                const float4 pj = staged ? stage[u] : vsrc[u];
-                hits |= (within_h(g, xi, f3(pj)) ? 1u : 0u) << (u - u0);
+                hits |= (within_h(g, xi, f3(vsrc[u])) ? 1u : 0u) << (u - u0);
                 u++;
             }
         }

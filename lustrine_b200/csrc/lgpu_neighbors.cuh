@@ -171,13 +171,72 @@ __device__ __forceinline__ int decode_code(const BlkDesc& d, uint32_t code) {
     return 0;
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+
 // Replays the table row of particle i (cnt entries).  body(pj, code, k): pj = position (and .w payload)
 // of the k-th neighbour, read from the stage (sand; from `src` through L1/L2 when the block is in
 // virtual-slot mode) or from the sorted solid array.
 // PAD = true: the row is processed in whole groups of four; the padding codes are 0 = the far-away
 // dummy, which every fast-arithmetic body maps to a zero contribution.
+// The whole row (MG groups of four codes) is loaded up front — before the caller waits for the
+// stage — so that the table traffic overlaps the bulk copies.
+template <int MG>
+struct TableRow {
+    uint2 w[MG];
+    __device__ __forceinline__ void load(const View& v, int i, int cnt) {
+        const uint2* __restrict__ col = v.nbr16 + i;
+        const int ng = (cnt + 3) >> 2;
+#pragma unroll
+        for (int g = 0; g < MG; g++) {
+            w[g] = make_uint2(0u, 0u);
+            if (g < ng) w[g] = col[(size_t)g * v.cap];
+        }
+    }
+};
+
+template <bool SOLIDS, bool PAD, int MG, class Body>
+__device__ __forceinline__ void replay_row(const View& v, const BlkDesc& d, const TableRow<MG>& row, uint32_t stage_addr,
+                                           const float4* __restrict__ src, int cnt, Body&& body) {
+    const int ng = (cnt + 3) >> 2;
+    if (d.mode == 0) {
+#pragma unroll
+        for (int g = 0; g < MG; g++) {
+            if (g < ng) {
+                const uint32_t code[4] = {row.w[g].x & 0xffffu, row.w[g].x >> 16, row.w[g].y & 0xffffu, row.w[g].y >> 16};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = 4 * g + q;
+                    if (!PAD && k >= cnt) break;
+                    float4 pj;
+                    if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
+                    else pj = lds128(stage_addr + code[q] * 16u);
+                    body(pj, code[q], k);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < MG; g++) {
+            if (g < ng) {
+                const uint32_t code[4] = {row.w[g].x & 0xffffu, row.w[g].x >> 16, row.w[g].y & 0xffffu, row.w[g].y >> 16};
+                for (int q = 0; q < 4; q++) {
+                    const int k = 4 * g + q;
+                    if (k >= cnt) break;
+                    const int j = decode_code(d, code[q]);
+                    body(j >= 0 ? src[j] : v.solid_pos[~j], code[q], k);
+                }
+            }
+        }
+    }
+}
+
+// generic width (max_neighbors != 32): groups are loaded one ahead
 template <bool SOLIDS, bool PAD, class Body>
-__device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, const float4* __restrict__ stage,
+__device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, uint32_t stage_addr,
                                              const float4* __restrict__ src, int i, int cnt, Body&& body) {
     const uint2* __restrict__ col = v.nbr16 + i;
     const int ng = (cnt + 3) >> 2;
@@ -193,7 +252,7 @@ __device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, co
                 if (!PAD && k >= cnt) break;
                 float4 pj;
                 if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
-                else pj = stage[code[q]];
+                else pj = lds128(stage_addr + code[q] * 16u);
                 body(pj, code[q], k);
             }
             w = wn;
@@ -206,5 +265,22 @@ __device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, co
             const int j = decode_code(d, code);
             body(j >= 0 ? src[j] : v.solid_pos[~j], code, k);
         }
+    }
+}
+
+// One entry point for the solver kernels: full-row preload for the default table width (32),
+// the generic loop otherwise.  Waits for the stage after the row loads were issued.
+template <bool SOLIDS, bool PAD, class Body>
+__device__ __forceinline__ void replay_neighbors(const View& v, const BlkDesc& d, uint64_t* bar, const float4* stage,
+                                                 const float4* __restrict__ src, int i, int cnt, Body&& body) {
+    const uint32_t stage_addr = smem_u32(stage);
+    if (v.M == 32) {
+        TableRow<8> row;
+        row.load(v, i, cnt);
+        stage_wait(d, bar);
+        replay_row<SOLIDS, PAD, 8>(v, d, row, stage_addr, src, cnt, body);
+    } else {
+        stage_wait(d, bar);
+        replay_table<SOLIDS, PAD>(v, d, stage_addr, src, i, cnt, body);
     }
 }

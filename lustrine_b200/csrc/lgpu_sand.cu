@@ -107,8 +107,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     F3 deltap = f3(0.0f, 0.0f, 0.0f);
     bool touched = false;
     if (!(word & LGPU_CNT_WALK)) {
-        stage_wait(d, &bar);
-        replay_table<SOLIDS, true>(v, d, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+        replay_neighbors<SOLIDS, true>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
             const bool is_sand = !(SOLIDS && (code & LGPU_SOLID_CODE));
             sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[decode_code(d, code)]); }, deltap, touched);
         });
