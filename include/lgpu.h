@@ -141,6 +141,10 @@ LGPU_API long lgpu_launch_count(const lgpu_ctx* ctx);
 LGPU_API int lgpu_set_phase_timing(lgpu_ctx* ctx, int on);
 /* 1 = replay each step as a CUDA graph (re-captured when n / mode / iterations change). */
 LGPU_API int lgpu_set_use_graph(lgpu_ctx* ctx, int on);
+/* Tuning / test hook: capacity (in particles) of the shared-memory stage a thread block may use for
+ * its neighbourhood; blocks that need more read their neighbours through L1/L2 instead ("virtual
+ * slots").  Clamped to the compiled maximum; results do not depend on it. */
+LGPU_API int lgpu_set_stage_slots(lgpu_ctx* ctx, int slots);
 
 /* Grid queries on the device grid of the last step ("next" rows). */
 LGPU_API int lgpu_cell_count(lgpu_ctx* ctx, const int lo[3], const int hi[3], int include_solid, int* count);

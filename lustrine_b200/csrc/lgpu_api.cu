@@ -76,7 +76,8 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     c->cap = cfg->capacity_sand > 0 ? cfg->capacity_sand : 1;
     c->cap_solid = cfg->capacity_solid;
     c->M = cfg->max_neighbors > 0 ? cfg->max_neighbors : LGPU_DEFAULT_MAX_NEIGHBORS;
-    c->M = (c->M + 3) & ~3;  // the table stores groups of four 16-bit codes
+    c->M = (c->M + 3) & ~3;
+    c->stage_slots = LGPU_STAGE_SLOTS;  // the table stores groups of four 16-bit codes
     if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 1;
@@ -166,6 +167,11 @@ extern "C" int lgpu_set_use_graph(lgpu_ctx* c, int on) {
     if (!c) return LGPU_ERR_ARG;
     c->use_graph = on != 0;
     if (!on && c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return LGPU_OK;
+}
+extern "C" int lgpu_set_stage_slots(lgpu_ctx* c, int slots) {
+    if (!c || slots < 1) return LGPU_ERR_ARG;
+    c->stage_slots = slots < LGPU_STAGE_SLOTS ? slots : LGPU_STAGE_SLOTS;
     return LGPU_OK;
 }
 extern "C" int lgpu_sync(lgpu_ctx* c) {

@@ -19,7 +19,7 @@
 #ifndef LGPU_STAGE_SLOTS
 #define LGPU_STAGE_SLOTS 5120    // float4 slots of the shared-memory stage (80 KB); slot 0 = far-away dummy
 #endif
-#define LGPU_VIRTUAL_SLOTS 65535 // a neighbourhood larger than the stage is addressed with the same codes, read from L1/L2
+#define LGPU_VIRTUAL_SLOTS 32767 // a neighbourhood larger than the stage is addressed with the same codes (< 0x8000), read from L1/L2
 #define LGPU_SOLID_CODE 0x8000u  // table code of a solid neighbour: 0x8000 | run << 11 | offset in the run's window
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
@@ -33,7 +33,7 @@
 struct BlkDesc {
     int nr;            // number of copy ranges (<= 9)
     int mode;          // 0 = staged in shared memory; 1 = virtual slots (too large for the stage: same codes,
-                       // neighbours read through L1/L2); 2 = re-walk the stencil
+                       // at most 3 ranges, neighbours read through L1/L2); 2 = re-walk the stencil
     int g0[9], len[9], s0[9];  // copy m: sorted slots [g0, g0+len) -> stage slots [s0, s0+len)
     int slotbase[9];   // stage slot of sorted particle j reached through stencil column r = slotbase[r] + j
     int sbase[9];      // first sorted solid slot of stencil column r's window
@@ -90,6 +90,7 @@ struct lgpu_ctx {
     cudaStream_t stream;
     bool own_stream;
     int n, n_owned, n_solid, cap, cap_solid, M;
+    int stage_slots;      // blocks whose neighbourhood needs more stage slots use virtual slots (<= LGPU_STAGE_SLOTS)
     bool grid_valid;      // cell_start/key describe the current storage
     bool solids_sorted;
     // device buffers (see View)

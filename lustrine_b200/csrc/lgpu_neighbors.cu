@@ -7,7 +7,7 @@
 // block descriptors: which contiguous ranges of the sorted storage a block of LGPU_TILE particles
 // needs staged (one thread per block; a few thousand threads in all)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks) {
+__global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks, int stage_slots) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_blocks) return;
     const Geom& g = v.g;
@@ -44,11 +44,25 @@ __global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks) {
         member_of[r] = nr;
     }
     if (open) { d.g0[nr] = cur_lo; d.len[nr] = cur_hi - cur_lo; d.s0[nr] = slots; slots += cur_hi - cur_lo; nr++; }
-    for (int m = nr; m < 9; m++) { d.g0[m] = 0; d.len[m] = 0; d.s0[m] = 0; }
+    d.mode = 0;
+    if (slots > stage_slots) {
+        // Too large for the stage (dense neighbour columns).  Virtual slots: one range per stencil
+        // row dy spanning its three columns, same 16-bit codes, neighbours read through L1/L2.
+        nr = 0; slots = 1;
+        for (int t = 0; t < 3; t++) {
+            int a = 0x7fffffff, e = 0;
+            for (int r = 3 * t; r < 3 * t + 3; r++) {
+                member_of[r] = -1;
+                if (hi[r] > lo[r]) { a = min(a, lo[r]); e = max(e, hi[r]); member_of[r] = nr; }
+            }
+            if (e > a) { d.g0[nr] = a; d.len[nr] = e - a; d.s0[nr] = slots; slots += e - a; nr++; }
+        }
+        d.mode = slots <= LGPU_VIRTUAL_SLOTS ? 1 : 2;
+    }
+    for (int m = nr; m < 9; m++) { d.g0[m] = 0; d.len[m] = 0; d.s0[m] = 0x7fffffff; }
 #pragma unroll
     for (int r = 0; r < 9; r++) d.slotbase[r] = member_of[r] >= 0 ? d.s0[member_of[r]] - d.g0[member_of[r]] : 0;
     d.nr = nr;
-    d.mode = slots <= LGPU_STAGE_SLOTS ? 0 : (slots <= LGPU_VIRTUAL_SLOTS ? 1 : 2);
     v.blk[b] = d;
 }
 
@@ -214,7 +228,7 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
         CUDA_TRY(cudaFuncSetAttribute(k_build_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_attr_done = true;
     }
-    k_block_ranges<<<(nb + 127) / 128, 128, 0, c->stream>>>(v, nb);
+    k_block_ranges<<<(nb + 127) / 128, 128, 0, c->stream>>>(v, nb, c->stage_slots);
     if (sand_order) k_build_table<true><<<nb, LGPU_TILE, smem, c->stream>>>(v);
     else k_build_table<false><<<nb, LGPU_TILE, smem, c->stream>>>(v);
     c->launches += 2;

@@ -163,9 +163,16 @@ __device__ __forceinline__ void stage_wait(const BlkDesc& d, uint64_t* bar) {
     if (d.mode == 0 && d.nr > 0) mbar_wait(bar, 0);
 }
 
+// virtual-slot mode: at most 3 ranges, unused ones have s0 = INT_MAX
+__device__ __forceinline__ int decode_virtual(const BlkDesc& d, uint32_t code) {
+    const int m = ((int)code >= d.s0[1] ? 1 : 0) + ((int)code >= d.s0[2] ? 1 : 0);
+    return (int)code + d.g0[m] - d.s0[m];
+}
+
 // sorted sand slot (>= 0) or ~solid slot (< 0) of a table code
 __device__ __forceinline__ int decode_code(const BlkDesc& d, uint32_t code) {
     if (code & LGPU_SOLID_CODE) return ~(d.sbase[(code >> 11) & 15] + (int)(code & (LGPU_SOLID_WINDOW - 1)));
+    if (d.mode == 1) return decode_virtual(d, code);
     for (int m = 0; m < d.nr; m++)
         if ((int)code >= d.s0[m] && (int)code < d.s0[m] + d.len[m]) return d.g0[m] + (int)code - d.s0[m];
     return 0;
@@ -226,8 +233,10 @@ __device__ __forceinline__ void replay_row(const View& v, const BlkDesc& d, cons
                 for (int q = 0; q < 4; q++) {
                     const int k = 4 * g + q;
                     if (k >= cnt) break;
-                    const int j = decode_code(d, code[q]);
-                    body(j >= 0 ? src[j] : v.solid_pos[~j], code[q], k);
+                    float4 pj;
+                    if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
+                    else pj = src[decode_virtual(d, code[q])];
+                    body(pj, code[q], k);
                 }
             }
         }
@@ -262,8 +271,10 @@ __device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, ui
             if ((k & 3) == 0 && k) w = col[(size_t)(k >> 2) * v.cap];
             const uint32_t pair = (k & 2) ? w.y : w.x;
             const uint32_t code = (k & 1) ? pair >> 16 : pair & 0xffffu;
-            const int j = decode_code(d, code);
-            body(j >= 0 ? src[j] : v.solid_pos[~j], code, k);
+            float4 pj;
+            if (SOLIDS && (code & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code >> 11) & 15] + (int)(code & (LGPU_SOLID_WINDOW - 1))];
+            else pj = src[decode_virtual(d, code)];
+            body(pj, code, k);
         }
     }
 }

@@ -178,6 +178,25 @@ def test_fluid_table_overflow_falls_back_to_walk():
     G.close(); P.close()
 
 
+@pytest.mark.parametrize("slots", [600, 40])
+def test_small_stage_uses_virtual_slots_or_walk(slots):
+    # a stage too small for the neighbourhoods: blocks switch to virtual slots (same codes, neighbours
+    # read through L1/L2) and, beyond the 16-bit code space, to the stencil re-walk; results unchanged
+    domain, sand = scenes.dam_break(16)
+    P, G = make_pair(domain, sand, scenes.floor_plate(30, 20))
+    G.set_stage_slots(slots)
+    for step in range(2):
+        compare_fluid_substep(P, G, 2, False, True)
+        compare_fluid_substep(P, G, 1, True, False)
+    G.close(); P.close()
+    domain, sand, solids = scenes.sand_pile(12, drop=1.0)
+    P, G = make_pair(domain, sand, solids)
+    G.set_stage_slots(slots)
+    for step in range(3):
+        compare_sand_substep(P, G, 4, step % 2 == 0)
+    G.close(); P.close()
+
+
 def test_fluid_free_running_horizon():
     # 10 free-running substeps (no teacher forcing), K=1 literal vs the Jacobi oracle
     domain, sand = scenes.dam_break(20)
