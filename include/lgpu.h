@@ -70,6 +70,8 @@ typedef struct lgpu_config {
        x_lo = x_hi = 0 means the whole grid (single GPU).  See lgpu_halo_* below. */
     int slab_x_lo, slab_x_hi;
     void* stream;              /* cudaStream_t to launch on, NULL = a private non-blocking stream */
+    int halo_capacity;         /* slab mode: max particles per neighbour and substep in flight (migrants, ghost
+                                  copies); 0 = max(65536, capacity_sand / 4).  Must be equal on all slabs. */
 } lgpu_config;
 
 /* Per-step scalars.  The reference re-reads them from the public Simulation struct on
@@ -133,7 +135,8 @@ LGPU_API int lgpu_sync(lgpu_ctx* ctx);
 /* Device time of the last `lgpu_step_*` call (CUDA events on the context's stream).  phase 0 =
  * the whole step (always available).  With phase timing on, also the sum over the launches of
  * one kind: 1 predict+key+histogram, 2 cell prefix sum, 3 scatter+stable reorder, 4 neighbour
- * table, 6 density/lambda kernels, 7 delta-p (fluid) / contact (sand) kernels, 5 = 6 + 7. */
+ * table, 6 density/lambda kernels, 7 delta-p (fluid) / contact (sand) kernels, 5 = 6 + 7,
+ * 8 halo refresh messages of slab mode. */
 LGPU_API int lgpu_last_step_ms(lgpu_ctx* ctx, int phase, float* ms);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 LGPU_API long lgpu_launch_count(const lgpu_ctx* ctx);
@@ -145,6 +148,25 @@ LGPU_API int lgpu_set_use_graph(lgpu_ctx* ctx, int on);
  * its neighbourhood; blocks that need more read their neighbours through L1/L2 instead ("virtual
  * slots").  Clamped to the compiled maximum; results do not depend on it. */
 LGPU_API int lgpu_set_stage_slots(lgpu_ctx* ctx, int slots);
+
+/* ---- spatial slabs: one context per GPU owns the cell columns [slab_x_lo, slab_x_hi) ----
+ * No reference counterpart (the reference is single-threaded); the per-particle arithmetic is the
+ * single-GPU one.  Wiring: every context exports its peer-visible arena (one CUDA IPC handle, or the
+ * plain pointer for contexts of the same process) and connects to the arenas of its left (side 0)
+ * and right (side 1) neighbours.  Then lgpu_step_fluid / lgpu_step_sand run the slab protocol:
+ * migration + ghost copies after predict, ghost refresh after every solver pass, all written by the
+ * sender's kernels into the receiver's memory over NVLink.  literal_lambda_index must be 0.
+ * Particles carry caller-given global ids (lgpu_slab_upload / lgpu_slab_download).
+ * lgpu_slab_step_begin/_end split a substep so that ONE host thread can drive several contexts
+ * (tests on a single GPU): call _begin on all of them, then _end on all of them. */
+LGPU_API int lgpu_slab_export(lgpu_ctx* ctx, unsigned char handle[64], void** local_ptr, size_t* bytes);
+LGPU_API int lgpu_slab_connect(lgpu_ctx* ctx, int side, const unsigned char handle[64], void* same_process_ptr);
+/* out: x_lo, x_hi, local grid X, local cells, owned particles, ghost particles, halo capacity, x offset */
+LGPU_API int lgpu_slab_info(const lgpu_ctx* ctx, int out[8]);
+LGPU_API int lgpu_slab_upload(lgpu_ctx* ctx, int n, const float* pos, const float* vel, const int* flags, const int* ids);
+LGPU_API int lgpu_slab_download(lgpu_ctx* ctx, float* pos, float* vel, int* flags, int* ids, int* n_out);
+LGPU_API int lgpu_slab_step_begin(lgpu_ctx* ctx, const lgpu_step_params* p, int mode /* 1 fluid, 2 sand */);
+LGPU_API int lgpu_slab_step_end(lgpu_ctx* ctx);
 
 /* Grid queries on the device grid of the last step ("next" rows). */
 LGPU_API int lgpu_cell_count(lgpu_ctx* ctx, const int lo[3], const int hi[3], int include_solid, int* count);

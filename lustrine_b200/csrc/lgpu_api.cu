@@ -49,6 +49,14 @@ static void make_geom(const lgpu_config& cfg, Geom* g) {
     g->gX = (int)(g->domainX / g->cell_size) + 1;
     g->gY = (int)(g->domainY / g->cell_size) + 1;
     g->gZ = (int)(g->domainZ / g->cell_size) + 1;
+    g->x_off = 0; g->slab = 0; g->x_lo = 0; g->x_hi = g->gX;
+    if (cfg.slab_x_hi > cfg.slab_x_lo) {
+        // spatial slab: local grid = owned columns [x_lo, x_hi) plus one ghost column on either side
+        g->slab = 1;
+        g->x_lo = cfg.slab_x_lo; g->x_hi = cfg.slab_x_hi;
+        g->x_off = cfg.slab_x_lo - 1;
+        g->gX = cfg.slab_x_hi - cfg.slab_x_lo + 2;
+    }
     g->gXZ = g->gX * g->gZ;
     g->C = g->gX * g->gY * g->gZ;
 }
@@ -80,7 +88,7 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     c->stage_slots = LGPU_STAGE_SLOTS;  // the table stores groups of four 16-bit codes
     if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 1;
+    const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 2;  // + trash cell (slab mode) + end
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(dalloc(&c->pos[k], cap)); CUDA_TRY(dalloc(&c->vel[k], cap));
         CUDA_TRY(dalloc(&c->flags[k], cap)); CUDA_TRY(dalloc(&c->orig[k], cap));
@@ -110,6 +118,7 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     for (int k = 0; k < 2; k++) CUDA_TRY(cudaEventCreate(&c->ev[k]));
     for (int k = 0; k < LGPU_MAX_MARKS; k++) CUDA_TRY(cudaEventCreate(&c->ev_pool[k]));
     c->solids_sorted = true;  // no solids yet
+    if (c->g.slab) { int st = lgpu_slab_init(c); if (st) return st; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
     return LGPU_OK;
@@ -126,6 +135,7 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
     cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->blk); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
+    lgpu_slab_free(c);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev[k]);
     for (int k = 0; k < LGPU_MAX_MARKS; k++) cudaEventDestroy(c->ev_pool[k]);
@@ -136,7 +146,8 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
 View lgpu_make_view(lgpu_ctx* c) {
     View v;
     v.g = c->g;
-    v.n = c->n; v.n_owned = c->n_owned; v.n_solid = c->n_solid; v.cap = c->cap; v.M = c->M;
+    v.n = c->n; v.n_in = c->n_in; v.n_owned = c->n_owned; v.n_solid = c->n_solid; v.cap = c->cap; v.M = c->M;
+    lgpu_slab_fill_view(c, &v);
     v.pos_in = c->pos[0]; v.vel_in = c->vel[0]; v.pstar_in = c->pstar_unsorted;
     v.flags_in = c->flags[0]; v.orig_in = c->orig[0];
     v.pos = c->pos[1]; v.vel = c->vel[1]; v.x0 = c->x0; v.pa = c->pa; v.pb = c->pb;
@@ -178,7 +189,7 @@ extern "C" int lgpu_sync(lgpu_ctx* c) {
     if (!c) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return LGPU_OK;
+    return lgpu_slab_check(c);
 }
 
 // ---------------- state transfer ----------------
@@ -188,11 +199,11 @@ __global__ void k_unpack3(const float* __restrict__ src, int n, float4* __restri
     dst[offset + i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.0f);
 }
 __global__ void k_fill_meta(int n, int offset, const int* __restrict__ flags_src, int* __restrict__ flags, int* __restrict__ orig,
-                            float4* __restrict__ vel, int zero_vel) {
+                            float4* __restrict__ vel, int zero_vel, const int* __restrict__ ids) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     flags[offset + i] = flags_src ? flags_src[i] : 0;
-    orig[offset + i] = offset + i;
+    orig[offset + i] = ids ? ids[i] : offset + i;
     if (zero_vel) vel[offset + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 // scatter to the reference slot: out[orig[i]] = src[i]
@@ -209,7 +220,7 @@ __global__ void k_pack1_by_orig(const int* __restrict__ src, const int* __restri
     dst[orig[i]] = src[i];
 }
 
-static int put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float* vel, const int* flags) {
+int lgpu_put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float* vel, const int* flags, const int* ids) {
     if (n == 0) return LGPU_OK;
     const int blocks = lgpu_blocks(n);
     CUDA_TRY(cudaMemcpyAsync(c->d_stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
@@ -219,13 +230,17 @@ static int put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const floa
         CUDA_TRY(cudaMemcpyAsync(c->d_stage, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
         k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->d_stage, n, c->vel[0], offset);
     }
-    int* d_flags = nullptr;
+    int *d_flags = nullptr, *d_ids = nullptr;
+    if (flags || ids) CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (flags) {
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
         d_flags = (int*)c->d_stage;
         CUDA_TRY(cudaMemcpyAsync(d_flags, flags, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     }
-    k_fill_meta<<<blocks, LGPU_BLOCK, 0, c->stream>>>(n, offset, d_flags, c->flags[0], c->orig[0], c->vel[0], vel ? 0 : 1);
+    if (ids) {
+        d_ids = (int*)c->d_stage + n;
+        CUDA_TRY(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    k_fill_meta<<<blocks, LGPU_BLOCK, 0, c->stream>>>(n, offset, d_flags, c->flags[0], c->orig[0], c->vel[0], vel ? 0 : 1, d_ids);
     c->launches += vel ? 3 : 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -236,20 +251,21 @@ extern "C" int lgpu_upload_sand(lgpu_ctx* c, int n, const float* pos, const floa
     if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
     if (n > c->cap) { lgpu_set_error("lgpu_upload_sand: %d particles > capacity %d", n, c->cap); return LGPU_ERR_CAPACITY; }
     CUDA_TRY(cudaSetDevice(c->device));
-    c->n = c->n_owned = n;
+    c->n = c->n_owned = c->n_in = n;
+    c->n_ghost = 0;
     c->grid_valid = false;
     CUDA_TRY(cudaMemsetAsync(c->lambda_head, 0, sizeof(float) * LGPU_LAMBDA_HEAD, c->stream));
-    return put_sand(c, 0, n, pos, vel, flags);
+    return lgpu_put_sand(c, 0, n, pos, vel, flags, nullptr);
 }
 
 extern "C" int lgpu_append_sand(lgpu_ctx* c, int n, const float* pos, const float* vel, const int* flags) {
     if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
     if (c->n_owned + n > c->cap) { lgpu_set_error("lgpu_append_sand: capacity %d exceeded", c->cap); return LGPU_ERR_CAPACITY; }
     CUDA_TRY(cudaSetDevice(c->device));
-    int st = put_sand(c, c->n_owned, n, pos, vel, flags);
+    int st = lgpu_put_sand(c, c->n_owned, n, pos, vel, flags, nullptr);
     if (st) return st;
     c->n_owned += n;
-    c->n = c->n_owned;
+    c->n = c->n_in = c->n_owned;
     c->grid_valid = false;
     return LGPU_OK;
 }
@@ -258,7 +274,7 @@ extern "C" int lgpu_upload_solids(lgpu_ctx* c, int n, const float* pos) {
     if (!c || n < 0 || (n > 0 && !pos)) return LGPU_ERR_ARG;
     if (n > c->cap_solid) { lgpu_set_error("lgpu_upload_solids: %d > capacity %d", n, c->cap_solid); return LGPU_ERR_CAPACITY; }
     CUDA_TRY(cudaSetDevice(c->device));
-    c->n_solid = n;
+    c->n_solid = c->n_solid_uploaded = n;
     c->solids_sorted = false;
     if (n > 0) {
         float* stage;
@@ -302,13 +318,15 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
 }
 
 // ---------------- step drivers ----------------
+extern "C" int lgpu_slab_step_begin(lgpu_ctx* c, const lgpu_step_params* p, int mode);
+extern "C" int lgpu_slab_step_end(lgpu_ctx* c);
 static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     int st;
     lgpu_mark(c, 1);
     st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
     if (st) return st;
     lgpu_mark(c, 2);
-    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C, true);
+    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C + 1, true);  // + the trash cell of slab mode
     if (st) return st;
     lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, mode == 2);
@@ -324,6 +342,10 @@ static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
 
 static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
     if (!c || !p) return LGPU_ERR_ARG;
+    if (c->g.slab) {
+        int st = lgpu_slab_step_begin(c, p, mode);
+        return st ? st : lgpu_slab_step_end(c);
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->solids_sorted) { int st = lgpu_sort_solids(c); if (st) return st; }
     c->last_params = *p;
@@ -340,8 +362,31 @@ static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
 extern "C" int lgpu_step_fluid(lgpu_ctx* c, const lgpu_step_params* p) { return run_step(c, p, 1); }
 extern "C" int lgpu_step_sand(lgpu_ctx* c, const lgpu_step_params* p) { return run_step(c, p, 2); }
 
+// Slab mode: a substep in two halves so that several contexts driven by ONE host thread ("virtual
+// ranks", tests) can all post their halo messages before any of them waits.  One process per GPU
+// simply calls lgpu_step_* (= begin + end).
+extern "C" int lgpu_slab_step_begin(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
+    if (!c || !p || (mode != 1 && mode != 2) || !c->g.slab) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->solids_sorted) { int st = lgpu_sort_solids(c); if (st) return st; }
+    c->last_params = *p;
+    c->last_mode = mode;
+    c->n_marks = 0;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    return lgpu_slab_begin(c, *p, mode);
+}
+extern "C" int lgpu_slab_step_end(lgpu_ctx* c) {
+    if (!c || !c->g.slab || !c->last_mode) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int st = lgpu_slab_end(c, c->last_params, c->last_mode);
+    if (st) return st;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    c->grid_valid = true;
+    return LGPU_OK;
+}
+
 extern "C" int lgpu_last_step_ms(lgpu_ctx* c, int phase, float* ms) {
-    if (!c || !ms || phase < 0 || phase > 7) return LGPU_ERR_ARG;
+    if (!c || !ms || phase < 0 || phase > 8) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaEventSynchronize(c->ev[1]));
     *ms = 0.0f;
@@ -398,13 +443,13 @@ extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
     if (!c || !out) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const size_t n = (size_t)c->n_owned;
+    const size_t n = (size_t)(c->g.slab ? c->n : c->n_owned);  // slab mode: the sorted live particles, ghosts included
     const void* src = nullptr;
     size_t bytes = 0;
     switch (what) {
         case LGPU_DUMP_KEYS: src = c->key; bytes = sizeof(int) * n; break;
         case LGPU_DUMP_PERM: src = c->perm; bytes = sizeof(int) * n; break;
-        case LGPU_DUMP_ORIG: src = c->orig[0]; bytes = sizeof(int) * n; break;
+        case LGPU_DUMP_ORIG: src = c->g.slab ? c->orig[1] : c->orig[0]; bytes = sizeof(int) * n; break;  // slab mode: particle ids, ghosts included
         case LGPU_DUMP_NBR_COUNT: {
             bytes = sizeof(int) * n;
             if (out_bytes < bytes) return LGPU_ERR_ARG;

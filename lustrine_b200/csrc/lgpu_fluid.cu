@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     if (i >= v.n) return;
     const int word = v.nbr_cnt[i];
     const float4 ci = cur[i];
-    if (word & LGPU_CNT_GHOST) { next[i] = ci; return; }
+    if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+        if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
+        return;
+    }
     const Geom& g = v.g;
     const F3 xi = f3(ci);
     const float li = ci.w;
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
 
 template <class P, bool POLY6, bool SOLIDS>
 static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
-    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE;
+    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
     static bool attr_done = false;
     if (!attr_done) {
@@ -258,11 +261,14 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
+        if (c->n > 0) k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
+        if (c->slab && !fp.literal_lambda_index) { int st = lgpu_slab_refresh(c, cur); if (st) return st; }  // ghosts' lambda (.w)
         lgpu_mark(c, 7);
-        if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        if (c->n == 0) {}  // an empty slab still takes part in the refresh protocol
+        else if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
         else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
         c->launches += 2;
+        if (c->slab && it < iterations - 1) { int st = lgpu_slab_refresh(c, next); if (st) return st; }        // ghosts' corrected x*
         cur = next;
     }
     c->pstar_final = cur;
@@ -321,7 +327,7 @@ FluidParams lgpu_make_fluid_params(const Geom& g, const lgpu_step_params& p) {
 }
 
 int lgpu_launch_fluid_solver(lgpu_ctx* c, const lgpu_step_params& p) {
-    if (c->n_owned == 0) return LGPU_OK;
+    if (c->n == 0 && !c->slab) return LGPU_OK;
     View v = lgpu_make_view(c);
     FluidParams fp = lgpu_make_fluid_params(c->g, p);
     const int K = p.iterations < 1 ? 1 : p.iterations;
@@ -376,4 +382,20 @@ int lgpu_eval_kernel(lgpu_ctx* c, const lgpu_step_params* p, int which, const fl
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(d_in); cudaFree(d_out);
     return LGPU_OK;
+}
+
+
+#define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+template <class P, bool POLY6, bool SOLIDS> static int preload_fluid_variant() {
+    LGPU_PRELOAD((k_fluid_lambda<P, POLY6, SOLIDS>));
+    LGPU_PRELOAD((k_fluid_deltap<P, POLY6, SOLIDS, true>));
+    LGPU_PRELOAD((k_fluid_deltap<P, POLY6, SOLIDS, false>));
+    return LGPU_OK;
+}
+int lgpu_preload_fluid() {
+    int st = 0;
+    st |= preload_fluid_variant<Exact, true, true>(); st |= preload_fluid_variant<Exact, true, false>();
+    st |= preload_fluid_variant<Exact, false, true>(); st |= preload_fluid_variant<Exact, false, false>();
+    st |= preload_fluid_variant<Fast, false, true>(); st |= preload_fluid_variant<Fast, false, false>();
+    return st ? LGPU_ERR_CUDA : LGPU_OK;
 }

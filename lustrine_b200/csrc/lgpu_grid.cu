@@ -16,22 +16,53 @@
 // ------------------------------------------------------------------------------------------
 // predict (always Exact: x* feeds the cell key, which must be bit-exact)
 // ------------------------------------------------------------------------------------------
+// Slab mode, end of the predict kernels: a particle whose predicted cell column left [x_lo, x_hi)
+// emigrates to the neighbouring slab (record to the outbox); it now sits in this slab's ghost column,
+// so its slot lives on as a ghost copy that the new owner refreshes like any other ghost.  A particle
+// in the first / last owned column is sent as a ghost copy.  Returns true if the particle emigrated.
+__device__ __forceinline__ bool slab_classify(const View& v, int i, F3 x, F3 vel, F3 xs, int flags) {
+    const int cxg = cell_x_global(v.g, xs.x);
+    const int side = cxg < v.g.x_lo ? 0 : (cxg >= v.g.x_hi ? 1 : -1);
+    HaloRec rec;
+    rec.pos = f4(x); rec.vel = f4(vel); rec.pstar = f4(xs); rec.flags = flags; rec.orig = v.orig_in[i]; rec.pad0 = rec.pad1 = 0;
+    if (side >= 0 && v.has_nbr[side]) {
+        int slot = atomicAdd(&v.out_cnt[side], 1);
+        if (slot < v.halo_cap) { v.out_mig[side][slot] = rec; v.mig_src[side][slot] = i; }
+        else atomicAdd(&v.out_cnt[4], 1);
+        return true;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const bool edge = s == 0 ? cxg <= v.g.x_lo : cxg >= v.g.x_hi - 1;
+        if (edge && v.has_nbr[s]) {
+            int slot = atomicAdd(&v.out_cnt[2 + s], 1);
+            if (slot < v.halo_cap) { v.out_gho[s][slot] = rec; v.gho_src[s][slot] = i; }
+            else atomicAdd(&v.out_cnt[4], 1);
+        }
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_fluid(View v, float dt, F3 gm /* gravity*mass */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n) return;
-    F3 x = f3(v.pos_in[i]);
-    F3 vel = f3(v.vel_in[i]);
-    F3 xs;
-    if (i < v.n_owned) {
+    if (i >= v.n_in) return;
+    int key;
+    const int a = v.g.slab ? v.flags_in[i] : 0;
+    if (a & (LGPU_FLAG_DEAD | LGPU_FLAG_GHOST)) {
+        // slab mode: an emigrated particle or last step's ghost copy — dropped by the sort (trash cell C)
+        v.flags_in[i] = LGPU_FLAG_DEAD;
+        key = v.g.C;
+    } else {
+        F3 x = f3(v.pos_in[i]);
+        F3 vel = f3(v.vel_in[i]);
         // src/Simulate.cpp:49-50: v += gravity * mass * dt;  x* = x + v * dt
         vel = vadd<Exact>(vel, vscale<Exact>(gm, dt));
-        xs = vadd<Exact>(x, vscale<Exact>(vel, dt));
+        F3 xs = vadd<Exact>(x, vscale<Exact>(vel, dt));
         v.vel_in[i] = f4(vel);
-    } else {
-        xs = f3(v.pstar_in[i]);  // ghost: predicted by its owner
+        v.pstar_in[i] = f4(xs);
+        if (v.g.slab && slab_classify(v, i, x, vel, xs, a)) v.flags_in[i] = a | LGPU_FLAG_GHOST;
+        key = cell_id_checked(v.g, xs, v.counters);
     }
-    v.pstar_in[i] = f4(xs);
-    int key = cell_id_checked(v.g, xs, v.counters);
     v.key_in[i] = key;
     v.rank_in[i] = atomicAdd(&v.cell_count[key], 1);
 }
@@ -45,13 +76,17 @@ struct SandPredict {
 
 __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_sand(View v, SandPredict s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n) return;
+    if (i >= v.n_in) return;
     typedef Exact P;
-    F3 x = f3(v.pos_in[i]);
-    F3 vel = f3(v.vel_in[i]);
-    F3 xs;
-    if (i < v.n_owned) {
-        int a = v.flags_in[i];
+    int key;
+    int a = v.flags_in[i];
+    if (v.g.slab && (a & (LGPU_FLAG_DEAD | LGPU_FLAG_GHOST))) {
+        v.flags_in[i] = LGPU_FLAG_DEAD;
+        key = v.g.C;
+    } else {
+        F3 x = f3(v.pos_in[i]);
+        F3 vel = f3(v.vel_in[i]);
+        F3 xs;
         const float r = v.g.radius;
         float w = P::div(1.0f, s.mass);                                         // :189
         if (s.credits && (a & 2)) vel = f3(0.0f, -1.0f, 0.0f);                   // :362-364
@@ -84,30 +119,29 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_sand(View v, SandPredict
         xs.z = fminf(fmaxf(xs.z, r), P::sub(v.g.domainZ, r));
         v.vel_in[i] = f4(vel);
         v.flags_in[i] = a;
-    } else {
-        xs = f3(v.pstar_in[i]);
+        v.pstar_in[i] = f4(xs);
+        if (v.g.slab && slab_classify(v, i, x, vel, xs, a)) v.flags_in[i] = a | LGPU_FLAG_GHOST;
+        key = cell_id_checked(v.g, xs, v.counters);
     }
-    v.pstar_in[i] = f4(xs);
-    int key = cell_id_checked(v.g, xs, v.counters);
     v.key_in[i] = key;
     v.rank_in[i] = atomicAdd(&v.cell_count[key], 1);
 }
 
 int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p) {
-    if (c->n == 0) return LGPU_OK;
+    if (c->n_in == 0) return LGPU_OK;
     View v = lgpu_make_view(c);
     float dt = fminf(fmaxf(p.dt, 0.001f), 0.01f);  // src/Simulate.cpp:31
     // gravity * mass evaluated once on the host in fp32, like (gravity * mass) in :49
     F3 gm;
     gm.x = p.gravity[0] * p.mass; gm.y = p.gravity[1] * p.mass; gm.z = p.gravity[2] * p.mass;
-    k_predict_fluid<<<lgpu_blocks(c->n), LGPU_BLOCK, 0, c->stream>>>(v, dt, gm);
+    k_predict_fluid<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v, dt, gm);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }
 
 int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p) {
-    if (c->n == 0) return LGPU_OK;
+    if (c->n_in == 0) return LGPU_OK;
     View v = lgpu_make_view(c);
     SandPredict s;
     s.dt = p.dt;
@@ -117,7 +151,7 @@ int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p) {
     s.credits = p.credits;
     s.attract_radius = p.attract_radius; s.blow_radius = p.blow_radius;
     s.attract_coeff = p.attract_coeff; s.blow_coeff = p.blow_coeff; s.mass = p.mass;
-    k_predict_sand<<<lgpu_blocks(c->n), LGPU_BLOCK, 0, c->stream>>>(v, s);
+    k_predict_sand<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v, s);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
@@ -252,15 +286,16 @@ int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LGPU_BLOCK) k_scatter_ids(View v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n) return;
+    if (i >= v.n_in) return;
     v.tmp_id[v.cell_start[v.key_in[i]] + v.rank_in[i]] = i;
 }
 
 __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= v.n) return;
+    if (s >= v.n_in) return;
     int i = v.tmp_id[s];
     int c = v.key_in[i];
+    if (c == v.g.C) return;  // slab mode: dead slot (trash cell), dropped
     int b = v.cell_start[c], e = v.cell_start[c + 1];
     int mine = v.orig_in[i];
     int r = 0;
@@ -275,13 +310,14 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) 
     // the reference permutes its own storage in the sand path (src/neighbors/Neighbors.cpp:296-300):
     // the sorted slot becomes the particle's reference slot.  The fluid path keeps its storage order.
     v.orig[dst] = reset_orig ? dst : mine;
+    if (v.g.slab) v.inv[i] = dst;
 }
 
 int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig) {
-    if (c->n == 0) return LGPU_OK;
+    if (c->n_in == 0) return LGPU_OK;
     View v = lgpu_make_view(c);
-    k_scatter_ids<<<lgpu_blocks(c->n), LGPU_BLOCK, 0, c->stream>>>(v);
-    k_reorder<<<lgpu_blocks(c->n), LGPU_BLOCK, 0, c->stream>>>(v, reset_orig ? 1 : 0);
+    k_scatter_ids<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v);
+    k_reorder<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v, reset_orig ? 1 : 0);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
@@ -293,7 +329,15 @@ int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig) {
 __global__ void k_solid_keys(Geom g, const float4* pos, int n, int* keys, int* ranks, int* counts, unsigned long long* counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int key = cell_id_checked(g, f3(pos[i]), counters);
+    int key;
+    if (g.slab) {
+        // solids are replicated on every slab; each keeps those inside its columns (ghost columns included)
+        bool outside;
+        key = cell_id_slab(g, f3(pos[i]), counters, &outside);
+        if (outside) key = g.C;
+    } else {
+        key = cell_id_checked(g, f3(pos[i]), counters);
+    }
     keys[i] = key;
     ranks[i] = atomicAdd(&counts[key], 1);
 }
@@ -302,11 +346,12 @@ __global__ void k_solid_scatter(const int* keys, const int* ranks, const int* st
     if (i >= n) return;
     tmp[starts[keys[i]] + ranks[i]] = i;
 }
-__global__ void k_solid_reorder(const float4* pos_in, const int* keys, const int* starts, const int* tmp, int n, float4* pos_out, int* orig_out) {
+__global__ void k_solid_reorder(const float4* pos_in, const int* keys, const int* starts, const int* tmp, int n, float4* pos_out, int* orig_out, int trash) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int i = tmp[s];
     int c = keys[i];
+    if (c == trash) return;
     int b = starts[c], e = starts[c + 1];
     int r = 0;
     for (int u = b; u < e; u++) r += (tmp[u] < i) ? 1 : 0;
@@ -315,8 +360,9 @@ __global__ void k_solid_reorder(const float4* pos_in, const int* keys, const int
 }
 
 int lgpu_sort_solids(lgpu_ctx* c) {
-    const int n = c->n_solid, C = c->g.C;
-    CUDA_TRY(cudaMemsetAsync(c->solid_cell_start, 0, sizeof(int) * ((size_t)C + 1), c->stream));
+    const int n = c->n_solid_uploaded, C = c->g.C;
+    c->n_solid = n;
+    CUDA_TRY(cudaMemsetAsync(c->solid_cell_start, 0, sizeof(int) * ((size_t)C + 2), c->stream));
     if (n > 0) {
         // reuse the sand scratch (key_in / rank_in / tmp_id are dead between steps) when it is large
         // enough, otherwise allocate temporaries
@@ -324,16 +370,19 @@ int lgpu_sort_solids(lgpu_ctx* c) {
         CUDA_TRY(cudaMalloc(&keys, sizeof(int) * n));
         CUDA_TRY(cudaMalloc(&ranks, sizeof(int) * n));
         CUDA_TRY(cudaMalloc(&tmp, sizeof(int) * n));
-        CUDA_TRY(cudaMalloc(&counts, sizeof(int) * ((size_t)C + 1)));
-        CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)C + 1), c->stream));
+        CUDA_TRY(cudaMalloc(&counts, sizeof(int) * ((size_t)C + 2)));
+        CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)C + 2), c->stream));
         k_solid_keys<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->g, c->solid_pos_unsorted, n, keys, ranks, counts, c->counters);
-        int st = lgpu_launch_scan_cells(c, counts, c->solid_cell_start, C, false);
+        int st = lgpu_launch_scan_cells(c, counts, c->solid_cell_start, C + 1, false);
         if (st) return st;
         k_solid_scatter<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(keys, ranks, c->solid_cell_start, n, tmp);
-        k_solid_reorder<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->solid_pos_unsorted, keys, c->solid_cell_start, tmp, n, c->solid_pos, c->solid_orig);
+        k_solid_reorder<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->solid_pos_unsorted, keys, c->solid_cell_start, tmp, n, c->solid_pos, c->solid_orig, C);
         c->launches += 3;
         CUDA_TRY(cudaGetLastError());
+        int kept = n;
+        CUDA_TRY(cudaMemcpyAsync(&kept, c->solid_cell_start + C, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->n_solid = kept;  // slab mode: the solids inside this context's columns
         cudaFree(keys); cudaFree(ranks); cudaFree(tmp); cudaFree(counts);
     }
     c->solids_sorted = true;
@@ -389,5 +438,17 @@ int lgpu_counting_sort(const int* keys, int n, int num_cells, int* sorted, int d
     cudaFree(d_keys); cudaFree(d_ranks); cudaFree(d_tmp); cudaFree(d_sorted); cudaFree(d_counts); cudaFree(d_starts);
     cudaFree(tmpctx.scan_state);
     cudaStreamDestroy(tmpctx.stream);
+    return LGPU_OK;
+}
+
+
+// CUDA loads kernels lazily at their first launch, and that load can wait for the device to go
+// idle.  In slab mode a context may sit in a flag-wait kernel until its neighbour launches a
+// kernel for the first time — so every kernel of the step is loaded when the context is created.
+#define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+int lgpu_preload_grid() {
+    LGPU_PRELOAD(k_predict_fluid); LGPU_PRELOAD(k_predict_sand); LGPU_PRELOAD(k_scan_cells);
+    LGPU_PRELOAD(k_scatter_ids); LGPU_PRELOAD(k_reorder);
+    LGPU_PRELOAD(k_solid_keys); LGPU_PRELOAD(k_solid_scatter); LGPU_PRELOAD(k_solid_reorder);
     return LGPU_OK;
 }

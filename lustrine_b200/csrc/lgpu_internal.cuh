@@ -51,13 +51,50 @@ struct Geom {
     float h, h2;                      // kernelRadius and its fp32 square (src/neighbors/Neighbors.cpp:349)
     float cell_size, kernel_factor;
     float cubic_k, cubic_l;
-    int gX, gY, gZ, gXZ, C;
+    int gX, gY, gZ, gXZ, C;           // LOCAL grid of this context (== the reference's grid on a single GPU)
+    int x_off;                        // global cell x of local column 0 (slabs: x_lo - 1; single GPU: 0)
+    int slab;                         // 1 = this context owns the cell columns [x_lo, x_hi) of a larger grid
+    int x_lo, x_hi;                   // owned global cell columns (slab mode)
+};
+
+// particle flag bits above the reference's `attracted` bits (slab mode only)
+#define LGPU_FLAG_DEAD (1 << 30)    // slot no longer holds a particle of this context (emigrated, or a stale ghost)
+#define LGPU_FLAG_GHOST (1 << 29)   // ghost copy of a neighbouring slab's boundary particle (read, never updated here)
+
+// One particle in flight between two slabs (migrant or ghost copy): 64 bytes.
+struct HaloRec {
+    float4 pos, vel, pstar;
+    int flags, orig, pad0, pad1;
+};
+
+// Peer-visible memory of a slab context.  Everything a neighbour writes lives here, so one IPC handle
+// per context is enough.  side 0 = traffic from / to the LEFT neighbour (lower x), 1 = RIGHT.
+struct SlabHeader {
+    int flag[2];        // sequence number of the last complete message from side s (written by the peer)
+    int in_cnt[2][2];   // [side][0 = migrants, 1 = ghosts] of the last halo message (written by the peer)
+    int error;          // set by a wait kernel that timed out
+    int pad[25];
+};
+struct SlabArena {
+    SlabHeader* hdr;
+    HaloRec* in_mig[2];   // migrants received from side s
+    HaloRec* in_gho[2];   // ghost copies received from side s
+    float4* refresh[2][2];  // [parity][side]: refreshed ghost values (x*, lambda in w), message parity alternates;
+                            // 2 * halo_cap entries: the ghost copies first, then the particles that migrated the other way
 };
 
 struct View {
     Geom g;
-    int n;        // sand particles resident (owned + ghosts)
-    int n_owned;  // sand particles this context updates
+    int n;        // live sorted particles (owned + ghosts of neighbouring slabs)
+    int n_in;     // entries of the unsorted step-boundary storage (== n on a single GPU; slabs: previous
+                  // storage incl. dead slots + this step's inbox)
+    int n_owned;  // sand particles this context updates (host bookkeeping; kernels test the flag bits)
+    // slabs: outboxes filled by the predict kernel ([side]), and the unsorted index of every ghost copy sent
+    HaloRec *out_mig[2], *out_gho[2];
+    int *gho_src[2], *mig_src[2];  // unsorted index of every ghost copy / migrant sent to side s
+    int *out_cnt;   // [0..1] migrants to L/R, [2..3] ghosts to L/R, [4] halo capacity overflows
+    int halo_cap, has_nbr[2];
+    int *inv;       // slabs: unsorted index -> sorted slot of this step
     int n_solid;
     int cap;      // row stride of the neighbour table
     int M;        // neighbour table width
@@ -89,7 +126,8 @@ struct lgpu_ctx {
     int device;
     cudaStream_t stream;
     bool own_stream;
-    int n, n_owned, n_solid, cap, cap_solid, M;
+    int n, n_owned, n_solid, n_solid_uploaded, cap, cap_solid, M;
+    int n_in, n_ghost;
     int stage_slots;      // blocks whose neighbourhood needs more stage slots use virtual slots (<= LGPU_STAGE_SLOTS)
     bool grid_valid;      // cell_start/key describe the current storage
     bool solids_sorted;
@@ -108,6 +146,8 @@ struct lgpu_ctx {
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;
     float4* pstar_final;  // where the last step left x* (for dumps)
+    // ---- slabs (lgpu_slab.cu) ----
+    struct SlabState* slab;
     // staging
     float *h_stage, *d_stage;
     size_t stage_bytes;
@@ -149,6 +189,20 @@ static inline void lgpu_mark(lgpu_ctx* c, int phase) {
     c->ev_phase[c->n_marks] = phase;
     c->n_marks++;
 }
+
+// ---- slabs ----
+// called by the solver drivers after every pass: pushes the boundary particles' values of `buf` to the
+// neighbouring slabs and applies theirs to this context's ghosts (no-op on a single GPU)
+int lgpu_slab_refresh(lgpu_ctx* c, float4* buf);
+int lgpu_slab_init(lgpu_ctx* c);
+int lgpu_slab_check(lgpu_ctx* c);
+int lgpu_preload_grid(); int lgpu_preload_neighbors(); int lgpu_preload_fluid(); int lgpu_preload_sand();
+void lgpu_slab_free(lgpu_ctx* c);
+struct View;
+void lgpu_slab_fill_view(lgpu_ctx* c, View* v);
+int lgpu_slab_begin(lgpu_ctx* c, const lgpu_step_params& p, int mode);  // predict + post halo messages
+int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode);    // receive, grid, table, solver
+int lgpu_put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float* vel, const int* flags, const int* ids);
 
 // ---- launch wrappers, one per translation unit ----
 int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p);
@@ -205,13 +259,30 @@ __device__ __forceinline__ F3 vneg(F3 a) { return f3(-a.x, -a.y, -a.z); }
 
 // get_cell_id, src/neighbors/Utils.hpp:24-33: IEEE division, truncation toward zero, no clamp.
 // Ids outside [0, C) (undefined behaviour in the reference) are clamped and counted.
+__device__ __forceinline__ int cell_x_global(const Geom& g, float x) { return __float2int_rz(__fdiv_rn(x, g.cell_size)); }
 __device__ __forceinline__ int cell_id_raw(const Geom& g, F3 p) {
     int cx = __float2int_rz(__fdiv_rn(p.x, g.cell_size));
     int cy = __float2int_rz(__fdiv_rn(p.y, g.cell_size));
     int cz = __float2int_rz(__fdiv_rn(p.z, g.cell_size));
     return cy * g.gXZ + cx * g.gZ + cz;
 }
+// Slab mode: the key is taken in the local grid (columns x_off .. x_off + gX - 1 of the global grid,
+// same y-major / z-fastest order, so the order of the particles of a slab is the global order).
+// Out-of-grid coordinates are clamped per axis and counted.  `outside` = the particle is not in
+// any column this context stores (only possible for solids, which are replicated and filtered).
+__device__ __forceinline__ int cell_id_slab(const Geom& g, F3 p, unsigned long long* counters, bool* outside) {
+    int cx = __float2int_rz(__fdiv_rn(p.x, g.cell_size)) - g.x_off;
+    int cy = __float2int_rz(__fdiv_rn(p.y, g.cell_size));
+    int cz = __float2int_rz(__fdiv_rn(p.z, g.cell_size));
+    *outside = cx < 0 || cx >= g.gX;
+    if (cy < 0 || cy >= g.gY || cz < 0 || cz >= g.gZ || *outside) {
+        if (!*outside) atomicAdd(&counters[0], 1ULL);
+        cx = min(max(cx, 0), g.gX - 1); cy = min(max(cy, 0), g.gY - 1); cz = min(max(cz, 0), g.gZ - 1);
+    }
+    return cy * g.gXZ + cx * g.gZ + cz;
+}
 __device__ __forceinline__ int cell_id_checked(const Geom& g, F3 p, unsigned long long* counters) {
+    if (g.slab) { bool outside; return cell_id_slab(g, p, counters, &outside); }
     int id = cell_id_raw(g, p);
     if (id < 0 || id >= g.C) {
         atomicAdd(&counters[0], 1ULL);

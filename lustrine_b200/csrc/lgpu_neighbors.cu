@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
     stage_begin(v, v.x0, d, &bar, stage);
     if (i >= v.n) return;
     const Geom& g = v.g;
+    if (g.slab && (v.flags[i] & LGPU_FLAG_GHOST)) {  // ghost of a neighbouring slab: read by others, never updated here
+        v.nbr_cnt[i] = LGPU_CNT_GHOST;
+        return;
+    }
     const F3 xi = f3(v.x0[i]);
     const int key = v.key[i];
     RowWriter w;
@@ -219,7 +223,7 @@ done:
 
 static bool g_attr_done = false;
 int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
-    if (c->n == 0) return LGPU_OK;
+    if (c->n == 0) return LGPU_OK;  // (slab mode: the solver drivers still run the refresh protocol)
     View v = lgpu_make_view(c);
     const int nb = (c->n + LGPU_TILE - 1) / LGPU_TILE;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
@@ -233,5 +237,12 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
     else k_build_table<false><<<nb, LGPU_TILE, smem, c->stream>>>(v);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    return LGPU_OK;
+}
+
+
+#define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+int lgpu_preload_neighbors() {
+    LGPU_PRELOAD(k_block_ranges); LGPU_PRELOAD(k_build_table<true>); LGPU_PRELOAD(k_build_table<false>);
     return LGPU_OK;
 }

@@ -174,7 +174,7 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     // the compacted arrays were written to buffer set 1: make it the step-boundary storage
     std::swap(c->pos[0], c->pos[1]); std::swap(c->vel[0], c->vel[1]);
     std::swap(c->flags[0], c->flags[1]); std::swap(c->orig[0], c->orig[1]);
-    c->n_owned = c->n = n - n_dead;
+    c->n_owned = c->n = c->n_in = n - n_dead;
     c->grid_valid = false;
     if (removed) *removed = n_dead;
     cudaFree(d_cells); cudaFree(d_counts); cudaFree(d_list); cudaFree(d_dead); cudaFree(d_moved);

@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     if (i >= v.n) return;
     const int word = v.nbr_cnt[i];
     const float4 ci = cur[i];
-    if (word & LGPU_CNT_GHOST) { next[i] = ci; return; }
+    if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+        if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
+        return;
+    }
     const Geom& g = v.g;
     const F3 pi = f3(ci);
     const F3 xi_old = f3(v.pos[i]);
@@ -146,7 +149,7 @@ static float contact_threshold(float d) {
 }
 
 int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
-    if (c->n_owned == 0) return LGPU_OK;
+    if (c->n == 0 && !c->slab) return LGPU_OK;
     View v = lgpu_make_view(c);
     SandParams sp;
     sp.dt = p.dt; sp.mass = p.mass; sp.diameter = c->g.diameter;
@@ -156,7 +159,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     sp.cc_half = p.collision_coeff * p.mass / (p.mass + p.mass);  // src/Simulate.cpp:246, left to right
     sp.credits = p.credits;
     const int K = p.iterations < 1 ? 1 : p.iterations;
-    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE;
+    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
     const bool solids = c->n_solid > 0;
     const float4* cur = c->x0;
@@ -172,7 +175,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
             CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                                \
         }                                                                                                               \
-        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);                         \
+        if (c->n > 0) k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);           \
     } while (0)
         if (p.exact_math) {
             if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
@@ -183,9 +186,24 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         }
 #undef LGPU_SAND_LAUNCH
         c->launches++;
+        if (c->slab && !last) { int st = lgpu_slab_refresh(c, next); if (st) return st; }
         cur = next;
     }
     c->pstar_final = (float4*)cur;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
+}
+
+
+#define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+template <class P, bool SOLIDS> static int preload_sand_variant() {
+    LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, true>));
+    LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, false>));
+    return LGPU_OK;
+}
+int lgpu_preload_sand() {
+    int st = 0;
+    st |= preload_sand_variant<Exact, true>(); st |= preload_sand_variant<Exact, false>();
+    st |= preload_sand_variant<Fast, true>(); st |= preload_sand_variant<Fast, false>();
+    return st ? LGPU_ERR_CUDA : LGPU_OK;
 }

@@ -23,7 +23,7 @@ class Config(C.Structure):
     _fields_ = [("domain", c_i * 3), ("particle_radius", c_f), ("particle_diameter", c_f),
                 ("kernel_radius_scale", c_f), ("capacity_sand", c_i), ("capacity_solid", c_i),
                 ("max_neighbors", c_i), ("device", c_i), ("slab_x_lo", c_i), ("slab_x_hi", c_i),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("halo_capacity", c_i)]
 
 
 class StepParams(C.Structure):
@@ -53,6 +53,8 @@ SYMBOLS = [
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
     "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_set_stage_slots", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
+    "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_upload", "lgpu_slab_download",
+    "lgpu_slab_step_begin", "lgpu_slab_step_end",
 ]
 
 _lib = None
@@ -94,6 +96,13 @@ def lib():
         L.lgpu_dump.argtypes = [vp, c_i, vp, C.c_size_t]
         L.lgpu_eval_kernel.argtypes = [vp, C.POINTER(StepParams), c_i, vp, c_i, vp]
         L.lgpu_counting_sort.argtypes = [vp, c_i, c_i, vp, c_i]
+        L.lgpu_slab_export.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.lgpu_slab_connect.argtypes = [vp, c_i, vp, vp]
+        L.lgpu_slab_info.argtypes = [vp, C.POINTER(c_i * 8)]
+        L.lgpu_slab_upload.argtypes = [vp, c_i, vp, vp, vp, vp]
+        L.lgpu_slab_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(c_i)]
+        L.lgpu_slab_step_begin.argtypes = [vp, C.POINTER(StepParams), c_i]
+        L.lgpu_slab_step_end.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -132,7 +141,7 @@ class Context:
     """One device context = one Lustrine simulation's particle state on one GPU."""
 
     def __init__(self, domain, radius=0.5, diameter=1.0, capacity_sand=0, capacity_solid=0,
-                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None):
+                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None, slab=None, halo_capacity=0):
         L = lib()
         cfg = Config()
         for a in range(3):
@@ -145,6 +154,9 @@ class Context:
         cfg.max_neighbors = int(max_neighbors)
         cfg.device = device
         cfg.stream = stream
+        if slab is not None:
+            cfg.slab_x_lo, cfg.slab_x_hi = int(slab[0]), int(slab[1])
+        cfg.halo_capacity = int(halo_capacity)
         self._h = C.c_void_p()
         _check(L.lgpu_create(C.byref(cfg), C.byref(self._h)), "lgpu_create")
         self.L = L
@@ -240,6 +252,45 @@ class Context:
 
     def set_use_graph(self, on):
         _check(self.L.lgpu_set_use_graph(self._h, int(on)), "lgpu_set_use_graph")
+
+    # ---- spatial slabs (one context per GPU; see lustrine_b200/slabs.py) ----
+    def slab_export(self):
+        """(64-byte CUDA IPC handle, device pointer, bytes) of this context's peer-visible arena."""
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        nbytes = C.c_size_t()
+        _check(self.L.lgpu_slab_export(self._h, handle, C.byref(ptr), C.byref(nbytes)), "lgpu_slab_export")
+        return bytes(handle), ptr.value, nbytes.value
+
+    def slab_connect(self, side, handle=None, same_process_ptr=None):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        _check(self.L.lgpu_slab_connect(self._h, int(side), buf, same_process_ptr), "lgpu_slab_connect")
+
+    def slab_info(self):
+        out = (c_i * 8)()
+        _check(self.L.lgpu_slab_info(self._h, C.byref(out)), "lgpu_slab_info")
+        return dict(zip(("x_lo", "x_hi", "local_grid_x", "local_cells", "owned", "ghosts", "halo_capacity", "x_off"), list(out)))
+
+    def slab_upload(self, pos, ids, vel=None, flags=None):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        ids = np.ascontiguousarray(ids, np.int32)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
+        flags = None if flags is None else np.ascontiguousarray(flags, np.int32)
+        _check(self.L.lgpu_slab_upload(self._h, pos.shape[0], _ptr(pos), _ptr(vel), _ptr(flags), _ptr(ids)), "lgpu_slab_upload")
+
+    def slab_download(self):
+        n = self.n
+        pos = np.zeros((max(n, 1), 3), np.float32); vel = np.zeros((max(n, 1), 3), np.float32)
+        flags = np.zeros(max(n, 1), np.int32); ids = np.zeros(max(n, 1), np.int32)
+        got = c_i()
+        _check(self.L.lgpu_slab_download(self._h, _ptr(pos), _ptr(vel), _ptr(flags), _ptr(ids), C.byref(got)), "lgpu_slab_download")
+        return pos[:got.value], vel[:got.value], flags[:got.value], ids[:got.value]
+
+    def slab_step_begin(self, params, mode):
+        _check(self.L.lgpu_slab_step_begin(self._h, C.byref(params), int(mode)), "lgpu_slab_step_begin")
+
+    def slab_step_end(self):
+        _check(self.L.lgpu_slab_step_end(self._h), "lgpu_slab_step_end")
 
     # ---- grid queries ----
     def cell_count(self, lo, hi, include_solid):

@@ -1,0 +1,204 @@
+"""Spatial slabs: the particle domain partitioned across the GPUs of one box.
+
+Each rank (one process per GPU) owns the cell columns [x_lo, x_hi) of the reference's uniform grid
+and runs the same substep as the single-GPU path on its particles plus a one-column ghost layer.
+Per substep the neighbouring slabs exchange, with no collective on the data path:
+  * after predict: migrants (particles whose predicted cell column left the slab) and ghost copies
+    of the particles in the first / last owned column;
+  * after every solver pass but the last: the refreshed x* / lambda of the ghosts.
+The messages are written by the sender's CUDA kernels straight into the receiver's memory over
+NVLink (CUDA IPC-mapped arena) — see lustrine_b200/csrc/lgpu_slab.cu.  torch.distributed is only the
+plumbing: it ships the 64-byte IPC handles at start-up, the barriers and the max-over-ranks timing.
+
+This module holds the host logic: choosing the slab boundaries, dealing the particles, wiring the
+neighbours (multi-process through IPC handles, or several "virtual ranks" on one device for the
+single-GPU tests), gathering the result in particle-id order.
+"""
+import numpy as np
+
+from . import lgpu
+
+CELL_SCALE = np.float32(3.1)  # kernelRadius = 3.1f * particleRadius = cell size (reference src/Lustrine.cpp:253-254)
+
+
+def cell_size(radius=0.5, kernel_radius_scale=3.1):
+    return np.float32(np.float32(kernel_radius_scale) * np.float32(radius))
+
+
+def grid_dims(domain, cs):
+    """gridN = (int)(domainN / cell_size) + 1 in fp32 (reference src/Lustrine.cpp:261-266)."""
+    return tuple(int(np.float32(d) / cs) + 1 for d in domain)
+
+
+def cell_x(pos, cs):
+    """Global cell column of each position: (int)(x / cell_size), IEEE fp32 division, truncation."""
+    return (np.ascontiguousarray(pos[:, 0], np.float32) / cs).astype(np.int32)
+
+
+def plan_slabs(columns, grid_x, world):
+    """Slab boundaries [x_lo, x_hi) per rank, whole cell columns, covering [0, grid_x), chosen from the
+    per-column particle histogram so that the ranks hold (nearly) equal particle counts.
+    `columns` = cell column of every particle (any order)."""
+    if world < 1 or grid_x < world:
+        raise ValueError("need at least one cell column per rank (grid_x=%d, world=%d)" % (grid_x, world))
+    hist = np.bincount(np.clip(columns, 0, grid_x - 1), minlength=grid_x).astype(np.int64)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    total = int(cum[-1])
+    bounds = [0]
+    for k in range(1, world):
+        target = total * k / world
+        x = int(np.searchsorted(cum, target, side="left"))  # first boundary with cum >= target
+        # choose the closer of x-1 / x, keep at least one column per rank on both sides
+        if x > 0 and abs(cum[x - 1] - target) <= abs(cum[min(x, grid_x)] - target):
+            x -= 1
+        x = max(x, bounds[-1] + 1)
+        x = min(x, grid_x - (world - k))
+        bounds.append(x)
+    bounds.append(grid_x)
+    return [(bounds[k], bounds[k + 1]) for k in range(world)]
+
+
+def deal(pos, slabs, cs):
+    """Index arrays of the particles each slab owns at start (by the cell column of their position)."""
+    cx = cell_x(pos, cs)
+    out = []
+    for k, (lo, hi) in enumerate(slabs):
+        lo_eff = -(1 << 30) if k == 0 else lo
+        hi_eff = (1 << 30) if k == len(slabs) - 1 else hi
+        out.append(np.nonzero((cx >= lo_eff) & (cx < hi_eff))[0].astype(np.int32))
+    return out
+
+
+def merge_by_id(parts, n_total):
+    """Reassembles (pos, vel, flags, ids) tuples of all slabs into arrays indexed by particle id."""
+    pos = np.zeros((n_total, 3), np.float32)
+    vel = np.zeros((n_total, 3), np.float32)
+    flags = np.zeros(n_total, np.int32)
+    seen = np.zeros(n_total, np.int32)
+    for p, v, f, ids in parts:
+        pos[ids] = p
+        vel[ids] = v
+        flags[ids] = f
+        np.add.at(seen, ids, 1)
+    if not np.all(seen == 1):
+        raise RuntimeError("slab gather: %d particles missing, %d duplicated" % (int((seen == 0).sum()), int((seen > 1).sum())))
+    return pos, vel, flags
+
+
+def local_to_global_keys(keys, info, grid):
+    """Cell ids of a slab context (local grid) as ids of the reference's global grid."""
+    gX, gY, gZ = grid
+    lgx = info["local_grid_x"]
+    cy, rem = np.divmod(keys, lgx * gZ)
+    cxl, cz = np.divmod(rem, gZ)
+    return cy * (gX * gZ) + (cxl + info["x_off"]) * gZ + cz
+
+
+class SlabContext:
+    """One slab = one lgpu context plus what the host needs to know about it."""
+
+    def __init__(self, domain, slab, capacity, solids=None, device=-1, halo_capacity=0, **ctx_kw):
+        n_solid = 0 if solids is None else len(solids)
+        self.G = lgpu.Context(domain, capacity_sand=int(capacity), capacity_solid=n_solid, device=device, slab=slab,
+                              halo_capacity=halo_capacity, **ctx_kw)
+        if n_solid:
+            self.G.upload_solids(solids)  # replicated; the context keeps the solids inside its columns
+        self.slab = slab
+
+    def close(self):
+        self.G.close()
+
+
+class VirtualSlabs:
+    """P slabs on ONE device, driven by one host thread (tests, single-GPU debugging): same kernels,
+    same messages, neighbours' arenas addressed by plain device pointers instead of IPC handles."""
+
+    def __init__(self, domain, pos, world, solids=None, vel=None, flags=None, device=-1, capacity_factor=1.5, halo_capacity=0,
+                 slabs=None, **ctx_kw):
+        pos = np.ascontiguousarray(pos, np.float32)
+        self.n_total = len(pos)
+        cs = cell_size()
+        self.grid = grid_dims(domain, cs)
+        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], world)
+        owned = deal(pos, self.slabs, cs)
+        cap = int(max(len(o) for o in owned) * capacity_factor) + 4096
+        self.ctx = [SlabContext(domain, s, cap, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
+        exports = [c.G.slab_export() for c in self.ctx]
+        for k, c in enumerate(self.ctx):
+            if k > 0:
+                c.G.slab_connect(0, same_process_ptr=exports[k - 1][1])
+            if k + 1 < len(self.ctx):
+                c.G.slab_connect(1, same_process_ptr=exports[k + 1][1])
+        for c, idx in zip(self.ctx, owned):
+            c.G.slab_upload(pos[idx], idx, None if vel is None else vel[idx], None if flags is None else flags[idx])
+
+    def step(self, mode, params=None, **kw):
+        p = params if params is not None else lgpu.default_step_params(**kw)
+        for c in self.ctx:
+            c.G.slab_step_begin(p, mode)
+        for c in self.ctx:
+            c.G.slab_step_end()
+
+    def sync(self):
+        for c in self.ctx:
+            c.G.sync()
+
+    def gather(self):
+        return merge_by_id([c.G.slab_download() for c in self.ctx], self.n_total)
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+
+class DistributedSlab:
+    """This rank's slab of a torch.distributed job (one process per GPU, NCCL or gloo for the plumbing)."""
+
+    def __init__(self, domain, pos, solids=None, vel=None, flags=None, device=0, capacity_factor=1.5, halo_capacity=0,
+                 context_factory=None, **ctx_kw):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        pos = np.ascontiguousarray(pos, np.float32)
+        self.n_total = len(pos)
+        cs = cell_size()
+        self.grid = grid_dims(domain, cs)
+        # every rank holds the same synthetic scene and derives the same plan: no broadcast needed
+        self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
+        owned = deal(pos, self.slabs, cs)
+        cap = int(max(len(o) for o in owned) * capacity_factor) + 4096
+        self.ctx = (context_factory or SlabContext)(domain, self.slabs[self.rank], cap, solids, device, halo_capacity, **ctx_kw)
+        handle, _, _ = self.ctx.G.slab_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        if self.rank > 0:
+            self.ctx.G.slab_connect(0, handle=handles[self.rank - 1])
+        if self.rank + 1 < self.world:
+            self.ctx.G.slab_connect(1, handle=handles[self.rank + 1])
+        idx = owned[self.rank]
+        self.ctx.G.slab_upload(pos[idx], idx, None if vel is None else vel[idx], None if flags is None else flags[idx])
+        self.initial = (pos[idx].copy(), idx.copy())
+        dist.barrier()
+
+    @property
+    def G(self):
+        return self.ctx.G
+
+    def reset(self):
+        """Puts the slab back to its initial particles (all ranks must call it together)."""
+        self.ctx.G.slab_upload(self.initial[0], self.initial[1])
+
+    def step(self, mode, params):
+        if mode == 1:
+            self.ctx.G.step_fluid(params)
+        else:
+            self.ctx.G.step_sand(params)
+
+    def gather(self):
+        """All particles in id order on every rank."""
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, self.ctx.G.slab_download())
+        return merge_by_id(parts, self.n_total)
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,226 @@
+"""Spatial slabs: host logic on CPU (incl. a world_size-2 gloo run), and on the GPU the
+slab protocol itself with several "virtual ranks" on one device against the single-context run."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scenes
+from lustrine_b200 import lgpu, slabs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ host logic (CPU)
+def test_plan_covers_grid_and_balances():
+    domain, pos = scenes.dam_break(20)
+    cs = slabs.cell_size()
+    grid = slabs.grid_dims(domain, cs)
+    assert grid == (39, 26, 26)  # N=20 -> grid=39x26x26
+    cx = slabs.cell_x(pos, cs)
+    for world in (1, 2, 3, 4, 8):
+        plan = slabs.plan_slabs(cx, grid[0], world)
+        assert plan[0][0] == 0 and plan[-1][1] == grid[0]
+        assert all(a[1] == b[0] for a, b in zip(plan, plan[1:])) and all(hi > lo for lo, hi in plan)
+        owned = slabs.deal(pos, plan, cs)
+        assert sum(len(o) for o in owned) == len(pos) and len(np.unique(np.concatenate(owned))) == len(pos)
+        counts = np.array([len(o) for o in owned])
+        # whole columns only: the imbalance is bounded by the fullest column
+        assert counts.max() - counts.min() <= 2 * np.bincount(cx).max()
+    with pytest.raises(ValueError):
+        slabs.plan_slabs(cx, 3, 4)
+
+
+def test_plan_edge_cases():
+    # all particles in one column: every rank still gets at least one column
+    plan = slabs.plan_slabs(np.full(100, 5, np.int32), 12, 4)
+    assert plan[0][0] == 0 and plan[-1][1] == 12 and all(hi > lo for lo, hi in plan)
+    # no particles
+    plan = slabs.plan_slabs(np.zeros(0, np.int32), 8, 2)
+    assert plan[0][0] == 0 and plan[-1][1] == 8
+    # out-of-grid columns are clipped into the edge slabs
+    pos = np.array([[-3.0, 1, 1], [1000.0, 1, 1], [5.0, 1, 1]], np.float32)
+    owned = slabs.deal(pos, [(0, 4), (4, 9)], slabs.cell_size())
+    assert owned[0].tolist() == [0, 2] or owned[0].tolist() == [0] and owned[1].tolist() == [1, 2]
+    assert sorted(np.concatenate(owned).tolist()) == [0, 1, 2]
+
+
+def test_merge_by_id_detects_loss_and_duplicates():
+    a = (np.ones((2, 3), np.float32), np.zeros((2, 3), np.float32), np.zeros(2, np.int32), np.array([0, 2], np.int32))
+    b = (np.ones((1, 3), np.float32) * 2, np.zeros((1, 3), np.float32), np.ones(1, np.int32), np.array([1], np.int32))
+    pos, vel, flags = slabs.merge_by_id([a, b], 3)
+    assert pos[:, 0].tolist() == [1, 2, 1] and flags.tolist() == [0, 1, 0]
+    with pytest.raises(RuntimeError):
+        slabs.merge_by_id([a], 3)
+    with pytest.raises(RuntimeError):
+        slabs.merge_by_id([a, a, b], 3)
+
+
+def test_local_to_global_keys():
+    grid = (39, 26, 26)
+    info = dict(local_grid_x=7, x_off=9)
+    cy, cx, cz = 3, 11, 20
+    local = cy * 7 * 26 + (cx - 9) * 26 + cz
+    assert slabs.local_to_global_keys(np.array([local]), info, grid)[0] == cy * 39 * 26 + cx * 26 + cz
+
+
+GLOO_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch.distributed as dist
+import scenes
+from lustrine_b200 import slabs
+
+class FakeG:
+    """Stands in for the CUDA context: remembers what it was told, returns its particles unchanged."""
+    def __init__(self, rank): self.rank, self.connected, self.state = rank, {{}}, None
+    def slab_export(self): return (bytes([self.rank]) * 64, 0, 0)
+    def slab_connect(self, side, handle=None, same_process_ptr=None): self.connected[side] = handle[0]
+    def slab_upload(self, pos, ids, vel=None, flags=None): self.state = (pos.copy(), ids.copy())
+    def slab_download(self):
+        pos, ids = self.state
+        return pos, np.zeros_like(pos), np.zeros(len(ids), np.int32), ids
+    def close(self): pass
+
+class FakeCtx:
+    def __init__(self, domain, slab, capacity, solids, device, halo_capacity, **kw):
+        self.G, self.slab, self.capacity = FakeG(dist.get_rank()), slab, capacity
+    def close(self): pass
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+domain, pos = scenes.dam_break(16)
+S = slabs.DistributedSlab(domain, pos, context_factory=FakeCtx)
+assert S.slabs == slabs.plan_slabs(slabs.cell_x(pos, slabs.cell_size()), S.grid[0], world)
+# neighbours wired left/right with the right handles
+want = {{}}
+if rank > 0: want[0] = rank - 1
+if rank + 1 < world: want[1] = rank + 1
+assert S.G.connected == want, (S.G.connected, want)
+# every particle is owned exactly once and comes back in id order
+got, vel, flags = S.gather()
+assert np.array_equal(got, pos)
+counts = [None] * world
+dist.all_gather_object(counts, len(S.initial[1]))
+assert sum(counts) == len(pos) and S.ctx.capacity >= max(counts)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok", counts)
+'''
+
+
+def test_distributed_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+# ------------------------------------------------------------------ the protocol on one GPU
+REL_TOL, ABS_TOL = 1e-5, 1e-5
+
+
+def close(a, b, what, rtol=REL_TOL, atol=ABS_TOL):
+    err = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    bound = atol + rtol * np.abs(np.asarray(b, np.float64))
+    worst = float((err / bound).max()) if err.size else 0.0
+    print("  %-10s max|err| %.3e  worst err/bound %.3f" % (what, err.max() if err.size else 0.0, worst))
+    assert worst <= 1.0, what
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_fluid_slabs_match_single_context(world):
+    """P slabs == 1 slab == no slabs, same tolerances as the oracle parity (summation order only)."""
+    domain, pos = scenes.dam_break(16)
+    solids = scenes.floor_plate(30, 20)
+    vel0 = np.zeros_like(pos)
+    vel0[:, 0] = 12.0 * np.sin(pos[:, 2])  # sideways motion: particles cross the slab boundaries
+    kw = dict(dt=0.01, iterations=3, literal_lambda_index=0, exact_math=1)
+    with lgpu.Context(domain, capacity_sand=len(pos), capacity_solid=len(solids)) as G:
+        G.upload_sand(pos, vel0)
+        G.upload_solids(solids)
+        V = slabs.VirtualSlabs(domain, pos, world, solids=solids, vel=vel0)
+        moved = 0
+        for step in range(6):
+            G.step_fluid(**kw)
+            V.step(1, **kw)
+            rp, rv, _ = G.download()
+            sp, sv, _ = V.gather()
+            print("step", step, [c.G.slab_info()["owned"] for c in V.ctx], [c.G.slab_info()["ghosts"] for c in V.ctx])
+            close(sp, rp, "position")
+            close(sv, rv, "velocity", atol=1e-3)
+            owners = np.concatenate([np.full(c.G.n, k) for k, c in enumerate(V.ctx)])
+            moved = max(moved, abs(int((owners == 0).sum()) - len(slabs.deal(pos, V.slabs, slabs.cell_size())[0])))
+        assert moved > 0, "the test scene must make particles migrate"
+        assert sum(c.G.n for c in V.ctx) == len(pos)
+        V.close()
+
+
+@pytest.mark.gpu
+def test_sand_slabs_match_single_context():
+    domain, sand, solids = scenes.sand_pile(12, drop=1.0)
+    vel0 = np.zeros_like(sand)
+    vel0[:, 0] = 6.0 * np.cos(sand[:, 1])
+    kw = dict(dt=0.016, iterations=4, exact_math=1)
+    with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
+        G.upload_sand(sand, vel0)
+        G.upload_solids(solids)
+        V = slabs.VirtualSlabs(domain, sand, 3, solids=solids, vel=vel0)
+        ids = np.arange(len(sand))
+        for step in range(5):
+            G.step_sand(**kw)
+            V.step(2, **kw)
+            # the single context permutes its storage like the reference: follow the particles
+            ids = ids[G.dump(lgpu.DUMP_PERM)]
+            rp, rv, _ = G.download()
+            sp, sv, _ = V.gather()
+            close(sp[ids], rp, "position")
+            close(sv[ids], rv, "velocity", atol=1e-3)
+        V.close()
+
+
+@pytest.mark.gpu
+def test_slab_keys_and_neighbour_counts_are_the_single_gpu_ones():
+    domain, pos = scenes.dam_break(12)
+    kw = dict(dt=0.01, iterations=1, literal_lambda_index=0, exact_math=1)
+    with lgpu.Context(domain, capacity_sand=len(pos)) as G:
+        G.upload_sand(pos)
+        G.step_fluid(**kw)
+        keys = G.dump(lgpu.DUMP_KEYS); orig = G.dump(lgpu.DUMP_ORIG); cnt = G.dump(lgpu.DUMP_NBR_COUNT)
+        ref_key = np.zeros(len(pos), np.int64); ref_key[orig] = keys
+        ref_cnt = np.zeros(len(pos), np.int64); ref_cnt[orig] = cnt
+    V = slabs.VirtualSlabs(domain, pos, 2)
+    V.step(1, **kw)
+    seen = 0
+    for c in V.ctx:
+        info = c.G.slab_info()
+        n_live = info["owned"] + info["ghosts"]
+        # dumps cover the sorted live particles (owned + ghosts); ghosts have no list of their own
+        k = np.zeros(n_live, np.int32); o = np.zeros(n_live, np.int32); w = np.zeros(n_live, np.int32)
+        for what, arr in ((lgpu.DUMP_KEYS, k), (lgpu.DUMP_ORIG, o), (lgpu.DUMP_NBR_COUNT, w)):
+            lgpu._check(c.G.L.lgpu_dump(c.G._h, what, arr.ctypes.data, arr.nbytes), "lgpu_dump")
+        gk = slabs.local_to_global_keys(k.astype(np.int64), info, V.grid)
+        assert np.array_equal(gk, ref_key[o]), "cell keys of a slab are the global ones"
+        col = (gk // V.grid[2]) % V.grid[0]
+        own = (col >= info["x_lo"]) & (col < info["x_hi"])
+        assert own.sum() == info["owned"]
+        assert np.array_equal(w[own], ref_cnt[o[own]]), "neighbour counts of owned particles"
+        seen += int(own.sum())
+    assert seen == len(pos)
+    V.close()
+
+
+@pytest.mark.gpu
+def test_literal_lambda_index_is_refused_on_slabs():
+    domain, pos = scenes.dam_break(8)
+    V = slabs.VirtualSlabs(domain, pos, 2)
+    with pytest.raises(lgpu.LgpuError):
+        V.step(1, dt=0.01, iterations=1, literal_lambda_index=1)
+    V.close()
