@@ -43,7 +43,10 @@ WORKLOADS = {
     # name: (kind, cube side, iterations, dt)
     "dam_break_1m": ("fluid", 100, 4, 0.01),    # BASELINE.json configs[1]
     "dam_break_64k": ("fluid", 40, 4, 0.01),
-    "dam_break_2m": ("fluid", 126, 4, 0.01),    # per-GPU load of the 16M weak-scaling config
+    "dam_break_2m": ("fluid", 126, 4, 0.01),    # weak scaling: N x 1M particles on N GPUs
+    "dam_break_4m": ("fluid", 159, 4, 0.01),
+    "dam_break_8m": ("fluid", 200, 4, 0.01),
+    "dam_break_16m": ("fluid", 252, 4, 0.01),   # BASELINE.json configs[3]
     "sand_pile_4m": ("sand", 160, 4, 0.016),    # BASELINE.json configs[2]
     "sand_pile_262k": ("sand", 64, 4, 0.016),
 }
@@ -123,10 +126,12 @@ def make_scene(kind, side):
     return D, sand, np.concatenate([floor] + boxes).astype(np.float32)
 
 
-def step_kwargs(kind, K, dt, exact):
+def step_kwargs(kind, K, dt, exact, literal=0):
     kw = dict(dt=dt, iterations=K, exact_math=int(exact))
     if kind == "fluid":
-        kw["literal_lambda_index"] = 1
+        # lambdas[neighbour] by default; --literal 1 = the reference's lambdas[loop counter], which is
+        # only defined on a single GPU and collapses the column within a few hundred substeps
+        kw["literal_lambda_index"] = int(literal)
     return kw
 
 
@@ -196,6 +201,141 @@ def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
             "seconds": seconds, "host_cores_available": os.cpu_count()}, n, seconds
 
 
+def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src, domain, sand, solids, rank, world, local_rank):
+    """N > 1: the scene partitioned into spatial slabs, one per GPU (lustrine_b200/slabs.py)."""
+    import torch
+    import torch.distributed as dist
+    from lustrine_b200 import lgpu, slabs
+    n_total = len(sand)
+    S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank)
+    G = S.G
+    mode = 1 if kind == "fluid" else 2
+    params = lgpu.default_step_params(**step_kwargs(kind, K, dt, args.exact, 0))
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    def maybe_reset(k):
+        if args.reset_every and k % args.reset_every == 0:
+            S.reset()
+
+    for k in range(warmup):
+        maybe_reset(k)
+        S.step(mode, params)
+    G.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = G.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    owned_sum = 0
+    for k in range(steps):
+        maybe_reset(k)
+        flush_l2()
+        dist.barrier()          # all ranks start the substep together (outside the event bracket)
+        torch.cuda.synchronize()
+        S.step(mode, params)
+        G.sync()
+        dev_ms += G.last_step_ms(0)
+        owned_sum += G.n
+    dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = G.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps                      # max over ranks of the summed device time
+    cnt = torch.tensor([float(launches), float(owned_sum) / steps], dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(gathered, cnt)
+    value = n_total / (ms_per_step * 1e-3)
+
+    # per-kernel timing pass
+    G.set_phase_timing(True)
+    phase = np.zeros(9)
+    PH = 10
+    S.reset()
+    for _ in range(PH):
+        flush_l2()
+        dist.barrier()
+        S.step(mode, params)
+        G.sync()
+        for ph in range(9):
+            phase[ph] += G.last_step_ms(ph)
+    phase /= PH
+    G.set_phase_timing(False)
+    info = G.slab_info()
+    n_local = info["owned"]
+    cells_per_particle = info["local_cells"] / max(n_local, 1)
+    step_bytes = fluid_bytes_per_particle(K, cells_per_particle) if kind == "fluid" else sand_bytes_per_particle(K, cells_per_particle)
+    if kind == "fluid":
+        cand = {"fluid_lambda": phase[6] / K, "fluid_deltap": phase[7] / K}
+    else:
+        cand = {"sand_iteration": phase[7] / K}
+    dom = max(cand, key=lambda k: cand[k])
+    dom_bytes = KERNEL_BYTES[dom] * (info["owned"] + info["ghosts"])
+    achieved = dom_bytes / (cand[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": cand[dom], "algorithmic_bytes_per_launch": dom_bytes,
+                "note": "rank 0's slab; per-GPU figures"}
+    step_achieved = step_bytes * n_total / world / (ms_per_step * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": step_achieved / hbm_gbs,
+                     "algorithmic_bytes_per_particle_substep": step_bytes, "per": "GPU",
+                     "phases_ms_rank0": {"predict_key_hist_halo": phase[1], "scan": phase[2], "scatter_reorder": phase[3], "neighbour_table": phase[4],
+                                         "lambda_total": phase[6], "deltap_or_contact_total": phase[7], "halo_refresh_total": phase[8]}}
+
+    # e2e: host buffers in, host buffers out, every substep, on every rank
+    e2e = None
+    if not args.no_e2e:
+        S.reset()
+        pos, vel, flags, ids = G.slab_download()
+        e_steps = min(steps, args.reset_every or 20)
+        def one(pos, vel, flags, ids):
+            G.slab_upload(pos, ids, vel, flags)
+            S.step(mode, params)
+            return G.slab_download()
+        for _ in range(2):
+            pos, vel, flags, ids = one(pos, vel, flags, ids)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        moved = 0
+        for _ in range(e_steps):
+            moved += len(ids) * 32 * 2
+            pos, vel, flags, ids = one(pos, vel, flags, ids)
+        torch.cuda.synchronize()
+        e_t = torch.tensor([time.perf_counter() - t0, float(moved)], dtype=torch.float64, device="cuda")
+        e_max = e_t.clone()
+        dist.all_reduce(e_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e_t, op=dist.ReduceOp.SUM)
+        e_ms = float(e_max[0].item()) * 1e3 / e_steps
+        e2e = {"value": n_total / (e_ms * 1e-3), "unit": "particle-substeps/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(float(e_t[1].item()) / e_steps / 2), "d2h_bytes_per_step": int(float(e_t[1].item()) / e_steps / 2), "steps": e_steps,
+               "path": "lgpu_slab_upload + lgpu_step + lgpu_slab_download with host buffers on every rank (pageable numpy arrays)"}
+    plan = S.slabs
+    line = {"metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "kind": kind, "particles": n_total, "particles_per_gpu": [int(g[1].item()) for g in gathered],
+                       "domain": list(domain), "solver_iterations": K, "dt": dt,
+                       "partition": "x-slabs of whole cell columns, one-column ghost layer, migration + ghost refresh written peer-to-peer over NVLink",
+                       "slabs": [list(x) for x in plan], "collective": "none on the data path",
+                       "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
+                       "literal_lambda_index": 0 if kind == "fluid" else None, "scene_reset_every": args.reset_every,
+                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
+                       "timing": "CUDA events on the launching stream around every substep (barrier before each), summed, max over ranks",
+                       "wall_ms_per_step_incl_flush_and_barriers": t_wall * 1e3 / steps},
+            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": None, "e2e": e2e,
+            "gpu_launches": int(sum(g[0].item() for g in gathered)), "clocks": sampler.result()}
+    S.close()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--exact", type=int, default=0, help="1 = parity arithmetic (every fp32 op separately rounded)")
+    ap.add_argument("--literal", type=int, default=0, help="fluid: 1 = lambdas[loop counter] as in the reference (single GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
@@ -216,7 +357,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 3)
 
-    workload = args.workload or ("dam_break_1m" if args.gpus == 1 else "dam_break_2m")
+    # weak scaling: the N-GPU workload is N times the single-GPU one (1M particles per GPU)
+    workload = args.workload or ("dam_break_%dm" % args.gpus if "dam_break_%dm" % args.gpus in WORKLOADS else "dam_break_1m")
     kind, side, K, dt = WORKLOADS[workload]
     metric = "particle-substeps/s"
 
@@ -250,10 +392,10 @@ def main():
     domain, sand, solids = make_scene(kind, side)
     n = len(sand)
     if world > 1:
-        from lustrine_b200 import slabs  # spatial slabs with halo exchange
-        result = slabs.bench(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src)
+        result = run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src, domain, sand, solids, rank, world, local_rank)
         if rank == 0:
             print(json.dumps(result), flush=True)
+        dist.barrier()
         dist.destroy_process_group()
         return 0
 
@@ -261,7 +403,7 @@ def main():
     G.upload_sand(sand)
     if solids is not None:
         G.upload_solids(solids)
-    kw = step_kwargs(kind, K, dt, args.exact)
+    kw = step_kwargs(kind, K, dt, args.exact, args.literal)
     params = lgpu.default_step_params(**kw)
     step = G.step_fluid if kind == "fluid" else G.step_sand
 
@@ -272,11 +414,10 @@ def main():
         torch.cuda.synchronize()
 
     def maybe_reset(k):
-        # The literal reference fluid (lambdas[loop counter]) lets a 100-particle-tall column
-        # collapse into a degenerate pile within a few hundred substeps (thousands of particles per cell,
-        # particles leaving the grid).  The scene is therefore put back to its initial state every
-        # --reset-every substeps, outside the timed bracket, so that every timed substep runs in the
-        # regime the CPU baseline is timed in (the first substeps of the dam break).
+        # The scene is put back to its initial state every --reset-every substeps, outside the timed
+        # bracket, so that every timed substep runs in the regime the CPU baseline is timed in (the first
+        # substeps of the dam break; with --literal 1 the column would otherwise collapse into a degenerate
+        # pile within a few hundred substeps).
         if args.reset_every and k % args.reset_every == 0:
             G.upload_sand(sand)
 
@@ -392,7 +533,7 @@ def main():
             "config": {"workload": workload, "kind": kind, "particles": n, "solid_particles": 0 if solids is None else len(solids),
                        "domain": list(domain), "grid_cells": G.num_cells, "solver_iterations": K, "dt": dt,
                        "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
-                       "literal_lambda_index": 1 if kind == "fluid" else None,
+                       "literal_lambda_index": args.literal if kind == "fluid" else None,
                        "scene_reset_every": args.reset_every,
                        "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
                        "timing": "CUDA events on the launching stream around every substep, summed",

@@ -93,8 +93,11 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
         CUDA_TRY(dalloc(&c->pos[k], cap)); CUDA_TRY(dalloc(&c->vel[k], cap));
         CUDA_TRY(dalloc(&c->flags[k], cap)); CUDA_TRY(dalloc(&c->orig[k], cap));
     }
-    CUDA_TRY(dalloc(&c->pstar_unsorted, cap)); CUDA_TRY(dalloc(&c->x0, cap));
-    CUDA_TRY(dalloc(&c->pa, cap)); CUDA_TRY(dalloc(&c->pb, cap));
+    CUDA_TRY(dalloc(&c->pstar_unsorted, cap));
+    if (!c->g.slab) {  // slab mode: x0 / pa / pb live in the peer-visible arena (lgpu_slab_init)
+        CUDA_TRY(dalloc(&c->x0, cap)); CUDA_TRY(dalloc(&c->pa, cap)); CUDA_TRY(dalloc(&c->pb, cap));
+    }
+    if (c->g.slab) { int st = lgpu_slab_init(c); if (st) return st; }
     CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap)); CUDA_TRY(dalloc(&c->rank_in, cap));
     CUDA_TRY(dalloc(&c->tmp_id, cap)); CUDA_TRY(dalloc(&c->key, cap));
     CUDA_TRY(dalloc(&c->cell_count, C1)); CUDA_TRY(dalloc(&c->cell_start, C1));
@@ -118,7 +121,6 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     for (int k = 0; k < 2; k++) CUDA_TRY(cudaEventCreate(&c->ev[k]));
     for (int k = 0; k < LGPU_MAX_MARKS; k++) CUDA_TRY(cudaEventCreate(&c->ev_pool[k]));
     c->solids_sorted = true;  // no solids yet
-    if (c->g.slab) { int st = lgpu_slab_init(c); if (st) return st; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
     return LGPU_OK;
@@ -129,7 +131,8 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 2; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->flags[k]); cudaFree(c->orig[k]); }
-    cudaFree(c->pstar_unsorted); cudaFree(c->x0); cudaFree(c->pa); cudaFree(c->pb); cudaFree(c->perm);
+    cudaFree(c->pstar_unsorted); cudaFree(c->perm);
+    if (!c->g.slab) { cudaFree(c->x0); cudaFree(c->pa); cudaFree(c->pb); }
     cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_state);
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);

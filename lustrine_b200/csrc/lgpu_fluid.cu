@@ -135,15 +135,14 @@ struct LambdaAcc {
 // Reads x* of the neighbours from the stage, writes rho_i, lambda_i and also lambda_i into the w
 // lane of the particle's own x* so that the delta-p pass gets (x*_j, lambda_j) in one LDS.128.
 template <class P, bool POLY6, bool SOLIDS>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams fp, float4* __restrict__ cur) {
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams fp, float4* __restrict__ cur, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     stage_begin(v, cur, d, &bar, stage);
-    if (i >= v.n) return;
-    const int word = v.nbr_cnt[i];
-    if (word & LGPU_CNT_GHOST) return;
+    const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
+    if (!(word & LGPU_CNT_GHOST)) {
     const Geom& g = v.g;
     const F3 xi = f3(cur[i]);
     LambdaAcc<P, POLY6> acc;
@@ -160,6 +159,13 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     reinterpret_cast<float*>(cur + i)[3] = lam;
     int o = v.orig[i];
     if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
+    if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
+        const int2 t = push.tgt[i];
+        if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
+        if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
+    }
+    }
+    if (push.enabled) slab_push_signal(push);
 }
 
 // ---- delta-p + box collision (+ commit): src/Simulate.cpp:90-113 ----
@@ -186,19 +192,18 @@ __device__ __forceinline__ void deltap_pair(const Geom& g, const FluidParams& fp
 }
 
 template <class P, bool POLY6, bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next) {
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     stage_begin(v, cur, d, &bar, stage);
-    if (i >= v.n) return;
-    const int word = v.nbr_cnt[i];
-    const float4 ci = cur[i];
-    if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+    const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    if (word == -1) {
+    } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
         if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
-        return;
-    }
+    } else {
+    const float4 ci = cur[i];
     const Geom& g = v.g;
     const F3 xi = f3(ci);
     const float li = ci.w;
@@ -243,6 +248,13 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
         v.flags_in[i] = v.flags[i];
         v.orig_in[i] = v.orig[i];
     }
+    if (push.enabled) {  // slab mode: the corrected x* of a boundary particle goes straight into the neighbour's ghost slot
+        const int2 t = push.tgt[i];
+        if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
+        if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
+    }
+    }
+    if (push.enabled) slab_push_signal(push);
 }
 
 template <class P, bool POLY6, bool SOLIDS>
@@ -261,14 +273,17 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        if (c->n > 0) k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
-        if (c->slab && !fp.literal_lambda_index) { int st = lgpu_slab_refresh(c, cur); if (st) return st; }  // ghosts' lambda (.w)
+        // slab mode: the kernels store the boundary particles' lambda (.w of cur) / corrected x* (next) into the
+        // neighbours' ghost slots; a one-thread kernel then waits for the neighbours' stores of the same pass
+        SlabPush push = lgpu_slab_push(c, cur, !fp.literal_lambda_index);
+        k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
         lgpu_mark(c, 7);
-        if (c->n == 0) {}  // an empty slab still takes part in the refresh protocol
-        else if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
-        else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        push = lgpu_slab_push(c, next, it < iterations - 1);
+        if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
+        else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
         c->launches += 2;
-        if (c->slab && it < iterations - 1) { int st = lgpu_slab_refresh(c, next); if (st) return st; }        // ghosts' corrected x*
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
         cur = next;
     }
     c->pstar_final = cur;

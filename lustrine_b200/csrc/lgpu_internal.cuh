@@ -77,10 +77,11 @@ struct SlabHeader {
 };
 struct SlabArena {
     SlabHeader* hdr;
+    float4* buf[3];       // x0, pa, pb: the solver's position buffers; neighbours store their boundary
+                          // particles' new values straight into this context's ghost slots
+    int* slotmap[2];      // per ghost held from side s: its sorted slot here (sent to its owner once per substep)
     HaloRec* in_mig[2];   // migrants received from side s
     HaloRec* in_gho[2];   // ghost copies received from side s
-    float4* refresh[2][2];  // [parity][side]: refreshed ghost values (x*, lambda in w), message parity alternates;
-                            // 2 * halo_cap entries: the ghost copies first, then the particles that migrated the other way
 };
 
 struct View {
@@ -191,9 +192,37 @@ static inline void lgpu_mark(lgpu_ctx* c, int phase) {
 }
 
 // ---- slabs ----
-// called by the solver drivers after every pass: pushes the boundary particles' values of `buf` to the
-// neighbouring slabs and applies theirs to this context's ghosts (no-op on a single GPU)
-int lgpu_slab_refresh(lgpu_ctx* c, float4* buf);
+// Fused ghost refresh: the solver kernel that produces a value of a boundary particle also stores it
+// into the neighbouring slab's ghost slot (peer memory over NVLink) and, when its last block is done,
+// raises that neighbour's flag.  Passed by value to the solver kernels; enabled = 0 on a single GPU.
+struct SlabPush {
+    int enabled;
+    const int2* tgt;          // per sorted particle: its slot in the left / right neighbour's buffers, -1 = none
+    float4* peer_buf[2];      // the neighbours' copy of the buffer this kernel writes
+    volatile int* peer_flag[2];
+    unsigned int* ticket;
+    int seq[2];
+};
+// before a solver kernel: the SlabPush for its output buffer (sequence numbers advance);
+// after it: a one-thread kernel that waits until both neighbours' stores of the same pass have landed
+SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable);
+int lgpu_slab_wait(lgpu_ctx* c);
+
+__device__ __forceinline__ void slab_push_signal(const SlabPush& p) {
+    // all threads of the block; the last block of the grid raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *p.ticket = 0;
+            __threadfence_system();
+            if (p.peer_flag[0]) *p.peer_flag[0] = p.seq[0];
+            if (p.peer_flag[1]) *p.peer_flag[1] = p.seq[1];
+            __threadfence_system();
+        }
+    }
+}
 int lgpu_slab_init(lgpu_ctx* c);
 int lgpu_slab_check(lgpu_ctx* c);
 int lgpu_preload_grid(); int lgpu_preload_neighbors(); int lgpu_preload_fluid(); int lgpu_preload_sand();

@@ -152,7 +152,7 @@ __device__ __forceinline__ void stage_begin(const View& v, const float4* __restr
         stage[0] = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.0f);  // dummy: farther than any support radius
     }
     __syncthreads();
-    if (tid == 0 && d.mode == 0 && d.nr > 0) {
+    if (tid == 0 && d.mode == 0 && d.nr > 0 && v.n > 0) {
         uint32_t bytes = 0;
         for (int m = 0; m < d.nr; m++) bytes += (uint32_t)d.len[m] * 16u;
         mbar_expect_tx(bar, bytes);

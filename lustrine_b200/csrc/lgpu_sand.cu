@@ -91,19 +91,18 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
 }
 
 template <class P, bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
+__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     stage_begin(v, cur, d, &bar, stage);
-    if (i >= v.n) return;
-    const int word = v.nbr_cnt[i];
-    const float4 ci = cur[i];
-    if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+    const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    if (word == -1) {
+    } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
         if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
-        return;
-    }
+    } else {
+    const float4 ci = cur[i];
     const Geom& g = v.g;
     const F3 pi = f3(ci);
     const F3 xi_old = f3(v.pos[i]);
@@ -138,6 +137,13 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
         v.flags_in[i] = v.flags[i];
         v.orig_in[i] = v.orig[i];
     }
+    if (push.enabled) {  // slab mode: the new x* of a boundary particle goes straight into the neighbour's ghost slot
+        const int2 t = push.tgt[i];
+        if (t.x >= 0) push.peer_buf[0][t.x] = f4(ps);
+        if (t.y >= 0) push.peer_buf[1][t.y] = f4(ps);
+    }
+    }
+    if (push.enabled) slab_push_signal(push);
 }
 
 // largest fp32 x with sqrt_rn(x) <= d  (so that `sqrt(d2) > d` <=> `d2 > x`, bit-exactly)
@@ -168,6 +174,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
         lgpu_mark(c, 7);
+        SlabPush push = lgpu_slab_push(c, next, !last);
 #define LGPU_SAND_LAUNCH(PP, SS, LL)                                                                                    \
     do {                                                                                                                \
         static bool attr = false;                                                                                       \
@@ -175,7 +182,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
             CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                                \
         }                                                                                                               \
-        if (c->n > 0) k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);           \
+        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next, push);                   \
     } while (0)
         if (p.exact_math) {
             if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
@@ -186,7 +193,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         }
 #undef LGPU_SAND_LAUNCH
         c->launches++;
-        if (c->slab && !last) { int st = lgpu_slab_refresh(c, next); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
         cur = next;
     }
     c->pstar_final = (float4*)cur;

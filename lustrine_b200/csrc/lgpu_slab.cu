@@ -35,7 +35,8 @@ struct SlabState {
     int tx_seq[2], rx_seq[2];
     int n_gho_out[2], n_gho_in[2], n_mig_in[2], n_mig_out[2], in_base[2], mig_in_base[2];
     int* h_counts;        // pinned: [0..7] out_cnt, [8..] SlabHeader
-    int parity;
+    int2* push_tgt;       // per sorted particle: its ghost slot in the left / right neighbour, -1 = none
+    unsigned int* push_ticket;
     bool begun;
     int n_store;
 };
@@ -43,13 +44,13 @@ struct SlabState {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // the same layout on the owner and on its neighbours
-static size_t arena_layout(unsigned char* base, int halo_cap, SlabArena* a) {
+static size_t arena_layout(unsigned char* base, int cap, int halo_cap, SlabArena* a) {
     size_t off = 0;
     a->hdr = (SlabHeader*)(base + off); off += align_up(sizeof(SlabHeader), 256);
+    for (int b = 0; b < 3; b++) { a->buf[b] = (float4*)(base + off); off += align_up(sizeof(float4) * (size_t)cap, 256); }
+    for (int s = 0; s < 2; s++) { a->slotmap[s] = (int*)(base + off); off += align_up(sizeof(int) * 2 * (size_t)halo_cap, 256); }
     for (int s = 0; s < 2; s++) { a->in_mig[s] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
     for (int s = 0; s < 2; s++) { a->in_gho[s] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
-    for (int p = 0; p < 2; p++)
-        for (int s = 0; s < 2; s++) { a->refresh[p][s] = (float4*)(base + off); off += align_up(sizeof(float4) * 2 * (size_t)halo_cap, 256); }
     return off;
 }
 
@@ -60,10 +61,11 @@ int lgpu_slab_init(lgpu_ctx* c) {
     c->slab = S;
     S->halo_cap = c->cfg.halo_capacity > 0 ? c->cfg.halo_capacity : (c->cap / 4 > 65536 ? c->cap / 4 : 65536);
     SlabArena tmp;
-    S->arena_bytes = arena_layout(nullptr, S->halo_cap, &tmp);
+    S->arena_bytes = arena_layout(nullptr, c->cap, S->halo_cap, &tmp);
     CUDA_TRY(cudaMalloc((void**)&S->arena, S->arena_bytes));
     CUDA_TRY(cudaMemsetAsync(S->arena, 0, align_up(sizeof(SlabHeader), 256), c->stream));
-    arena_layout(S->arena, S->halo_cap, &S->local);
+    arena_layout(S->arena, c->cap, S->halo_cap, &S->local);
+    c->x0 = S->local.buf[0]; c->pa = S->local.buf[1]; c->pb = S->local.buf[2];
     for (int s = 0; s < 2; s++) {
         CUDA_TRY(cudaMalloc((void**)&S->out_mig[s], sizeof(HaloRec) * (size_t)S->halo_cap));
         CUDA_TRY(cudaMalloc((void**)&S->out_gho[s], sizeof(HaloRec) * (size_t)S->halo_cap));
@@ -74,6 +76,9 @@ int lgpu_slab_init(lgpu_ctx* c) {
     CUDA_TRY(cudaMalloc((void**)&S->ticket, sizeof(unsigned int) * 2));
     CUDA_TRY(cudaMemsetAsync(S->ticket, 0, sizeof(unsigned int) * 2, c->stream));
     CUDA_TRY(cudaMalloc((void**)&S->inv, sizeof(int) * (size_t)c->cap));
+    CUDA_TRY(cudaMalloc((void**)&S->push_tgt, sizeof(int2) * (size_t)c->cap));
+    CUDA_TRY(cudaMalloc((void**)&S->push_ticket, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(S->push_ticket, 0, sizeof(unsigned int), c->stream));
     CUDA_TRY(cudaMallocHost((void**)&S->h_counts, sizeof(int) * 64));
     // no kernel of the step may be loaded lazily while a neighbour waits for this context (see lgpu_grid.cu)
     int st = lgpu_preload_grid() | lgpu_preload_neighbors() | lgpu_preload_fluid() | lgpu_preload_sand() | lgpu_preload_slab();
@@ -87,7 +92,7 @@ void lgpu_slab_free(lgpu_ctx* c) {
         if (S->peer_ipc[s] && S->peer_base[s]) cudaIpcCloseMemHandle(S->peer_base[s]);
         cudaFree(S->out_mig[s]); cudaFree(S->out_gho[s]); cudaFree(S->gho_src[s]); cudaFree(S->mig_src[s]);
     }
-    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv);
+    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->push_tgt); cudaFree(S->push_ticket);
     cudaFreeHost(S->h_counts);
     delete S;
     c->slab = nullptr;
@@ -131,7 +136,7 @@ extern "C" int lgpu_slab_connect(lgpu_ctx* c, int side, const unsigned char hand
         S->peer_ipc[side] = true;
     }
     S->peer_base[side] = base;
-    arena_layout((unsigned char*)base, S->halo_cap, &S->peer[side]);
+    arena_layout((unsigned char*)base, c->cap, S->halo_cap, &S->peer[side]);
     S->has_nbr[side] = 1;
     return LGPU_OK;
 }
@@ -176,16 +181,33 @@ __global__ void __launch_bounds__(256) k_push_halo(const HaloRec* __restrict__ m
     signal_after_all_blocks(ticket, &dst_hdr->flag[dst_side], seq);
 }
 
-// refresh message: the current values of the particles the neighbour holds as ghosts — those that
-// were sent as ghost copies, then those that migrated in from that neighbour this substep
-__global__ void __launch_bounds__(256) k_push_refresh(const float4* __restrict__ buf, const int* __restrict__ inv, const int* __restrict__ gho_src, int n_gho,
-                                                      int mig_in_base, int n_mig, float4* __restrict__ dst, SlabHeader* dst_hdr, int dst_side,
-                                                      unsigned int* ticket, int seq) {
+// slot-map message, once per substep after the sort: for every ghost this context holds from side s
+// (ghost copies first, then the particles that emigrated to that side), its sorted slot here.  The
+// owner turns it into the per-particle store targets of the fused ghost refresh.
+__global__ void __launch_bounds__(256) k_push_slotmap(const int* __restrict__ inv, int in_base, int n_gho, const int* __restrict__ mig_src, int n_mig,
+                                                      int* __restrict__ dst, SlabHeader* dst_hdr, int dst_side, unsigned int* ticket, int seq) {
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_gho + n_mig; g += gridDim.x * blockDim.x)
-        dst[g] = buf[inv[g < n_gho ? gho_src[g] : mig_in_base + (g - n_gho)]];
+        dst[g] = inv[g < n_gho ? in_base + g : mig_src[g - n_gho]];
     signal_after_all_blocks(ticket, &dst_hdr->flag[dst_side], seq);
 }
+// owner side: particle sent as ghost copy g (or received as migrant g - n_gho) -> its slot in the neighbour
+__global__ void __launch_bounds__(256) k_build_push_tgt(const int* __restrict__ inv, const int* __restrict__ gho_src, int n_gho, int mig_in_base, int n_mig,
+                                                        const int* __restrict__ slotmap, int side, int2* __restrict__ tgt) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_gho + n_mig) return;
+    const int i = inv[g < n_gho ? gho_src[g] : mig_in_base + (g - n_gho)];
+    if (side == 0) tgt[i].x = slotmap[g];
+    else tgt[i].y = slotmap[g];
+}
 
+__global__ void k_wait_flags2(const volatile int* flag0, int expected0, const volatile int* flag1, int expected1, int* error) {
+    const long long t0 = clock64();
+    while ((flag0 && *flag0 < expected0) || (flag1 && *flag1 < expected1)) {
+        if (clock64() - t0 > 20000000000LL) { *error = 1; return; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
 __global__ void k_wait_flag(const volatile int* flag, int expected, int* error) {
     const long long t0 = clock64();
     while (*flag < expected) {
@@ -193,12 +215,6 @@ __global__ void k_wait_flag(const volatile int* flag, int expected, int* error) 
         __nanosleep(200);
     }
     __threadfence_system();
-}
-
-__global__ void __launch_bounds__(256) k_apply_refresh(float4* __restrict__ buf, const int* __restrict__ inv, int in_base, int n_gho,
-                                                       const int* __restrict__ mig_src, int n_mig, const float4* __restrict__ src) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_gho + n_mig) buf[inv[g < n_gho ? in_base + g : mig_src[g - n_gho]]] = src[g];
 }
 
 // inbox -> unsorted storage [n_store, n_store + total), keys + histogram
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_append_halo(View v, int n_store,
 __global__ void k_compact_owned(View v, int n_store, float* __restrict__ pos, float* __restrict__ vel, int* __restrict__ flags, int* __restrict__ ids,
                                 int* __restrict__ counter);
 int lgpu_preload_slab() {
-    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_refresh); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_apply_refresh);
+    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_push_tgt); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_wait_flags2);
     LGPU_PRELOAD(k_append_halo); LGPU_PRELOAD(k_compact_owned);
     return LGPU_OK;
 }
@@ -267,7 +283,6 @@ int lgpu_slab_begin(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     }
     CUDA_TRY(cudaGetLastError());
     S->begun = true;
-    S->parity = 0;
     return LGPU_OK;
 }
 
@@ -318,9 +333,28 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, false);  // particle ids are global: never renumbered
     if (st) return st;
+    // tell the owners where their particles sit here, and learn where mine sit in the neighbours
+    for (int s = 0; s < 2; s++) {
+        if (!S->has_nbr[s]) continue;
+        const int ds = 1 - s, n = S->n_gho_in[s] + S->n_mig_out[s];
+        int blocks = (n + 255) / 256;
+        blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+        k_push_slotmap<<<blocks, 256, 0, c->stream>>>(S->inv, S->in_base[s], S->n_gho_in[s], S->mig_src[s], S->n_mig_out[s], S->peer[s].slotmap[ds],
+                                                      S->peer[s].hdr, ds, S->ticket + s, ++S->tx_seq[s]);
+        c->launches++;
+    }
     lgpu_mark(c, 4);
-    st = lgpu_launch_build_table(c, mode == 2);
+    st = lgpu_launch_build_table(c, mode == 2);  // overlaps the slot-map messages in flight
     if (st) return st;
+    if (c->n > 0) CUDA_TRY(cudaMemsetAsync(S->push_tgt, 0xff, sizeof(int2) * (size_t)c->n, c->stream));
+    for (int s = 0; s < 2; s++) {
+        if (!S->has_nbr[s]) continue;
+        k_wait_flag<<<1, 1, 0, c->stream>>>(&S->local.hdr->flag[s], ++S->rx_seq[s], &S->local.hdr->error);
+        const int n = S->n_gho_out[s] + S->n_mig_in[s];
+        if (n > 0) k_build_push_tgt<<<(n + 255) / 256, 256, 0, c->stream>>>(S->inv, S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s],
+                                                                             S->local.slotmap[s], s, S->push_tgt);
+        c->launches += 2;
+    }
     st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
     if (st) return st;
     lgpu_mark(c, -1);
@@ -328,32 +362,32 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     return LGPU_OK;
 }
 
-int lgpu_slab_refresh(lgpu_ctx* c, float4* buf) {
+SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable) {
+    SlabPush p;
+    memset(&p, 0, sizeof(p));
+    SlabState* S = c->slab;
+    if (!S || !enable || (!S->has_nbr[0] && !S->has_nbr[1])) return p;
+    const int b = out_buf == c->x0 ? 0 : (out_buf == c->pa ? 1 : 2);
+    p.enabled = 1;
+    p.tgt = S->push_tgt;
+    p.ticket = S->push_ticket;
+    for (int s = 0; s < 2; s++) {
+        if (!S->has_nbr[s]) continue;
+        p.peer_buf[s] = S->peer[s].buf[b];
+        p.peer_flag[s] = &S->peer[s].hdr->flag[1 - s];
+        p.seq[s] = ++S->tx_seq[s];
+    }
+    return p;
+}
+
+int lgpu_slab_wait(lgpu_ctx* c) {
     SlabState* S = c->slab;
     if (!S || (!S->has_nbr[0] && !S->has_nbr[1])) return LGPU_OK;
-    lgpu_mark(c, 8);
-    const int par = S->parity;
-    for (int s = 0; s < 2; s++) {
-        if (!S->has_nbr[s]) continue;
-        const int ds = 1 - s, n = S->n_gho_out[s] + S->n_mig_in[s];
-        int blocks = (n + 255) / 256;
-        blocks = blocks < 1 ? 1 : (blocks > 128 ? 128 : blocks);
-        k_push_refresh<<<blocks, 256, 0, c->stream>>>(buf, S->inv, S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s],
-                                                      S->peer[s].refresh[par][ds], S->peer[s].hdr, ds, S->ticket + s, ++S->tx_seq[s]);
-        c->launches++;
-    }
-    for (int s = 0; s < 2; s++) {
-        if (!S->has_nbr[s]) continue;
-        k_wait_flag<<<1, 1, 0, c->stream>>>(&S->local.hdr->flag[s], ++S->rx_seq[s], &S->local.hdr->error);
-        c->launches++;
-        const int n_in = S->n_gho_in[s] + S->n_mig_out[s];
-        if (n_in > 0) {
-            k_apply_refresh<<<(n_in + 255) / 256, 256, 0, c->stream>>>(buf, S->inv, S->in_base[s], S->n_gho_in[s], S->mig_src[s], S->n_mig_out[s],
-                                                                     S->local.refresh[par][s]);
-            c->launches++;
-        }
-    }
-    S->parity ^= 1;
+    const volatile int* f0 = S->has_nbr[0] ? &S->local.hdr->flag[0] : nullptr;
+    const volatile int* f1 = S->has_nbr[1] ? &S->local.hdr->flag[1] : nullptr;
+    const int e0 = S->has_nbr[0] ? ++S->rx_seq[0] : 0, e1 = S->has_nbr[1] ? ++S->rx_seq[1] : 0;
+    k_wait_flags2<<<1, 1, 0, c->stream>>>(f0, e0, f1, e1, &S->local.hdr->error);
+    c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }

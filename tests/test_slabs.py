@@ -108,7 +108,7 @@ dist.all_gather_object(counts, len(S.initial[1]))
 assert sum(counts) == len(pos) and S.ctx.capacity >= max(counts)
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok", counts)
+sys.stdout.write("slab-rank-%d-ok %s\n" % (rank, counts)); sys.stdout.flush()
 '''
 
 
@@ -119,7 +119,7 @@ def test_distributed_host_logic_gloo_world2(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert out.stdout.count("slab-rank-") == 2 and out.stdout.count("-ok") == 2, out.stdout
 
 
 # ------------------------------------------------------------------ the protocol on one GPU
