@@ -352,6 +352,15 @@ def main():
                     help="re-upload the initial scene every R substeps (outside the timed bracket); 0 = free run")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner,
+    # torchrun notices) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -375,7 +384,7 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------- B200 arm ----------------
@@ -394,7 +403,7 @@ def main():
     if world > 1:
         result = run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src, domain, sand, solids, rank, world, local_rank)
         if rank == 0:
-            print(json.dumps(result), flush=True)
+            emit(result)
         dist.barrier()
         dist.destroy_process_group()
         return 0
@@ -541,7 +550,7 @@ def main():
                        "table_overflows": int(counters[1]), "key_violations": int(counters[0])},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": sampler.result()}
-    print(json.dumps(line), flush=True)
+    emit(line)
     G.close()
     return 0
 

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
     if (!(word & LGPU_CNT_GHOST)) {
@@ -161,11 +162,12 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
     if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
+        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
         if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
     }
     }
-    if (push.enabled) slab_push_signal(push);
+    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 // ---- delta-p + box collision (+ commit): src/Simulate.cpp:90-113 ----
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
     if (word == -1) {
@@ -250,11 +253,12 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     }
     if (push.enabled) {  // slab mode: the corrected x* of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
+        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
         if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
     }
     }
-    if (push.enabled) slab_push_signal(push);
+    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 template <class P, bool POLY6, bool SOLIDS>

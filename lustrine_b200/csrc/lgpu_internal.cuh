@@ -208,9 +208,12 @@ struct SlabPush {
 SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable);
 int lgpu_slab_wait(lgpu_ctx* c);
 
-__device__ __forceinline__ void slab_push_signal(const SlabPush& p) {
-    // all threads of the block; the last block of the grid raises the flags
-    __threadfence_system();
+__device__ __forceinline__ void slab_push_signal(const SlabPush& p, bool pushed) {
+    // All threads of the block.  Only the threads that stored into a neighbour's memory pay for the
+    // system-scope fence (MEMBAR.SYS by every thread of every block doubled the kernel time); the
+    // barrier orders them before thread 0's ticket, and the last block of the grid fences again
+    // before it raises the flags (fence cumulativity: store -> fence.sys -> bar -> atom -> atom -> fence.sys -> flag).
+    if (pushed) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(p.ticket, 1u);

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
     if (word == -1) {
@@ -139,11 +140,12 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     }
     if (push.enabled) {  // slab mode: the new x* of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
+        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) push.peer_buf[0][t.x] = f4(ps);
         if (t.y >= 0) push.peer_buf[1][t.y] = f4(ps);
     }
     }
-    if (push.enabled) slab_push_signal(push);
+    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 // largest fp32 x with sqrt_rn(x) <= d  (so that `sqrt(d2) > d` <=> `d2 > x`, bit-exactly)
