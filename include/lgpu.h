@@ -148,6 +148,9 @@ LGPU_API int lgpu_set_use_graph(lgpu_ctx* ctx, int on);
  * its neighbourhood; blocks that need more read their neighbours through L1/L2 instead ("virtual
  * slots").  Clamped to the compiled maximum; results do not depend on it. */
 LGPU_API int lgpu_set_stage_slots(lgpu_ctx* ctx, int slots);
+/* Test hook: 1 = run the fast-arithmetic fluid step with the generic solver kernels (the ones that also
+ * serve exact_math / poly6 / literal_lambda_index) instead of the specialised k_fluid_*_fast pair. */
+LGPU_API int lgpu_set_generic_kernels(lgpu_ctx* ctx, int on);
 
 /* ---- spatial slabs: one context per GPU owns the cell columns [slab_x_lo, slab_x_hi) ----
  * No reference counterpart (the reference is single-threaded); the per-particle arithmetic is the

@@ -188,6 +188,11 @@ extern "C" int lgpu_set_stage_slots(lgpu_ctx* c, int slots) {
     c->stage_slots = slots < LGPU_STAGE_SLOTS ? slots : LGPU_STAGE_SLOTS;
     return LGPU_OK;
 }
+extern "C" int lgpu_set_generic_kernels(lgpu_ctx* c, int on) {
+    if (!c) return LGPU_ERR_ARG;
+    c->generic_kernels = on != 0;
+    return LGPU_OK;
+}
 extern "C" int lgpu_sync(lgpu_ctx* c) {
     if (!c) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));

@@ -26,6 +26,12 @@ struct FluidParams {
     float cA, cB;     // Fast delta-p pass: gradW coefficient = cA*q + cB             (q <= 0.5)
     float kx;         // cubic_k / W(s_corr_dq)
     float mk;         // mass * cubic_k
+    // branch-free inner evaluation of the fast kernels (k_fluid_*_fast), in terms of len = |d| and r2 = len^2:
+    float fA, fB;     // W/cubic_k = 1 + r2 * (len*fA - fB)                    (6c^3, 6c^2, c = kernelFactor/h)
+    float thr2;       // r2 > thr2 <=> q > 0.5: the pair is corrected out of line
+    float fgA;        // lambda pass:  -(m/rho0) * gradW coefficient = len*fgA + gB
+    float fcA;        // delta-p pass: gradW coefficient = len*fcA + cB
+    float xA, xB;     // delta-p pass: W/W(s_corr_dq) = kx + r2 * (len*xA - xB)
     int literal_lambda_index;
 };
 
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     LambdaAcc<P, POLY6> acc;
     acc.init();
     if (!(word & LGPU_CNT_WALK)) {
-        replay_neighbors<SOLIDS, !(P::exact || POLY6)>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK,
+        replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK,
                                                    [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
     } else {
         walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { acc.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     const bool literal = fp.literal_lambda_index != 0;
     F3 f = f3(0.0f, 0.0f, 0.0f);
     if (!(word & LGPU_CNT_WALK)) {
-        replay_neighbors<SOLIDS, !(P::exact || POLY6)>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int t) {
+        replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int t) {
             // :97 — the reference indexes lambdas with the LOOP COUNTER
             float lj;
             if (literal) lj = t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f;
@@ -259,6 +265,235 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     }
     }
     if (push.enabled) slab_push_signal(push, pushed);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Fast-policy kernels of the default configuration (cubic spline, lambdas[neighbour], s_corr_n = 4,
+// table width 32).  Same algebra as above, arranged for the issue-bound inner loop:
+//   * every list neighbour starts the substep at q <= 0.5 (the list predicate r <= h IS q <= 0.5,
+//     SURVEY F3), so the loop evaluates only the inner branch of the spline, branch-free, in terms
+//     of r2 and len (no q): ~20 instructions per neighbour instead of ~40;
+//   * the few neighbours that have drifted beyond q = 0.5 are flagged in a bit mask and corrected
+//     after the loop (true value minus what the loop added);
+//   * padding entries are the particle's own slot: zero separation, every term vanishes;
+//   * the thread's own loads (list length, x*, first five table groups) are issued before the
+//     block-wide prologue so that they overlap the descriptor load and the bulk copies.
+// Rows the table could not hold and blocks in virtual-slot mode take the generic path.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t row_code(const View& v, int i, int k) {
+    const uint2 w = v.nbr16[(size_t)(k >> 2) * v.cap + i];
+    const uint32_t pair = (k & 2) ? w.y : w.x;
+    return (k & 1) ? pair >> 16 : pair & 0xffffu;
+}
+template <bool SOLIDS>
+__device__ __forceinline__ float4 fetch_code(const View& v, const BlkDesc& d, uint32_t stage_addr, uint32_t code) {
+    if (SOLIDS && (code & LGPU_SOLID_CODE)) return v.solid_pos[d.sbase[(code >> 11) & 15] + (int)(code & (LGPU_SOLID_WINDOW - 1))];
+    return lds128(slot_addr(stage_addr, code));
+}
+
+template <bool SOLIDS>
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidParams fp, float4* __restrict__ cur, SlabPush push) {
+    extern __shared__ float4 stage[];
+    __shared__ BlkDesc d;
+    __shared__ uint64_t bar;
+    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    const int ic = i < v.n ? i : 0;
+    bool pushed = false;
+    const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
+    const float4 ci = cur[ic];
+    TableRow<8> row;
+    load_row_early<8, 5>(row, v, ic);
+    stage_begin(v, cur, d, &bar, stage);
+    if (!(word & LGPU_CNT_GHOST)) {
+    const F3 xi = f3(ci);
+    const int cnt = word & LGPU_CNT_MASK;
+    float rho, lam;
+    if (d.mode == 0 && !(word & LGPU_CNT_WALK)) {
+        load_row_rest<8, 5>(row, v, i, cnt);
+        const uint32_t stage_addr = smem_u32(stage);
+        float acc = 0.0f, sum = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        uint32_t far = 0;
+        stage_wait(d, &bar);
+        replay_row<SOLIDS, true, 8>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t, int k) {
+            const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float len = sqrt_approx(r2);
+            acc = fmaf(r2, fmaf(len, fp.fA, -fp.fB), acc);       // sum of W/cubic_k - 1
+            const float gs = fmaf(len, fp.fgA, fp.gB);
+            sum = fmaf(gs * gs, r2, sum);
+            gx = fmaf(-gs, dx, gx); gy = fmaf(-gs, dy, gy); gz = fmaf(-gs, dz, gz);
+            if (r2 > fp.thr2) far |= 1u << k;
+        });
+        while (far) {  // neighbours beyond q = 0.5: replace the inner-branch terms by the true ones
+            const int k = __ffs(far) - 1;
+            far &= far - 1;
+            const float4 pj = fetch_code<SOLIDS>(v, d, stage_addr, row_code(v, i, k));
+            const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float len = sqrt_approx(r2);
+            const float wf = fmaf(r2, fmaf(len, fp.fA, -fp.fB), 1.0f);
+            const float gf = fmaf(len, fp.fgA, fp.gB);
+            float wt, gt;
+            cubic_pair_inner(fp, r2, fp.gA, fp.gB, -fp.neg_mr * fp.l_kfh, wt, gt);
+            acc += wt - wf;
+            sum = fmaf(gt * gt - gf * gf, r2, sum);
+            const float dg = gt - gf;
+            gx = fmaf(-dg, dx, gx); gy = fmaf(-dg, dy, gy); gz = fmaf(-dg, dz, gz);
+        }
+        rho = fmaf(acc + (float)cnt, fp.mk, fp.mass * fp.W_zero);
+        const float Ci = rho * fp.inv_rho0 - 1.0f;
+        sum += gx * gx + gy * gy + gz * gz;
+        lam = sum > 0.0f ? __fdividef(-Ci, sum + fp.eps) : 0.0f;
+    } else {
+        LambdaAcc<Fast, false> a;
+        a.init();
+        const Geom& g = v.g;
+        if (!(word & LGPU_CNT_WALK)) {
+            replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, cnt, [&](float4 pj, uint32_t, int) { a.pair(g, fp, xi, f3(pj)); });
+        } else {
+            walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { a.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
+        }
+        lam = a.finish(fp);
+        rho = a.rho;
+    }
+    v.density[i] = rho;
+    v.lambda[i] = lam;
+    reinterpret_cast<float*>(cur + i)[3] = lam;
+    if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
+        const int2 t = push.tgt[i];
+        pushed = t.x >= 0 || t.y >= 0;
+        if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
+        if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
+    }
+    }
+    if (push.enabled) slab_push_signal(push, pushed);
+}
+
+template <bool SOLIDS, bool LAST>
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+    extern __shared__ float4 stage[];
+    __shared__ BlkDesc d;
+    __shared__ uint64_t bar;
+    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
+    const int ic = i < v.n ? i : 0;
+    bool pushed = false;
+    const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    const float4 ci = cur[ic];
+    TableRow<8> row;
+    load_row_early<8, 5>(row, v, ic);
+    stage_begin(v, cur, d, &bar, stage);
+    if (word == -1) {
+    } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+        if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
+    } else {
+    const Geom& g = v.g;
+    const F3 xi = f3(ci);
+    const float li = ci.w;
+    const int cnt = word & LGPU_CNT_MASK;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    if (d.mode == 0 && !(word & LGPU_CNT_WALK)) {
+        load_row_rest<8, 5>(row, v, i, cnt);
+        const uint32_t stage_addr = smem_u32(stage);
+        uint32_t far = 0;
+        stage_wait(d, &bar);
+        replay_row<SOLIDS, true, 8>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t code, int k) {
+            const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float len = sqrt_approx(r2);
+            const float x = fmaf(r2, fmaf(len, fp.xA, -fp.xB), fp.kx);   // W / W(s_corr_dq)
+            const float x2 = x * x;
+            const float lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
+            const float w = fmaf(-fp.s_corr_k, x2 * x2, li + lj) * fmaf(len, fp.fcA, fp.cB);
+            fx = fmaf(w, dx, fx); fy = fmaf(w, dy, fy); fz = fmaf(w, dz, fz);
+            if (r2 > fp.thr2) far |= 1u << k;
+        });
+        while (far) {
+            const int k = __ffs(far) - 1;
+            far &= far - 1;
+            const uint32_t code = row_code(v, i, k);
+            const float4 pj = fetch_code<SOLIDS>(v, d, stage_addr, code);
+            const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float len = sqrt_approx(r2);
+            const float lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
+            const float xf = fmaf(r2, fmaf(len, fp.xA, -fp.xB), fp.kx);
+            const float xf2 = xf * xf;
+            const float wf = fmaf(-fp.s_corr_k, xf2 * xf2, li + lj) * fmaf(len, fp.fcA, fp.cB);
+            float wp, cf;
+            cubic_pair_inner(fp, r2, fp.cA, fp.cB, -fp.l_kfh, wp, cf);
+            const float xt = wp * fp.kx;
+            const float xt2 = xt * xt;
+            const float dw = fmaf(-fp.s_corr_k, xt2 * xt2, li + lj) * cf - wf;
+            fx = fmaf(dw, dx, fx); fy = fmaf(dw, dy, fy); fz = fmaf(dw, dz, fz);
+        }
+    } else {
+        F3 f = f3(0.0f, 0.0f, 0.0f);
+        if (!(word & LGPU_CNT_WALK)) {
+            replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, cnt, [&](float4 pj, uint32_t code, int) {
+                const float lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
+                deltap_pair<Fast, false>(g, fp, xi, f3(pj), li, lj, f);
+            });
+        } else {
+            walk<false>(v, i, f3(v.x0[i]), [&](int j, int) {
+                deltap_pair<Fast, false>(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]), li, j >= 0 ? v.lambda[j] : 0.0f, f);
+            });
+        }
+        fx = f.x; fy = f.y; fz = f.z;
+    }
+    F3 p = f3(fmaf(fx, fp.inv_rho0, xi.x), fmaf(fy, fp.inv_rho0, xi.y), fmaf(fz, fp.inv_rho0, xi.z));
+    const float r = g.radius;
+    p.x = resolve_collision(p.x, r, __fsub_rn((float)g.idomX, r));                 // :106-108
+    p.y = resolve_collision(p.y, r, __fsub_rn((float)g.idomY, r));
+    p.z = resolve_collision(p.z, r, __fsub_rn((float)g.idomZ, r));
+    next[i] = f4(p);
+    if (LAST) {  // :110-111, always Exact (v and x feed the next step's keys); written to the step-boundary storage
+        F3 xo = f3(v.pos[i]);
+        v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(p, xo), fp.dt));
+        v.pos_in[i] = f4(p);
+        v.flags_in[i] = v.flags[i];
+        v.orig_in[i] = v.orig[i];
+    }
+    if (push.enabled) {
+        const int2 t = push.tgt[i];
+        pushed = t.x >= 0 || t.y >= 0;
+        if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
+        if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
+    }
+    }
+    if (push.enabled) slab_push_signal(push, pushed);
+}
+
+template <bool SOLIDS>
+static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
+    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
+    const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda_fast<SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    float4* cur = c->x0;
+    float4* bufs[2] = {c->pa, c->pb};
+    for (int it = 0; it < iterations; it++) {
+        float4* next = bufs[it & 1];
+        lgpu_mark(c, 6);
+        SlabPush push = lgpu_slab_push(c, cur, true);
+        k_fluid_lambda_fast<SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        lgpu_mark(c, 7);
+        push = lgpu_slab_push(c, next, it < iterations - 1);
+        if (it == iterations - 1) k_fluid_deltap_fast<SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
+        else k_fluid_deltap_fast<SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
+        c->launches += 2;
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        cur = next;
+    }
+    c->pstar_final = cur;
+    CUDA_TRY(cudaGetLastError());
+    return LGPU_OK;
 }
 
 template <class P, bool POLY6, bool SOLIDS>
@@ -341,6 +576,10 @@ FluidParams lgpu_make_fluid_params(const Geom& g, const lgpu_step_params& p) {
     fp.gA = fp.neg_mr * fp.cA; fp.gB = fp.neg_mr * fp.cB;
     fp.kx = g.cubic_k / fp.W_dq;
     fp.mk = p.mass * g.cubic_k;
+    fp.fA = 6.0f * fp.c_q * fp.c_q * fp.c_q; fp.fB = 6.0f * fp.c_q * fp.c_q;
+    fp.thr2 = (0.5f / fp.c_q) * (0.5f / fp.c_q);
+    fp.fgA = fp.gA * fp.c_q; fp.fcA = fp.cA * fp.c_q;
+    fp.xA = fp.kx * fp.fA; fp.xB = fp.kx * fp.fB;
     fp.literal_lambda_index = p.literal_lambda_index;
     return fp;
 }
@@ -353,6 +592,8 @@ int lgpu_launch_fluid_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     const bool solids = c->n_solid > 0;
     if (p.sph_kernel == 1) return solids ? run_fluid<Exact, true, true>(c, v, fp, K) : run_fluid<Exact, true, false>(c, v, fp, K);
     if (p.exact_math) return solids ? run_fluid<Exact, false, true>(c, v, fp, K) : run_fluid<Exact, false, false>(c, v, fp, K);
+    if (!p.literal_lambda_index && p.s_corr_n == 4.0f && c->M == 32 && !c->generic_kernels)
+        return solids ? run_fluid_fast<true>(c, v, fp, K) : run_fluid_fast<false>(c, v, fp, K);
     return solids ? run_fluid<Fast, false, true>(c, v, fp, K) : run_fluid<Fast, false, false>(c, v, fp, K);
 }
 
@@ -413,6 +654,9 @@ template <class P, bool POLY6, bool SOLIDS> static int preload_fluid_variant() {
 }
 int lgpu_preload_fluid() {
     int st = 0;
+    LGPU_PRELOAD(k_fluid_lambda_fast<true>); LGPU_PRELOAD(k_fluid_lambda_fast<false>);
+    LGPU_PRELOAD((k_fluid_deltap_fast<true, true>)); LGPU_PRELOAD((k_fluid_deltap_fast<true, false>));
+    LGPU_PRELOAD((k_fluid_deltap_fast<false, true>)); LGPU_PRELOAD((k_fluid_deltap_fast<false, false>));
     st |= preload_fluid_variant<Exact, true, true>(); st |= preload_fluid_variant<Exact, true, false>();
     st |= preload_fluid_variant<Exact, false, true>(); st |= preload_fluid_variant<Exact, false, false>();
     st |= preload_fluid_variant<Fast, false, true>(); st |= preload_fluid_variant<Fast, false, false>();

@@ -130,6 +130,7 @@ struct lgpu_ctx {
     int n, n_owned, n_solid, n_solid_uploaded, cap, cap_solid, M;
     int n_in, n_ghost;
     int stage_slots;      // blocks whose neighbourhood needs more stage slots use virtual slots (<= LGPU_STAGE_SLOTS)
+    bool generic_kernels; // test hook: run the fast-arithmetic fluid step with the generic kernels (lgpu_set_generic_kernels)
     bool grid_valid;      // cell_start/key describe the current storage
     bool solids_sorted;
     // device buffers (see View)

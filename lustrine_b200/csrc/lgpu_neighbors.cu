@@ -69,29 +69,42 @@ __global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks, in
 // ------------------------------------------------------------------------------------------
 // table build
 // ------------------------------------------------------------------------------------------
-// Appends 16-bit codes to a table row: four consecutive codes share one 8-byte group, groups are
-// strided by the capacity (nbr16 layout in lgpu_internal.cuh).
+// Appends 16-bit codes to a table row.  Four consecutive codes share one 8-byte group and the groups
+// are strided by the capacity (nbr16 layout in lgpu_internal.cuh): the codes are packed in a 64-bit
+// shift register and every fourth emit stores one group — coalesced across the warp.
 struct RowWriter {
-    unsigned short* base;  // code 0 of this particle's row
-    uint32_t idx;          // offset of the next code
-    uint32_t jump;         // distance between two groups of the same particle, in codes, minus 3
+    uint2* col;       // next group of this particle's row
+    size_t stride;    // capacity
+    uint32_t lo, hi;  // shift register: after four emits lo = c0 | c1 << 16, hi = c2 | c3 << 16
     int M, cnt;
     bool bad;
     __device__ __forceinline__ void init(const View& v, int i) {
-        base = reinterpret_cast<unsigned short*>(v.nbr16 + i);
-        idx = 0;
-        jump = (uint32_t)v.cap * 4u - 3u;
+        col = v.nbr16 + i;
+        stride = (size_t)v.cap;
+        lo = hi = 0;
         M = v.M; cnt = 0; bad = false;
+    }
+    __device__ __forceinline__ void shift_in(uint32_t code) {
+        lo = __byte_perm(lo, hi, 0x5432);    // (lo >> 16) | (hi << 16)
+        hi = __byte_perm(hi, code, 0x5432);  // (hi >> 16) | (code << 16)
     }
     __device__ __forceinline__ void emit(uint32_t code) {
         if (cnt < M) {
-            base[idx] = (unsigned short)code;
-            idx += (cnt & 3) == 3 ? jump : 1u;
+            shift_in(code);
+            if ((cnt & 3) == 3) { *col = make_uint2(lo, hi); col += stride; }
         }
         cnt++;
     }
-    __device__ __forceinline__ void finish() {  // pad the last group with the dummy code
-        if (cnt < M) for (int k = cnt & 3; k != 0 && k < 4; k++) base[idx++] = 0;
+    __device__ __forceinline__ void emit_unchecked(uint32_t code) {  // the caller has checked cnt + (codes to come) <= M
+        shift_in(code);
+        if ((cnt & 3) == 3) { *col = make_uint2(lo, hi); col += stride; }
+        cnt++;
+    }
+    __device__ __forceinline__ void finish(uint32_t pad) {  // completes the last group with the padding code
+        if (cnt < M && (cnt & 3)) {
+            for (int k = cnt & 3; k < 4; k++) shift_in(pad);
+            *col = make_uint2(lo, hi);
+        }
     }
 };
 
@@ -100,12 +113,12 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
-    // per thread and stencil column: candidate range [lo, hi) in stage slots, replaced by the 32-bit
-    // hit mask once the column has been tested; lo16 keeps the range start for the emit phase
-    __shared__ uint32_t seg[9][LGPU_TILE];
-    __shared__ unsigned short lo16[9][LGPU_TILE];
     const int tid = threadIdx.x;
     const int i = blockIdx.x * LGPU_TILE + tid;
+    const int ic = i < v.n ? i : 0;
+    // the thread's own loads first: they overlap the descriptor load and the bulk copies
+    const float4 x0i = v.x0[ic];
+    const int key = v.key[ic];
     stage_begin(v, v.x0, d, &bar, stage);
     if (i >= v.n) return;
     const Geom& g = v.g;
@@ -113,8 +126,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
         v.nbr_cnt[i] = LGPU_CNT_GHOST;
         return;
     }
-    const F3 xi = f3(v.x0[i]);
-    const int key = v.key[i];
+    const F3 xi = f3(x0i);
     RowWriter w;
     w.init(v, i);
 
@@ -127,79 +139,68 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
         return;
     }
 
+    // per stencil column: first candidate (stage slot) and number of candidates — the three cells
+    // z-1..z+1 of a column are contiguous in the sorted storage
     const CellCoord c = decode_cell(g, key);
     const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
+    uint32_t first[9];
+    int ncand[9];
     bool slow = false;  // solids in the 27 cells, or a column with more than 32 candidates
 #pragma unroll
     for (int r = 0; r < 9; r++) {
         const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
-        uint32_t s = 0;
+        first[r] = 0; ncand[r] = 0;
         if (y >= 0 && y < g.gY && x >= 0 && x < g.gX) {
             const int base = y * g.gXZ + x * g.gZ;
             const int b = v.cell_start[base + zlo], e = v.cell_start[base + zhi + 1];
-            if (e > b) s = (uint32_t)(d.slotbase[r] + b) | ((uint32_t)(d.slotbase[r] + e) << 16);
+            first[r] = (uint32_t)(d.slotbase[r] + b);
+            ncand[r] = e - b;
             if (e - b > 32) slow = true;
             if (v.n_solid && v.solid_cell_start[base + zhi + 1] > v.solid_cell_start[base + zlo]) slow = true;
         }
-        seg[r][tid] = s;
-        lo16[r][tid] = (unsigned short)(s & 0xffffu);
     }
+    const uint32_t self_code = (uint32_t)(d.slotbase[4] + i);
     stage_wait(d, &bar);
 
     if (!slow) {
         // No solid in the 27 cells: the reference order is simply ascending sorted slot over the 9
-        // columns (fluid: self included; sand: self skipped — SURVEY F7).
-        // Phase 1: one flattened loop over the thread's own candidate ranges (lanes with different
-        // range lengths do not idle); the hits of a column are collected in a 32-bit mask.
-        if (d.mode == 0) {
-            const uint32_t stage_addr = smem_u32(stage);
-            int r = 0;
-            uint32_t s = seg[0][tid];
-            uint32_t a = stage_addr + (s & 0xffffu) * 16u, aend = stage_addr + (s >> 16) * 16u, hits = 0, bit = 1;
-            while (true) {
-                while (a >= aend) {
-                    seg[r][tid] = hits;
-                    if (++r == 9) goto emit_phase;
-                    s = seg[r][tid];
-                    a = stage_addr + (s & 0xffffu) * 16u; aend = stage_addr + (s >> 16) * 16u; hits = 0; bit = 1;
+        // columns (fluid: self included; sand: self skipped — SURVEY F7).  Per column: test the
+        // candidates with the Exact predicate into a 32-bit hit mask, then emit the hits.
+        const uint32_t stage_addr = smem_u32(stage);
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            const int n = ncand[r];
+            if (n == 0) continue;
+            // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at
+            // bit n-1-t.  The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has
+            // the exact sign and is +0 on equality), so a test costs the 8 separately rounded
+            // operations of the reference's predicate plus one FADD and one funnel shift.
+            uint32_t out = 0;
+            if (d.mode == 0) {
+                const uint32_t a = slot_addr(stage_addr, first[r]);
+#pragma unroll 4
+                for (int t = 0; t < n; t++) {
+                    const float4 pj = lds128(a + 16u * (uint32_t)t);
+                    const F3 dd = vsub<Exact>(xi, f3(pj));
+                    out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
                 }
-                const float4 pj = lds128(a);
-                if (within_h(g, xi, f3(pj))) hits |= bit;
-                bit += bit;
-                a += 16u;
+            } else {
+                // virtual-slot mode: same codes, candidates read from the global storage
+                const float4* vsrc = v.x0 + ((int)first[r] - d.slotbase[r]);
+                for (int t = 0; t < n; t++) {
+                    const F3 dd = vsub<Exact>(xi, f3(vsrc[t]));
+                    out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
+                }
             }
-        } else {
-            // virtual-slot mode: same codes, candidates read from the global storage
-            int r = 0;
-            uint32_t s = seg[0][tid];
-            uint32_t u = s & 0xffffu, end = s >> 16, u0 = u, hits = 0;
-            const float4* vsrc = v.x0 - d.slotbase[0];  // slot -> sorted particle of column r
-            while (true) {
-                while (u >= end) {
-                    seg[r][tid] = hits;
-                    if (++r == 9) goto emit_phase;
-                    s = seg[r][tid];
-                    u = s & 0xffffu; end = s >> 16; u0 = u; hits = 0;
-                    vsrc = v.x0 - d.slotbase[r];
-                }
-                hits |= (within_h(g, xi, f3(vsrc[u])) ? 1u : 0u) << (u - u0);
-                u++;
-            }
-        }
-    emit_phase:
-        // Phase 2: one flattened loop over the hits.
-        if (SAND) seg[4][tid] &= ~(1u << ((uint32_t)(d.slotbase[4] + i) - (uint32_t)lo16[4][tid]));
-        {
-            int r = 0;
-            uint32_t m = seg[0][tid], base = lo16[0][tid];
-            while (true) {
-                while (m == 0) {
-                    if (++r == 9) goto done;
-                    m = seg[r][tid]; base = lo16[r][tid];
-                }
-                const uint32_t t = __ffs(m) - 1;
-                m &= m - 1;
-                w.emit(base + t);
+            uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
+            const uint32_t top = first[r] + (uint32_t)(n - 1);  // code of bit k = top - k
+            if (SAND && r == 4) m &= ~(1u << (top - self_code));
+            const int hits = __popc(m);
+            if (w.cnt + hits > w.M) { w.cnt += hits; w.bad = true; continue; }  // row too long: the solver passes re-walk
+            while (m) {  // ascending candidate = descending bit
+                const uint32_t k = 31u - (uint32_t)__clz(m);
+                m ^= 1u << k;
+                w.emit_unchecked(top - k);
             }
         }
     } else {
@@ -214,8 +215,9 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
             }
         });
     }
-done:
-    w.finish();
+    // padding: sand = the far-away dummy (no contact); fluid = the particle itself (zero separation:
+    // every term of the branch-free fluid bodies vanishes)
+    w.finish(SAND ? 0u : self_code);
     int word = w.cnt;
     if (w.cnt > w.M || w.bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
     v.nbr_cnt[i] = word;

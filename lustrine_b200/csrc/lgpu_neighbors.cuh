@@ -184,11 +184,19 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return r;
 }
 
+// shared address of stage slot `code`: one IMAD (the compiler's own shift/mask/add sequence takes three)
+__device__ __forceinline__ uint32_t slot_addr(uint32_t stage_addr, uint32_t code) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a) : "r"(code), "r"(stage_addr));
+    return a;
+}
+
 // Replays the table row of particle i (cnt entries).  body(pj, code, k): pj = position (and .w payload)
 // of the k-th neighbour, read from the stage (sand; from `src` through L1/L2 when the block is in
 // virtual-slot mode) or from the sorted solid array.
-// PAD = true: the row is processed in whole groups of four; the padding codes are 0 = the far-away
-// dummy, which every fast-arithmetic body maps to a zero contribution.
+// PAD = true: the row is processed in whole groups of four.  The padding codes of a SAND table are
+// 0 = the far-away dummy (no contact); those of a FLUID table are the particle's own slot, whose
+// zero separation makes every term of the branch-free fluid bodies vanish (lgpu_fluid.cu).
 // The whole row (MG groups of four codes) is loaded up front — before the caller waits for the
 // stage — so that the table traffic overlaps the bulk copies.
 template <int MG>
@@ -205,6 +213,25 @@ struct TableRow {
     }
 };
 
+// Row load that does not wait for the list length: the first EARLY groups are fetched
+// unconditionally (stale codes beyond the list are never replayed), the rest once cnt is known.
+template <int MG, int EARLY>
+__device__ __forceinline__ void load_row_early(TableRow<MG>& row, const View& v, int i) {
+    const uint2* __restrict__ col = v.nbr16 + i;
+#pragma unroll
+    for (int g = 0; g < EARLY; g++) row.w[g] = col[(size_t)g * v.cap];
+}
+template <int MG, int EARLY>
+__device__ __forceinline__ void load_row_rest(TableRow<MG>& row, const View& v, int i, int cnt) {
+    const uint2* __restrict__ col = v.nbr16 + i;
+    const int ng = (cnt + 3) >> 2;
+#pragma unroll
+    for (int g = EARLY; g < MG; g++) {
+        row.w[g] = make_uint2(0u, 0u);
+        if (g < ng) row.w[g] = col[(size_t)g * v.cap];
+    }
+}
+
 template <bool SOLIDS, bool PAD, int MG, class Body>
 __device__ __forceinline__ void replay_row(const View& v, const BlkDesc& d, const TableRow<MG>& row, uint32_t stage_addr,
                                            const float4* __restrict__ src, int cnt, Body&& body) {
@@ -220,7 +247,7 @@ __device__ __forceinline__ void replay_row(const View& v, const BlkDesc& d, cons
                     if (!PAD && k >= cnt) break;
                     float4 pj;
                     if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
-                    else pj = lds128(stage_addr + code[q] * 16u);
+                    else pj = lds128(slot_addr(stage_addr, code[q]));
                     body(pj, code[q], k);
                 }
             }
@@ -261,7 +288,7 @@ __device__ __forceinline__ void replay_table(const View& v, const BlkDesc& d, ui
                 if (!PAD && k >= cnt) break;
                 float4 pj;
                 if (SOLIDS && (code[q] & LGPU_SOLID_CODE)) pj = v.solid_pos[d.sbase[(code[q] >> 11) & 15] + (int)(code[q] & (LGPU_SOLID_WINDOW - 1))];
-                else pj = lds128(stage_addr + code[q] * 16u);
+                else pj = lds128(slot_addr(stage_addr, code[q]));
                 body(pj, code[q], k);
             }
             w = wn;

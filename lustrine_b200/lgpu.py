@@ -51,7 +51,7 @@ SYMBOLS = [
     "lgpu_default_step_params", "lgpu_create", "lgpu_destroy", "lgpu_last_error", "lgpu_get_grid",
     "lgpu_upload_sand", "lgpu_upload_solids", "lgpu_append_sand", "lgpu_download_sand", "lgpu_num_sand",
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
-    "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_set_stage_slots", "lgpu_cell_count",
+    "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
     "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_upload", "lgpu_slab_download",
     "lgpu_slab_step_begin", "lgpu_slab_step_end",
@@ -90,6 +90,7 @@ def lib():
         L.lgpu_set_phase_timing.argtypes = [vp, c_i]
         L.lgpu_set_use_graph.argtypes = [vp, c_i]
         L.lgpu_set_stage_slots.argtypes = [vp, c_i]
+        L.lgpu_set_generic_kernels.argtypes = [vp, c_i]
         L.lgpu_cell_count.argtypes = [vp, C.POINTER(c_i * 3), C.POINTER(c_i * 3), c_i, C.POINTER(c_i)]
         L.lgpu_remove_in_cells.argtypes = [vp, vp, c_i, C.POINTER(c_i)]
         L.lgpu_aabb_first_k.argtypes = [vp, C.POINTER(c_f * 3), C.POINTER(c_f * 3), c_i, vp, C.POINTER(c_i)]
@@ -249,6 +250,9 @@ class Context:
 
     def set_stage_slots(self, slots):
         _check(self.L.lgpu_set_stage_slots(self._h, int(slots)), "lgpu_set_stage_slots")
+
+    def set_generic_kernels(self, on):
+        _check(self.L.lgpu_set_generic_kernels(self._h, int(on)), "lgpu_set_generic_kernels")
 
     def set_use_graph(self, on):
         _check(self.L.lgpu_set_use_graph(self._h, int(on)), "lgpu_set_use_graph")

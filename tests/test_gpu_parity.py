@@ -169,6 +169,43 @@ def test_fluid_modes(iterations, literal, exact):
     G.close(); P.close()
 
 
+@pytest.mark.parametrize("with_solids,generic,slots", [(False, False, 0), (True, False, 0), (True, True, 0), (True, False, 600), (False, False, 40)])
+def test_fluid_fast_kernels(with_solids, generic, slots):
+    """Throughput arithmetic (exact_math=0), 4 iterations, lambdas[neighbour]: the specialised
+    k_fluid_*_fast pair (branch-free inner spline + out-of-line correction of the neighbours that drifted
+    beyond q = 0.5) and the generic kernels (test hook) both stay within the parity tolerance, also when
+    the blocks run in virtual-slot / re-walk mode."""
+    domain, sand = scenes.dam_break(16)
+    P, G = make_pair(domain, sand, scenes.floor_plate(30, 20) if with_solids else None)
+    G.set_generic_kernels(generic)
+    if slots:
+        G.set_stage_slots(slots)
+    for step in range(4):
+        print("substep", step)
+        compare_fluid_substep(P, G, 4, False, False)
+    G.close(); P.close()
+
+
+def test_fluid_fast_matches_generic_on_a_moving_scene():
+    """Fast vs generic kernels on a scene with sideways motion (many neighbours cross q = 0.5 inside a
+    substep, which exercises the out-of-line correction): 5 substeps, the fast context teacher-forced to
+    the generic context's state before each one, same tolerance as the oracle parity."""
+    domain, sand = scenes.dam_break(24)
+    vel = np.zeros_like(sand)
+    vel[:, 0] = 6.0 * np.sin(sand[:, 2]); vel[:, 2] = 6.0 * np.cos(sand[:, 0])
+    kw = dict(dt=0.01, iterations=4, literal_lambda_index=0, exact_math=0)
+    with lgpu.Context(domain, capacity_sand=len(sand)) as A, lgpu.Context(domain, capacity_sand=len(sand)) as B:
+        B.set_generic_kernels(1)
+        pos = sand
+        for step in range(5):
+            A.upload_sand(pos, vel); B.upload_sand(pos, vel)
+            A.step_fluid(**kw); B.step_fluid(**kw)
+            pa, va, _ = A.download(); pos, vel, _ = B.download()
+            print("substep", step)
+            close(A.dump(lgpu.DUMP_LAMBDA), B.dump(lgpu.DUMP_LAMBDA), "lambda", atol=1e-7)
+            close(pa, pos, "position")
+
+
 def test_fluid_table_overflow_falls_back_to_walk():
     domain, sand = scenes.dam_break(12)
     P, G = make_pair(domain, sand, max_neighbors=6)
