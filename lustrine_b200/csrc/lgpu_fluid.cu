@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
+    if (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK)) stage_wait(&bar);  // (the table path waits after its row loads)
     if (!(word & LGPU_CNT_GHOST)) {
     const Geom& g = v.g;
     const F3 xi = f3(cur[i]);
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
     if (word == -1) {
     } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
         if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
@@ -281,19 +283,47 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
 //     block-wide prologue so that they overlap the descriptor load and the bulk copies.
 // Rows the table could not hold and blocks in virtual-slot mode take the generic path.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t row_code(const View& v, int i, int k) {
-    const uint2 w = v.nbr16[(size_t)(k >> 2) * v.cap + i];
-    const uint32_t pair = (k & 2) ? w.y : w.x;
-    return (k & 1) ? pair >> 16 : pair & 0xffffu;
-}
 template <bool SOLIDS>
 __device__ __forceinline__ float4 fetch_code(const View& v, const BlkDesc& d, uint32_t stage_addr, uint32_t code) {
     if (SOLIDS && (code & LGPU_SOLID_CODE)) return v.solid_pos[d.sbase[(code >> 11) & 15] + (int)(code & (LGPU_SOLID_WINDOW - 1))];
     return lds128(slot_addr(stage_addr, code));
 }
 
+// out-of-line paths of the fast kernels: virtual-slot tiles and rows the table could not hold
 template <bool SOLIDS>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidParams fp, float4* __restrict__ cur, SlabPush push) {
+__device__ __noinline__ float2 lambda_slow(const View& v, const FluidParams& fp, const BlkDesc& d, uint32_t stage_addr, const float4* __restrict__ cur,
+                                           int i, int word, F3 xi) {
+    LambdaAcc<Fast, false> a;
+    a.init();
+    const Geom& g = v.g;
+    if (!(word & LGPU_CNT_WALK)) {
+        replay_table<SOLIDS, false>(v, d, stage_addr, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t, int) { a.pair(g, fp, xi, f3(pj)); });
+    } else {
+        walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { a.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
+    }
+    const float lam = a.finish(fp);
+    return make_float2(a.rho, lam);
+}
+template <bool SOLIDS>
+__device__ __noinline__ float3 deltap_slow(const View& v, const FluidParams& fp, const BlkDesc& d, uint32_t stage_addr, const float4* __restrict__ cur,
+                                           int i, int word, F3 xi, float li) {
+    const Geom& g = v.g;
+    F3 f = f3(0.0f, 0.0f, 0.0f);
+    if (!(word & LGPU_CNT_WALK)) {
+        replay_table<SOLIDS, false>(v, d, stage_addr, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+            const float lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
+            deltap_pair<Fast, false>(g, fp, xi, f3(pj), li, lj, f);
+        });
+    } else {
+        walk<false>(v, i, f3(v.x0[i]), [&](int j, int) {
+            deltap_pair<Fast, false>(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]), li, j >= 0 ? v.lambda[j] : 0.0f, f);
+        });
+    }
+    return make_float3(f.x, f.y, f.z);
+}
+
+template <bool SOLIDS>
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, float4* __restrict__ cur, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -305,17 +335,18 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidPa
     TableRow<8> row;
     load_row_early<8, 5>(row, v, ic);
     stage_begin(v, cur, d, &bar, stage);
+    const int cnt = word & LGPU_CNT_MASK;
+    const bool table = !(word & (LGPU_CNT_GHOST | LGPU_CNT_WALK));
+    if (table) load_row_rest<8, 5>(row, v, i, cnt);
+    stage_wait(&bar);
     if (!(word & LGPU_CNT_GHOST)) {
     const F3 xi = f3(ci);
-    const int cnt = word & LGPU_CNT_MASK;
+    const uint32_t stage_addr = smem_u32(stage);
     float rho, lam;
-    if (d.mode == 0 && !(word & LGPU_CNT_WALK)) {
-        load_row_rest<8, 5>(row, v, i, cnt);
-        const uint32_t stage_addr = smem_u32(stage);
+    if (d.mode == 0 && table) {
         float acc = 0.0f, sum = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
         uint32_t far = 0;
-        stage_wait(d, &bar);
-        replay_row<SOLIDS, true, 8>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t, int k) {
+        replay_row<SOLIDS, true, 8, true>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t, int k) {
             const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const float len = sqrt_approx(r2);
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidPa
         while (far) {  // neighbours beyond q = 0.5: replace the inner-branch terms by the true ones
             const int k = __ffs(far) - 1;
             far &= far - 1;
-            const float4 pj = fetch_code<SOLIDS>(v, d, stage_addr, row_code(v, i, k));
+            const float4 pj = fetch_code<SOLIDS>(v, d, stage_addr, row_code_reg(row, k));
             const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const float len = sqrt_approx(r2);
@@ -346,16 +377,8 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidPa
         sum += gx * gx + gy * gy + gz * gz;
         lam = sum > 0.0f ? __fdividef(-Ci, sum + fp.eps) : 0.0f;
     } else {
-        LambdaAcc<Fast, false> a;
-        a.init();
-        const Geom& g = v.g;
-        if (!(word & LGPU_CNT_WALK)) {
-            replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, cnt, [&](float4 pj, uint32_t, int) { a.pair(g, fp, xi, f3(pj)); });
-        } else {
-            walk<false>(v, i, f3(v.x0[i]), [&](int j, int) { a.pair(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j])); });
-        }
-        lam = a.finish(fp);
-        rho = a.rho;
+        const float2 r = lambda_slow<SOLIDS>(v, fp, d, stage_addr, cur, i, word, xi);
+        rho = r.x; lam = r.y;
     }
     v.density[i] = rho;
     v.lambda[i] = lam;
@@ -371,7 +394,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(View v, FluidPa
 }
 
 template <bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -383,6 +406,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidPa
     TableRow<8> row;
     load_row_early<8, 5>(row, v, ic);
     stage_begin(v, cur, d, &bar, stage);
+    const int cnt = word & LGPU_CNT_MASK;
+    const bool table = word != -1 && !(word & (LGPU_CNT_GHOST | LGPU_CNT_WALK));
+    if (table) load_row_rest<8, 5>(row, v, i, cnt);
+    stage_wait(&bar);
     if (word == -1) {
     } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
         if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
@@ -390,14 +417,11 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidPa
     const Geom& g = v.g;
     const F3 xi = f3(ci);
     const float li = ci.w;
-    const int cnt = word & LGPU_CNT_MASK;
+    const uint32_t stage_addr = smem_u32(stage);
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    if (d.mode == 0 && !(word & LGPU_CNT_WALK)) {
-        load_row_rest<8, 5>(row, v, i, cnt);
-        const uint32_t stage_addr = smem_u32(stage);
+    if (d.mode == 0 && table) {
         uint32_t far = 0;
-        stage_wait(d, &bar);
-        replay_row<SOLIDS, true, 8>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t code, int k) {
+        replay_row<SOLIDS, true, 8, true>(v, d, row, stage_addr, cur, cnt, [&](float4 pj, uint32_t code, int k) {
             const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             const float len = sqrt_approx(r2);
@@ -411,7 +435,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidPa
         while (far) {
             const int k = __ffs(far) - 1;
             far &= far - 1;
-            const uint32_t code = row_code(v, i, k);
+            const uint32_t code = row_code_reg(row, k);
             const float4 pj = fetch_code<SOLIDS>(v, d, stage_addr, code);
             const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -428,17 +452,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(View v, FluidPa
             fx = fmaf(dw, dx, fx); fy = fmaf(dw, dy, fy); fz = fmaf(dw, dz, fz);
         }
     } else {
-        F3 f = f3(0.0f, 0.0f, 0.0f);
-        if (!(word & LGPU_CNT_WALK)) {
-            replay_neighbors<SOLIDS, false>(v, d, &bar, stage, cur, i, cnt, [&](float4 pj, uint32_t code, int) {
-                const float lj = (SOLIDS && (code & LGPU_SOLID_CODE)) ? 0.0f : pj.w;
-                deltap_pair<Fast, false>(g, fp, xi, f3(pj), li, lj, f);
-            });
-        } else {
-            walk<false>(v, i, f3(v.x0[i]), [&](int j, int) {
-                deltap_pair<Fast, false>(g, fp, xi, j >= 0 ? f3(cur[j]) : f3(v.solid_pos[~j]), li, j >= 0 ? v.lambda[j] : 0.0f, f);
-            });
-        }
+        const float3 f = deltap_slow<SOLIDS>(v, fp, d, stage_addr, cur, i, word, xi, li);
         fx = f.x; fy = f.y; fz = f.z;
     }
     F3 p = f3(fmaf(fx, fp.inv_rho0, xi.x), fmaf(fy, fp.inv_rho0, xi.y), fmaf(fz, fp.inv_rho0, xi.z));

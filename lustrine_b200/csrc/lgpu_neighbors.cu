@@ -108,28 +108,88 @@ struct RowWriter {
     }
 };
 
+// Out-of-line paths of the table build: tiles in virtual-slot mode (candidates read from the global
+// storage) and particles with solids in their 27 cells or a very dense column (the reference's nested
+// order over the global storage).
 template <bool SAND>
-__global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
+__device__ __noinline__ int2 build_row_virtual(const View& v, const BlkDesc& d, int i, F3 xi, int key, uint32_t pad) {
+    const Geom& g = v.g;
+    RowWriter w;
+    w.init(v, i);
+    const uint32_t self_code = (uint32_t)(d.slotbase[4] + i);
+    const CellCoord c = decode_cell(g, key);
+    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
+    for (int r = 0; r < 9; r++) {
+        const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
+        if (y < 0 || y >= g.gY || x < 0 || x >= g.gX) continue;
+        const int base = y * g.gXZ + x * g.gZ;
+        const int b = v.cell_start[base + zlo], e = v.cell_start[base + zhi + 1];
+        const uint32_t first = (uint32_t)(d.slotbase[r] + b);
+        for (int u = b; u < e; u++) {
+            if (!within_h(g, xi, f3(v.x0[u]))) continue;
+            const uint32_t code = first + (uint32_t)(u - b);
+            if (SAND && code == self_code) continue;
+            w.emit(code);
+        }
+    }
+    w.finish(pad);
+    return make_int2(w.cnt, w.bad ? 1 : 0);
+}
+template <bool SAND>
+__device__ __noinline__ int2 build_row_walk(const View& v, const BlkDesc& d, int i, F3 xi, uint32_t pad) {
+    RowWriter w;
+    w.init(v, i);
+    walk<SAND>(v, i, xi, [&](int j, int r) {
+        if (j >= 0) w.emit((uint32_t)(d.slotbase[r] + j));
+        else {
+            int off = ~j - d.sbase[r];
+            if (off >= LGPU_SOLID_WINDOW) { w.bad = true; off = 0; }
+            w.emit(LGPU_SOLID_CODE | ((uint32_t)r << 11) | (uint32_t)off);
+        }
+    });
+    w.finish(pad);
+    return make_int2(w.cnt, w.bad ? 1 : 0);
+}
+
+template <bool SAND>
+__global__ void __launch_bounds__(LGPU_TILE) k_build_table(const __grid_constant__ View v) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
     const int i = blockIdx.x * LGPU_TILE + tid;
     const int ic = i < v.n ? i : 0;
-    // the thread's own loads first: they overlap the descriptor load and the bulk copies
+    const Geom& g = v.g;
+    // the thread's own loads first (position, key, the cell offsets of its nine stencil columns):
+    // they overlap the descriptor load and the bulk copies
     const float4 x0i = v.x0[ic];
     const int key = v.key[ic];
+    const int flags = g.slab ? v.flags[ic] : 0;
     stage_begin(v, v.x0, d, &bar, stage);
+    // per stencil column: the candidates are the sorted slots [cb, ce) — the three cells z-1..z+1
+    // of a column are contiguous in the sorted storage
+    const CellCoord c = decode_cell(g, key);
+    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
+    int cb[9], ce[9];
+    bool slow = false;  // solids in the 27 cells, or a column with more than 32 candidates
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
+        cb[r] = ce[r] = 0;
+        if (y >= 0 && y < g.gY && x >= 0 && x < g.gX) {
+            const int base = y * g.gXZ + x * g.gZ;
+            cb[r] = v.cell_start[base + zlo]; ce[r] = v.cell_start[base + zhi + 1];
+            if (ce[r] - cb[r] > 32) slow = true;
+            if (v.n_solid && v.solid_cell_start[base + zhi + 1] > v.solid_cell_start[base + zlo]) slow = true;
+        }
+    }
+    stage_wait(&bar);  // every thread waits: no bulk copy may outlive the block
     if (i >= v.n) return;
-    const Geom& g = v.g;
-    if (g.slab && (v.flags[i] & LGPU_FLAG_GHOST)) {  // ghost of a neighbouring slab: read by others, never updated here
+    if (flags & LGPU_FLAG_GHOST) {  // ghost of a neighbouring slab: read by others, never updated here
         v.nbr_cnt[i] = LGPU_CNT_GHOST;
         return;
     }
     const F3 xi = f3(x0i);
-    RowWriter w;
-    w.init(v, i);
-
     if (d.mode == 2) {
         // neighbourhood beyond the 16-bit code space: count only, the solver passes re-walk the stencil
         int cnt = 0;
@@ -138,62 +198,44 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
         atomicAdd(&v.counters[1], 1ULL);
         return;
     }
-
-    // per stencil column: first candidate (stage slot) and number of candidates — the three cells
-    // z-1..z+1 of a column are contiguous in the sorted storage
-    const CellCoord c = decode_cell(g, key);
-    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
-    uint32_t first[9];
-    int ncand[9];
-    bool slow = false;  // solids in the 27 cells, or a column with more than 32 candidates
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
-        first[r] = 0; ncand[r] = 0;
-        if (y >= 0 && y < g.gY && x >= 0 && x < g.gX) {
-            const int base = y * g.gXZ + x * g.gZ;
-            const int b = v.cell_start[base + zlo], e = v.cell_start[base + zhi + 1];
-            first[r] = (uint32_t)(d.slotbase[r] + b);
-            ncand[r] = e - b;
-            if (e - b > 32) slow = true;
-            if (v.n_solid && v.solid_cell_start[base + zhi + 1] > v.solid_cell_start[base + zlo]) slow = true;
-        }
-    }
     const uint32_t self_code = (uint32_t)(d.slotbase[4] + i);
-    stage_wait(d, &bar);
-
-    if (!slow) {
+    // padding: sand = the far-away dummy (no contact); fluid = the particle itself (zero separation:
+    // every term of the branch-free fluid bodies vanishes)
+    const uint32_t pad = SAND ? 0u : self_code;
+    int cnt;
+    bool bad;
+    if (slow) {
+        const int2 r = build_row_walk<SAND>(v, d, i, xi, pad);
+        cnt = r.x; bad = r.y != 0;
+    } else if (d.mode != 0) {
+        const int2 r = build_row_virtual<SAND>(v, d, i, xi, key, pad);
+        cnt = r.x; bad = r.y != 0;
+    } else {
+        RowWriter w;
+        w.init(v, i);
         // No solid in the 27 cells: the reference order is simply ascending sorted slot over the 9
         // columns (fluid: self included; sand: self skipped — SURVEY F7).  Per column: test the
-        // candidates with the Exact predicate into a 32-bit hit mask, then emit the hits.
+        // candidates with the Exact predicate into a hit mask, then emit the hits.
         const uint32_t stage_addr = smem_u32(stage);
 #pragma unroll
         for (int r = 0; r < 9; r++) {
-            const int n = ncand[r];
+            const int n = ce[r] - cb[r];
             if (n == 0) continue;
+            const uint32_t first = (uint32_t)(d.slotbase[r] + cb[r]);
             // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at
             // bit n-1-t.  The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has
             // the exact sign and is +0 on equality), so a test costs the 8 separately rounded
             // operations of the reference's predicate plus one FADD and one funnel shift.
             uint32_t out = 0;
-            if (d.mode == 0) {
-                const uint32_t a = slot_addr(stage_addr, first[r]);
+            const uint32_t a = slot_addr(stage_addr, first);
 #pragma unroll 4
-                for (int t = 0; t < n; t++) {
-                    const float4 pj = lds128(a + 16u * (uint32_t)t);
-                    const F3 dd = vsub<Exact>(xi, f3(pj));
-                    out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
-                }
-            } else {
-                // virtual-slot mode: same codes, candidates read from the global storage
-                const float4* vsrc = v.x0 + ((int)first[r] - d.slotbase[r]);
-                for (int t = 0; t < n; t++) {
-                    const F3 dd = vsub<Exact>(xi, f3(vsrc[t]));
-                    out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
-                }
+            for (int t = 0; t < n; t++) {
+                const float4 pj = lds128(a + 16u * (uint32_t)t);
+                const F3 dd = vsub<Exact>(xi, f3(pj));
+                out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
             }
             uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
-            const uint32_t top = first[r] + (uint32_t)(n - 1);  // code of bit k = top - k
+            const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
             if (SAND && r == 4) m &= ~(1u << (top - self_code));
             const int hits = __popc(m);
             if (w.cnt + hits > w.M) { w.cnt += hits; w.bad = true; continue; }  // row too long: the solver passes re-walk
@@ -203,23 +245,11 @@ __global__ void __launch_bounds__(LGPU_TILE) k_build_table(View v) {
                 w.emit_unchecked(top - k);
             }
         }
-    } else {
-        // solids interleave with the sand per cell (or a column is very dense): walk in the
-        // reference's nested order over the global storage
-        walk<SAND>(v, i, xi, [&](int j, int r) {
-            if (j >= 0) w.emit((uint32_t)(d.slotbase[r] + j));
-            else {
-                int off = ~j - d.sbase[r];
-                if (off >= LGPU_SOLID_WINDOW) { w.bad = true; off = 0; }
-                w.emit(LGPU_SOLID_CODE | ((uint32_t)r << 11) | (uint32_t)off);
-            }
-        });
+        w.finish(pad);
+        cnt = w.cnt; bad = w.bad;
     }
-    // padding: sand = the far-away dummy (no contact); fluid = the particle itself (zero separation:
-    // every term of the branch-free fluid bodies vanishes)
-    w.finish(SAND ? 0u : self_code);
-    int word = w.cnt;
-    if (w.cnt > w.M || w.bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
+    int word = cnt;
+    if (cnt > v.M || bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
     v.nbr_cnt[i] = word;
 }
 

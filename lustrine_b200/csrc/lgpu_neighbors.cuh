@@ -141,27 +141,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
-// Block prologue of every staged kernel: loads the block descriptor, starts the bulk copies of
-// `src` (the array the neighbours are read from) and returns; stage_wait() blocks until they landed.
-// Must be called by all threads of the block (contains __syncthreads).
+// Block prologue of every staged kernel.  Warp 0 loads the block descriptor and starts the bulk
+// copies of `src` (the array the neighbours are read from); nobody else waits for that: the other
+// warps go on to their own loads and meet the copies at stage_wait().  `d` may only be read after
+// stage_wait() (the mbarrier's completion publishes warp 0's descriptor stores).
+// Must be called by all threads of the block (contains one __syncthreads, before anything is in flight).
 __device__ __forceinline__ void stage_begin(const View& v, const float4* __restrict__ src, BlkDesc& d, uint64_t* bar, float4* stage) {
     const int tid = threadIdx.x;
-    if (tid < (int)(sizeof(BlkDesc) / sizeof(int))) ((int*)&d)[tid] = ((const int*)&v.blk[blockIdx.x])[tid];
     if (tid == 0) {
         mbar_init(bar, 1);
         stage[0] = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.0f);  // dummy: farther than any support radius
     }
     __syncthreads();
-    if (tid == 0 && d.mode == 0 && d.nr > 0 && v.n > 0) {
-        uint32_t bytes = 0;
-        for (int m = 0; m < d.nr; m++) bytes += (uint32_t)d.len[m] * 16u;
-        mbar_expect_tx(bar, bytes);
-        for (int m = 0; m < d.nr; m++) bulk_g2s(stage + d.s0[m], src + d.g0[m], (uint32_t)d.len[m] * 16u, bar);
+    if (tid < 32) {
+        const int* gsrc = (const int*)&v.blk[blockIdx.x];
+        for (int t = tid; t < (int)(sizeof(BlkDesc) / sizeof(int)); t += 32) ((int*)&d)[t] = gsrc[t];
+        __syncwarp();
+        if (tid == 0) {
+            const bool copy = d.mode == 0 && v.n > 0;
+            uint32_t bytes = 0;
+            if (copy) for (int m = 0; m < d.nr; m++) bytes += (uint32_t)d.len[m] * 16u;
+            mbar_expect_tx(bar, bytes);  // arrive (release); the phase completes at once when there is nothing to copy
+            if (copy) for (int m = 0; m < d.nr; m++) bulk_g2s(stage + d.s0[m], src + d.g0[m], (uint32_t)d.len[m] * 16u, bar);
+        }
     }
 }
-__device__ __forceinline__ void stage_wait(const BlkDesc& d, uint64_t* bar) {
-    if (d.mode == 0 && d.nr > 0) mbar_wait(bar, 0);
-}
+__device__ __forceinline__ void stage_wait(uint64_t* bar) { mbar_wait(bar, 0); }
 
 // virtual-slot mode: at most 3 ranges, unused ones have s0 = INT_MAX
 __device__ __forceinline__ int decode_virtual(const BlkDesc& d, uint32_t code) {
@@ -232,11 +237,29 @@ __device__ __forceinline__ void load_row_rest(TableRow<MG>& row, const View& v, 
     }
 }
 
-template <bool SOLIDS, bool PAD, int MG, class Body>
+// code number k of a row held in registers (k is not a constant; a switch keeps the row in registers,
+// an indexed or select-chain formulation makes the compiler move it to local memory)
+__device__ __forceinline__ uint32_t row_code_reg(const TableRow<8>& row, int k) {
+    uint32_t pair;
+    switch (k >> 1) {
+        case 0: pair = row.w[0].x; break;  case 1: pair = row.w[0].y; break;
+        case 2: pair = row.w[1].x; break;  case 3: pair = row.w[1].y; break;
+        case 4: pair = row.w[2].x; break;  case 5: pair = row.w[2].y; break;
+        case 6: pair = row.w[3].x; break;  case 7: pair = row.w[3].y; break;
+        case 8: pair = row.w[4].x; break;  case 9: pair = row.w[4].y; break;
+        case 10: pair = row.w[5].x; break; case 11: pair = row.w[5].y; break;
+        case 12: pair = row.w[6].x; break; case 13: pair = row.w[6].y; break;
+        case 14: pair = row.w[7].x; break; default: pair = row.w[7].y; break;
+    }
+    return (k & 1) ? pair >> 16 : pair & 0xffffu;
+}
+
+// STAGED = true: the caller has checked d.mode == 0 (the virtual-slot loop is not instantiated)
+template <bool SOLIDS, bool PAD, int MG, bool STAGED = false, class Body>
 __device__ __forceinline__ void replay_row(const View& v, const BlkDesc& d, const TableRow<MG>& row, uint32_t stage_addr,
                                            const float4* __restrict__ src, int cnt, Body&& body) {
     const int ng = (cnt + 3) >> 2;
-    if (d.mode == 0) {
+    if (STAGED || d.mode == 0) {
 #pragma unroll
         for (int g = 0; g < MG; g++) {
             if (g < ng) {
@@ -315,10 +338,10 @@ __device__ __forceinline__ void replay_neighbors(const View& v, const BlkDesc& d
     if (v.M == 32) {
         TableRow<8> row;
         row.load(v, i, cnt);
-        stage_wait(d, bar);
+        stage_wait(bar);
         replay_row<SOLIDS, PAD, 8>(v, d, row, stage_addr, src, cnt, body);
     } else {
-        stage_wait(d, bar);
+        stage_wait(bar);
         replay_table<SOLIDS, PAD>(v, d, stage_addr, src, i, cnt, body);
     }
 }

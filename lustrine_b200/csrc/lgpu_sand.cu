@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
     if (word == -1) {
     } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
         if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
