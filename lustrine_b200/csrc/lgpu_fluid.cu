@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
     if (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK)) stage_wait(&bar);  // (the table path waits after its row loads)
@@ -169,12 +168,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
     if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
-        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
         if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
     }
     }
-    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 // ---- delta-p + box collision (+ commit): src/Simulate.cpp:90-113 ----
@@ -206,7 +203,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
     if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
@@ -261,12 +257,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
     }
     if (push.enabled) {  // slab mode: the corrected x* of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
-        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
         if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
     }
     }
-    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 
@@ -323,13 +317,12 @@ __device__ __noinline__ float3 deltap_slow(const View& v, const FluidParams& fp,
 }
 
 template <bool SOLIDS>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, float4* __restrict__ cur, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_lambda_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, float4* __restrict__ cur, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     const int ic = i < v.n ? i : 0;
-    bool pushed = false;
     const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
     const float4 ci = cur[ic];
     TableRow<8> row;
@@ -385,22 +378,19 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda_fast(const __grid_co
     reinterpret_cast<float*>(cur + i)[3] = lam;
     if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
-        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
         if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
     }
     }
-    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 template <bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_deltap_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     const int ic = i < v.n ? i : 0;
-    bool pushed = false;
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
     const float4 ci = cur[ic];
     TableRow<8> row;
@@ -470,12 +460,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap_fast(const __grid_co
     }
     if (push.enabled) {
         const int2 t = push.tgt[i];
-        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
         if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
     }
     }
-    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 template <bool SOLIDS>
@@ -496,13 +484,13 @@ static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int
         lgpu_mark(c, 6);
         SlabPush push = lgpu_slab_push(c, cur, true);
         k_fluid_lambda_fast<SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
         lgpu_mark(c, 7);
         push = lgpu_slab_push(c, next, it < iterations - 1);
         if (it == iterations - 1) k_fluid_deltap_fast<SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
         else k_fluid_deltap_fast<SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
         c->launches += 2;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
         cur = next;
     }
     c->pstar_final = cur;
@@ -530,13 +518,13 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
         // neighbours' ghost slots; a one-thread kernel then waits for the neighbours' stores of the same pass
         SlabPush push = lgpu_slab_push(c, cur, !fp.literal_lambda_index);
         k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
         lgpu_mark(c, 7);
         push = lgpu_slab_push(c, next, it < iterations - 1);
         if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
         else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
         c->launches += 2;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
         cur = next;
     }
     c->pstar_final = cur;

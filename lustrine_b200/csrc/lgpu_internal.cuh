@@ -11,13 +11,16 @@
 #define LGPU_LAMBDA_HEAD 4096  // lambdas[loop counter] table: first slots in reference order
 #define LGPU_BLOCK 128
 #define LGPU_MAX_MARKS 96
+#ifndef LGPU_BLOCKS_PER_SM
+#define LGPU_BLOCKS_PER_SM 3     // resident blocks per SM the hot staged kernels are compiled for (register cap)
+#endif
 
 // ---- staged neighbour table (lgpu_stage.cuh) ----
 #ifndef LGPU_TILE
-#define LGPU_TILE 512            // particles per thread block of the table / solver kernels
+#define LGPU_TILE 384            // particles per thread block of the table / solver kernels
 #endif
 #ifndef LGPU_STAGE_SLOTS
-#define LGPU_STAGE_SLOTS 5120    // float4 slots of the shared-memory stage (80 KB); slot 0 = far-away dummy
+#define LGPU_STAGE_SLOTS 4608    // float4 slots of the shared-memory stage (72 KB, three blocks per SM); slot 0 = far-away dummy
 #endif
 #define LGPU_VIRTUAL_SLOTS 32767 // a neighbourhood larger than the stage is addressed with the same codes (< 0x8000), read from L1/L2
 #define LGPU_SOLID_CODE 0x8000u  // table code of a solid neighbour: 0x8000 | run << 11 | offset in the run's window
@@ -194,8 +197,12 @@ static inline void lgpu_mark(lgpu_ctx* c, int phase) {
 
 // ---- slabs ----
 // Fused ghost refresh: the solver kernel that produces a value of a boundary particle also stores it
-// into the neighbouring slab's ghost slot (peer memory over NVLink) and, when its last block is done,
-// raises that neighbour's flag.  Passed by value to the solver kernels; enabled = 0 on a single GPU.
+// into the neighbouring slab's ghost slot (peer memory over NVLink).  The kernel that follows on the
+// stream (k_signal_wait, one thread) raises the neighbours' sequence flags — stream order puts it
+// after every store of the solver kernel — and then waits for the neighbours' flags of the same pass.
+// (Signalling from inside the solver kernel — a fence by every storing thread, a block barrier and a
+// ticket atomic per block — made the passes 30-40 % slower in slab mode.)
+// Passed by value to the solver kernels; enabled = 0 on a single GPU.
 struct SlabPush {
     int enabled;
     const int2* tgt;          // per sorted particle: its slot in the left / right neighbour's buffers, -1 = none
@@ -205,28 +212,11 @@ struct SlabPush {
     int seq[2];
 };
 // before a solver kernel: the SlabPush for its output buffer (sequence numbers advance);
-// after it: a one-thread kernel that waits until both neighbours' stores of the same pass have landed
+// after it: a one-thread kernel that raises the neighbours' flags and waits until both neighbours'
+// stores of the same pass have landed
 SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable);
-int lgpu_slab_wait(lgpu_ctx* c);
+int lgpu_slab_wait(lgpu_ctx* c, const SlabPush& push);
 
-__device__ __forceinline__ void slab_push_signal(const SlabPush& p, bool pushed) {
-    // All threads of the block.  Only the threads that stored into a neighbour's memory pay for the
-    // system-scope fence (MEMBAR.SYS by every thread of every block doubled the kernel time); the
-    // barrier orders them before thread 0's ticket, and the last block of the grid fences again
-    // before it raises the flags (fence cumulativity: store -> fence.sys -> bar -> atom -> atom -> fence.sys -> flag).
-    if (pushed) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int t = atomicAdd(p.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *p.ticket = 0;
-            __threadfence_system();
-            if (p.peer_flag[0]) *p.peer_flag[0] = p.seq[0];
-            if (p.peer_flag[1]) *p.peer_flag[1] = p.seq[1];
-            __threadfence_system();
-        }
-    }
-}
 int lgpu_slab_init(lgpu_ctx* c);
 int lgpu_slab_check(lgpu_ctx* c);
 int lgpu_preload_grid(); int lgpu_preload_neighbors(); int lgpu_preload_fluid(); int lgpu_preload_sand();

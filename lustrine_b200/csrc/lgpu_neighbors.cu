@@ -152,7 +152,7 @@ __device__ __noinline__ int2 build_row_walk(const View& v, const BlkDesc& d, int
 }
 
 template <bool SAND>
-__global__ void __launch_bounds__(LGPU_TILE) k_build_table(const __grid_constant__ View v) {
+__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_build_table(const __grid_constant__ View v) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;

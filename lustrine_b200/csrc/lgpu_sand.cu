@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    bool pushed = false;
     stage_begin(v, cur, d, &bar, stage);
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
     if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
@@ -141,12 +140,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     }
     if (push.enabled) {  // slab mode: the new x* of a boundary particle goes straight into the neighbour's ghost slot
         const int2 t = push.tgt[i];
-        pushed = t.x >= 0 || t.y >= 0;
         if (t.x >= 0) push.peer_buf[0][t.x] = f4(ps);
         if (t.y >= 0) push.peer_buf[1][t.y] = f4(ps);
     }
     }
-    if (push.enabled) slab_push_signal(push, pushed);
 }
 
 // largest fp32 x with sqrt_rn(x) <= d  (so that `sqrt(d2) > d` <=> `d2 > x`, bit-exactly)
@@ -196,7 +193,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         }
 #undef LGPU_SAND_LAUNCH
         c->launches++;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c); if (st) return st; }
+        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
         cur = next;
     }
     c->pstar_final = (float4*)cur;

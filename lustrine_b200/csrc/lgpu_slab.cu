@@ -13,6 +13,7 @@
 // NVLink (peer-mapped "arena", one CUDA IPC handle per context; a plain pointer for contexts that
 // share a process), followed by a sequence-number flag; the receiver's stream waits on the flag
 // with a one-thread kernel.  Nothing goes through the host except four counters per substep.
+#include <stdlib.h>
 #include <string.h>
 
 #include "lgpu_internal.cuh"
@@ -39,6 +40,7 @@ struct SlabState {
     unsigned int* push_ticket;
     bool begun;
     int n_store;
+    void* d_xfer;         // device side of lgpu_slab_download (allocated once)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -92,7 +94,7 @@ void lgpu_slab_free(lgpu_ctx* c) {
         if (S->peer_ipc[s] && S->peer_base[s]) cudaIpcCloseMemHandle(S->peer_base[s]);
         cudaFree(S->out_mig[s]); cudaFree(S->out_gho[s]); cudaFree(S->gho_src[s]); cudaFree(S->mig_src[s]);
     }
-    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->push_tgt); cudaFree(S->push_ticket);
+    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->push_tgt); cudaFree(S->push_ticket); cudaFree(S->d_xfer);
     cudaFreeHost(S->h_counts);
     delete S;
     c->slab = nullptr;
@@ -200,7 +202,14 @@ __global__ void __launch_bounds__(256) k_build_push_tgt(const int* __restrict__ 
     else tgt[i].y = slotmap[g];
 }
 
-__global__ void k_wait_flags2(const volatile int* flag0, int expected0, const volatile int* flag1, int expected1, int* error) {
+// after a solver pass: tell the neighbours that this slab's stores of the pass are complete (they were
+// issued by the previous kernel on this stream), then wait for theirs
+__global__ void k_signal_wait(volatile int* peer0, int seq0, volatile int* peer1, int seq1,
+                              const volatile int* flag0, int expected0, const volatile int* flag1, int expected1, int* error) {
+    __threadfence_system();
+    if (peer0) *peer0 = seq0;
+    if (peer1) *peer1 = seq1;
+    __threadfence_system();
     const long long t0 = clock64();
     while ((flag0 && *flag0 < expected0) || (flag1 && *flag1 < expected1)) {
         if (clock64() - t0 > 20000000000LL) { *error = 1; return; }
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_append_halo(View v, int n_store,
 __global__ void k_compact_owned(View v, int n_store, float* __restrict__ pos, float* __restrict__ vel, int* __restrict__ flags, int* __restrict__ ids,
                                 int* __restrict__ counter);
 int lgpu_preload_slab() {
-    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_push_tgt); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_wait_flags2);
+    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_push_tgt); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_signal_wait);
     LGPU_PRELOAD(k_append_halo); LGPU_PRELOAD(k_compact_owned);
     return LGPU_OK;
 }
@@ -380,13 +389,13 @@ SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable) {
     return p;
 }
 
-int lgpu_slab_wait(lgpu_ctx* c) {
+int lgpu_slab_wait(lgpu_ctx* c, const SlabPush& push) {
     SlabState* S = c->slab;
     if (!S || (!S->has_nbr[0] && !S->has_nbr[1])) return LGPU_OK;
     const volatile int* f0 = S->has_nbr[0] ? &S->local.hdr->flag[0] : nullptr;
     const volatile int* f1 = S->has_nbr[1] ? &S->local.hdr->flag[1] : nullptr;
     const int e0 = S->has_nbr[0] ? ++S->rx_seq[0] : 0, e1 = S->has_nbr[1] ? ++S->rx_seq[1] : 0;
-    k_wait_flags2<<<1, 1, 0, c->stream>>>(f0, e0, f1, e1, &S->local.hdr->error);
+    k_signal_wait<<<1, 1, 0, c->stream>>>(push.peer_flag[0], push.seq[0], push.peer_flag[1], push.seq[1], f0, e0, f1, e1, &S->local.hdr->error);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
@@ -426,10 +435,16 @@ extern "C" int lgpu_slab_download(lgpu_ctx* c, float* pos, float* vel, int* flag
     const int n_store = c->n, n = c->n_owned;
     *n_out = 0;
     if (n == 0) return LGPU_OK;
-    float *d_pos, *d_vel; int *d_flags, *d_ids, *d_counter;
-    CUDA_TRY(cudaMalloc((void**)&d_pos, sizeof(float) * 3 * n)); CUDA_TRY(cudaMalloc((void**)&d_vel, sizeof(float) * 3 * n));
-    CUDA_TRY(cudaMalloc((void**)&d_flags, sizeof(int) * n)); CUDA_TRY(cudaMalloc((void**)&d_ids, sizeof(int) * n));
-    CUDA_TRY(cudaMalloc((void**)&d_counter, sizeof(int)));
+    // one transfer area per context, allocated at the first download and kept: cudaMalloc / cudaFree
+    // are device-wide synchronisation points and, with peer mappings in place, cost milliseconds
+    SlabState* S = c->slab;
+    const size_t need = sizeof(int) * 8 * (size_t)c->cap + 256;
+    if (!S->d_xfer) { CUDA_TRY(cudaMalloc((void**)&S->d_xfer, need)); }
+    float* d_pos = (float*)S->d_xfer;
+    float* d_vel = d_pos + 3 * (size_t)c->cap;
+    int* d_flags = (int*)(d_vel + 3 * (size_t)c->cap);
+    int* d_ids = d_flags + c->cap;
+    int* d_counter = d_ids + c->cap;
     CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(int), c->stream));
     View v = lgpu_make_view(c);
     k_compact_owned<<<lgpu_blocks(n_store), LGPU_BLOCK, 0, c->stream>>>(v, n_store, d_pos, d_vel, d_flags, d_ids, d_counter);
@@ -441,7 +456,6 @@ extern "C" int lgpu_slab_download(lgpu_ctx* c, float* pos, float* vel, int* flag
     CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(ids, d_ids, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(d_pos); cudaFree(d_vel); cudaFree(d_flags); cudaFree(d_ids); cudaFree(d_counter);
     if (got != n) { lgpu_set_error("lgpu_slab_download: %d owned particles found, %d expected", got, n); return LGPU_ERR_CUDA; }
     *n_out = n;
     return LGPU_OK;

@@ -282,10 +282,17 @@ class Context:
         flags = None if flags is None else np.ascontiguousarray(flags, np.int32)
         _check(self.L.lgpu_slab_upload(self._h, pos.shape[0], _ptr(pos), _ptr(vel), _ptr(flags), _ptr(ids)), "lgpu_slab_upload")
 
-    def slab_download(self):
+    def slab_download(self, out=None):
+        """(pos, vel, flags, ids) of the owned particles.  out = caller-owned arrays of at least
+        self.n rows (e.g. views of pinned memory) to avoid the allocation and the pageable copy."""
         n = self.n
-        pos = np.zeros((max(n, 1), 3), np.float32); vel = np.zeros((max(n, 1), 3), np.float32)
-        flags = np.zeros(max(n, 1), np.int32); ids = np.zeros(max(n, 1), np.int32)
+        if out is not None:
+            pos, vel, flags, ids = out
+            if len(pos) < n or len(vel) < n or len(flags) < n or len(ids) < n:
+                raise LgpuError("slab_download: output buffers hold fewer than %d particles" % n)
+        else:
+            pos = np.zeros((max(n, 1), 3), np.float32); vel = np.zeros((max(n, 1), 3), np.float32)
+            flags = np.zeros(max(n, 1), np.int32); ids = np.zeros(max(n, 1), np.int32)
         got = c_i()
         _check(self.L.lgpu_slab_download(self._h, _ptr(pos), _ptr(vel), _ptr(flags), _ptr(ids), C.byref(got)), "lgpu_slab_download")
         return pos[:got.value], vel[:got.value], flags[:got.value], ids[:got.value]
