@@ -69,6 +69,19 @@ def deal(pos, slabs, cs):
     return out
 
 
+def slab_capacity(pos, slabs, owned, cs, grid_x, factor=1.5):
+    """Particle capacity of every slab context (equal on all ranks).  The storage of a substep holds the
+    previous substep's slots (owned + ghost copies, the latter dead by then) plus the incoming ghost copies
+    and migrants, so the ghost columns on both sides count twice; `factor` is the head room for
+    particles gathering in a slab before the boundaries are re-planned."""
+    hist = np.bincount(np.clip(cell_x(pos, cs), 0, grid_x - 1), minlength=grid_x).astype(np.int64)
+    need = 0
+    for (lo, hi), o in zip(slabs, owned):
+        ghosts = (int(hist[lo - 1]) if lo > 0 else 0) + (int(hist[hi]) if hi < grid_x else 0)
+        need = max(need, len(o) + 2 * ghosts)
+    return int(need * factor) + 4096
+
+
 def merge_by_id(parts, n_total):
     """Reassembles (pos, vel, flags, ids) tuples of all slabs into arrays indexed by particle id."""
     pos = np.zeros((n_total, 3), np.float32)
@@ -121,7 +134,7 @@ class VirtualSlabs:
         self.grid = grid_dims(domain, cs)
         self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], world)
         owned = deal(pos, self.slabs, cs)
-        cap = int(max(len(o) for o in owned) * capacity_factor) + 4096
+        cap = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
         self.ctx = [SlabContext(domain, s, cap, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
         exports = [c.G.slab_export() for c in self.ctx]
         for k, c in enumerate(self.ctx):
@@ -166,7 +179,7 @@ class DistributedSlab:
         # every rank holds the same synthetic scene and derives the same plan: no broadcast needed
         self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
         owned = deal(pos, self.slabs, cs)
-        cap = int(max(len(o) for o in owned) * capacity_factor) + 4096
+        cap = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
         self.ctx = (context_factory or SlabContext)(domain, self.slabs[self.rank], cap, solids, device, halo_capacity, **ctx_kw)
         handle, _, _ = self.ctx.G.slab_export()
         handles = [None] * self.world
