@@ -141,7 +141,7 @@ struct LambdaAcc {
 // Reads x* of the neighbours from the stage, writes rho_i, lambda_i and also lambda_i into the w
 // lane of the particle's own x* so that the delta-p pass gets (x*_j, lambda_j) in one LDS.128.
 template <class P, bool POLY6, bool SOLIDS>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams fp, float4* __restrict__ cur, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams fp, float4* __restrict__ cur) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -166,11 +166,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_lambda(View v, FluidParams 
     reinterpret_cast<float*>(cur + i)[3] = lam;
     int o = v.orig[i];
     if (o < LGPU_LAMBDA_HEAD) v.lambda_head[o] = lam;  // lambdas[] in reference slot order, for F4
-    if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
-        const int2 t = push.tgt[i];
-        if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
-        if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
-    }
     }
 }
 
@@ -198,7 +193,7 @@ __device__ __forceinline__ void deltap_pair(const Geom& g, const FluidParams& fp
 }
 
 template <class P, bool POLY6, bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -254,11 +249,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_fluid_deltap(View v, FluidParams 
         v.pos_in[i] = f4(p);
         v.flags_in[i] = v.flags[i];
         v.orig_in[i] = v.orig[i];
-    }
-    if (push.enabled) {  // slab mode: the corrected x* of a boundary particle goes straight into the neighbour's ghost slot
-        const int2 t = push.tgt[i];
-        if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
-        if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
     }
     }
 }
@@ -317,7 +307,7 @@ __device__ __noinline__ float3 deltap_slow(const View& v, const FluidParams& fp,
 }
 
 template <bool SOLIDS>
-__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_lambda_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, float4* __restrict__ cur, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_lambda_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, float4* __restrict__ cur) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -376,16 +366,11 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_lambda_
     v.density[i] = rho;
     v.lambda[i] = lam;
     reinterpret_cast<float*>(cur + i)[3] = lam;
-    if (push.enabled) {  // slab mode: lambda of a boundary particle goes straight into the neighbour's ghost slot
-        const int2 t = push.tgt[i];
-        if (t.x >= 0) reinterpret_cast<float*>(push.peer_buf[0] + t.x)[3] = lam;
-        if (t.y >= 0) reinterpret_cast<float*>(push.peer_buf[1] + t.y)[3] = lam;
-    }
     }
 }
 
 template <bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_deltap_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_deltap_fast(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, const float4* __restrict__ cur, float4* __restrict__ next) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -458,11 +443,6 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_deltap_
         v.flags_in[i] = v.flags[i];
         v.orig_in[i] = v.orig[i];
     }
-    if (push.enabled) {
-        const int2 t = push.tgt[i];
-        if (t.x >= 0) push.peer_buf[0][t.x] = f4(p);
-        if (t.y >= 0) push.peer_buf[1][t.y] = f4(p);
-    }
     }
 }
 
@@ -479,18 +459,17 @@ static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int
     }
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
+    const bool slab = lgpu_slab_active(c);
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        SlabPush push = lgpu_slab_push(c, cur, true);
-        k_fluid_lambda_fast<SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
+        k_fluid_lambda_fast<SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
+        if (slab) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
-        push = lgpu_slab_push(c, next, it < iterations - 1);
-        if (it == iterations - 1) k_fluid_deltap_fast<SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
-        else k_fluid_deltap_fast<SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
+        if (it == iterations - 1) k_fluid_deltap_fast<SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        else k_fluid_deltap_fast<SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
         c->launches += 2;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
+        if (slab && it < iterations - 1) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;
     }
     c->pstar_final = cur;
@@ -511,20 +490,19 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
     }
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
+    const bool slab = lgpu_slab_active(c);
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        // slab mode: the kernels store the boundary particles' lambda (.w of cur) / corrected x* (next) into the
-        // neighbours' ghost slots; a one-thread kernel then waits for the neighbours' stores of the same pass
-        SlabPush push = lgpu_slab_push(c, cur, !fp.literal_lambda_index);
-        k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, push);
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
+        // slab mode: after each pass a small kernel copies the boundary particles' lambda (.w of cur) / corrected x*
+        // (next) into the neighbours' ghost slots and waits for the neighbours' stores of the same pass
+        k_fluid_lambda<P, POLY6, SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
+        if (slab && !fp.literal_lambda_index) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
-        push = lgpu_slab_push(c, next, it < iterations - 1);
-        if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
-        else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next, push);
+        if (it == iterations - 1) k_fluid_deltap<P, POLY6, SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        else k_fluid_deltap<P, POLY6, SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
         c->launches += 2;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
+        if (slab && it < iterations - 1) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;
     }
     c->pstar_final = cur;

@@ -196,27 +196,11 @@ static inline void lgpu_mark(lgpu_ctx* c, int phase) {
 }
 
 // ---- slabs ----
-// Fused ghost refresh: the solver kernel that produces a value of a boundary particle also stores it
-// into the neighbouring slab's ghost slot (peer memory over NVLink).  The kernel that follows on the
-// stream (k_signal_wait, one thread) raises the neighbours' sequence flags — stream order puts it
-// after every store of the solver kernel — and then waits for the neighbours' flags of the same pass.
-// (Signalling from inside the solver kernel — a fence by every storing thread, a block barrier and a
-// ticket atomic per block — made the passes 30-40 % slower in slab mode.)
-// Passed by value to the solver kernels; enabled = 0 on a single GPU.
-struct SlabPush {
-    int enabled;
-    const int2* tgt;          // per sorted particle: its slot in the left / right neighbour's buffers, -1 = none
-    float4* peer_buf[2];      // the neighbours' copy of the buffer this kernel writes
-    volatile int* peer_flag[2];
-    unsigned int* ticket;
-    int seq[2];
-};
-// before a solver kernel: the SlabPush for its output buffer (sequence numbers advance);
-// after it: a one-thread kernel that raises the neighbours' flags and waits until both neighbours'
-// stores of the same pass have landed
-SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable);
-int lgpu_slab_wait(lgpu_ctx* c, const SlabPush& push);
-
+// Ghost refresh of slab mode (lgpu_slab.cu): after a solver kernel has written `buf`, ONE small kernel
+// copies the boundary particles' new values into the neighbours' ghost slots (peer stores over
+// NVLink), raises the neighbours' sequence flags and waits for theirs.  w_only: just lambda (w lane).
+bool lgpu_slab_active(const lgpu_ctx* c);
+int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only);
 int lgpu_slab_init(lgpu_ctx* c);
 int lgpu_slab_check(lgpu_ctx* c);
 int lgpu_preload_grid(); int lgpu_preload_neighbors(); int lgpu_preload_fluid(); int lgpu_preload_sand();

@@ -91,7 +91,7 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
 }
 
 template <class P, bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next, SlabPush push) {
+__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
     extern __shared__ float4 stage[];
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
@@ -138,11 +138,6 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
         v.flags_in[i] = v.flags[i];
         v.orig_in[i] = v.orig[i];
     }
-    if (push.enabled) {  // slab mode: the new x* of a boundary particle goes straight into the neighbour's ghost slot
-        const int2 t = push.tgt[i];
-        if (t.x >= 0) push.peer_buf[0][t.x] = f4(ps);
-        if (t.y >= 0) push.peer_buf[1][t.y] = f4(ps);
-    }
     }
 }
 
@@ -174,7 +169,6 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
         lgpu_mark(c, 7);
-        SlabPush push = lgpu_slab_push(c, next, !last);
 #define LGPU_SAND_LAUNCH(PP, SS, LL)                                                                                    \
     do {                                                                                                                \
         static bool attr = false;                                                                                       \
@@ -182,7 +176,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
             CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                                \
         }                                                                                                               \
-        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next, push);                   \
+        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);                         \
     } while (0)
         if (p.exact_math) {
             if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
@@ -193,7 +187,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         }
 #undef LGPU_SAND_LAUNCH
         c->launches++;
-        if (push.enabled) { lgpu_mark(c, 8); int st = lgpu_slab_wait(c, push); if (st) return st; }
+        if (!last && lgpu_slab_active(c)) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;
     }
     c->pstar_final = (float4*)cur;

@@ -36,7 +36,8 @@ struct SlabState {
     int tx_seq[2], rx_seq[2];
     int n_gho_out[2], n_gho_in[2], n_mig_in[2], n_mig_out[2], in_base[2], mig_in_base[2];
     int* h_counts;        // pinned: [0..7] out_cnt, [8..] SlabHeader
-    int2* push_tgt;       // per sorted particle: its ghost slot in the left / right neighbour, -1 = none
+    int* ref_src[2];      // ghost refresh list of side s: sorted slot here of every particle that has a ghost copy in that
+                          // neighbour (its slot there is local.slotmap[s][g], sent by the neighbour once per substep)
     unsigned int* push_ticket;
     bool begun;
     int n_store;
@@ -78,7 +79,7 @@ int lgpu_slab_init(lgpu_ctx* c) {
     CUDA_TRY(cudaMalloc((void**)&S->ticket, sizeof(unsigned int) * 2));
     CUDA_TRY(cudaMemsetAsync(S->ticket, 0, sizeof(unsigned int) * 2, c->stream));
     CUDA_TRY(cudaMalloc((void**)&S->inv, sizeof(int) * (size_t)c->cap));
-    CUDA_TRY(cudaMalloc((void**)&S->push_tgt, sizeof(int2) * (size_t)c->cap));
+    for (int s = 0; s < 2; s++) CUDA_TRY(cudaMalloc((void**)&S->ref_src[s], sizeof(int) * 2 * (size_t)S->halo_cap));
     CUDA_TRY(cudaMalloc((void**)&S->push_ticket, sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(S->push_ticket, 0, sizeof(unsigned int), c->stream));
     CUDA_TRY(cudaMallocHost((void**)&S->h_counts, sizeof(int) * 64));
@@ -94,7 +95,7 @@ void lgpu_slab_free(lgpu_ctx* c) {
         if (S->peer_ipc[s] && S->peer_base[s]) cudaIpcCloseMemHandle(S->peer_base[s]);
         cudaFree(S->out_mig[s]); cudaFree(S->out_gho[s]); cudaFree(S->gho_src[s]); cudaFree(S->mig_src[s]);
     }
-    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->push_tgt); cudaFree(S->push_ticket); cudaFree(S->d_xfer);
+    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->ref_src[0]); cudaFree(S->ref_src[1]); cudaFree(S->push_ticket); cudaFree(S->d_xfer);
     cudaFreeHost(S->h_counts);
     delete S;
     c->slab = nullptr;
@@ -192,31 +193,64 @@ __global__ void __launch_bounds__(256) k_push_slotmap(const int* __restrict__ in
         dst[g] = inv[g < n_gho ? in_base + g : mig_src[g - n_gho]];
     signal_after_all_blocks(ticket, &dst_hdr->flag[dst_side], seq);
 }
-// owner side: particle sent as ghost copy g (or received as migrant g - n_gho) -> its slot in the neighbour
-__global__ void __launch_bounds__(256) k_build_push_tgt(const int* __restrict__ inv, const int* __restrict__ gho_src, int n_gho, int mig_in_base, int n_mig,
-                                                        const int* __restrict__ slotmap, int side, int2* __restrict__ tgt) {
+// owner side: particle sent as ghost copy g (or received as migrant g - n_gho) -> its sorted slot here
+__global__ void __launch_bounds__(256) k_build_refresh_list(const int* __restrict__ inv, const int* __restrict__ gho_src, int n_gho, int mig_in_base, int n_mig,
+                                                            int* __restrict__ ref_src) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_gho + n_mig) return;
-    const int i = inv[g < n_gho ? gho_src[g] : mig_in_base + (g - n_gho)];
-    if (side == 0) tgt[i].x = slotmap[g];
-    else tgt[i].y = slotmap[g];
+    ref_src[g] = inv[g < n_gho ? gho_src[g] : mig_in_base + (g - n_gho)];
 }
 
-// after a solver pass: tell the neighbours that this slab's stores of the pass are complete (they were
-// issued by the previous kernel on this stream), then wait for theirs
-__global__ void k_signal_wait(volatile int* peer0, int seq0, volatile int* peer1, int seq1,
-                              const volatile int* flag0, int expected0, const volatile int* flag1, int expected1, int* error) {
-    __threadfence_system();
-    if (peer0) *peer0 = seq0;
-    if (peer1) *peer1 = seq1;
-    __threadfence_system();
-    const long long t0 = clock64();
-    while ((flag0 && *flag0 < expected0) || (flag1 && *flag1 < expected1)) {
-        if (clock64() - t0 > 20000000000LL) { *error = 1; return; }
-        __nanosleep(100);
+// Ghost refresh after a solver pass: copies the value every boundary particle got in the pass
+// (x* as a float4, or only lambda in the w lane) from `buf` into its ghost slot in the neighbour's
+// copy of the same buffer — peer stores over NVLink —, then the last block raises the neighbours'
+// sequence flags and waits for theirs.  The stores are NOT issued by the solver kernels themselves:
+// a store to peer memory holds up the SM's memory pipeline for microseconds, which made the passes
+// 20-45 % slower; here they come from a handful of blocks that do nothing else.
+struct RefreshArgs {
+    const float4* buf;
+    int w_only;
+    const int* src[2];
+    const int* dst[2];       // slot maps (written by the neighbours into this slab's arena)
+    int n[2];
+    float4* peer_buf[2];
+    volatile int* peer_flag[2];
+    int seq[2];
+    const volatile int* flag[2];
+    int expected[2];
+    unsigned int* ticket;
+    int* error;
+};
+__global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.n[0] + a.n[1]) {
+        const int s = t < a.n[0] ? 0 : 1, g = t - (s ? a.n[0] : 0);
+        const float4 val = a.buf[a.src[s][g]];
+        float4* dst = a.peer_buf[s] + a.dst[s][g];
+        if (a.w_only) reinterpret_cast<float*>(dst)[3] = val.w;
+        else *dst = val;
     }
-    __threadfence_system();
+    // one system-scope fence per block, by the thread that takes the ticket: the barrier makes the block's
+    // stores visible to it, the fence orders them (cumulativity) before the ticket and the flags
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int ticket = atomicAdd(a.ticket, 1u);
+        if (ticket == gridDim.x - 1) {
+            *a.ticket = 0;
+            __threadfence_system();
+            if (a.peer_flag[0]) *a.peer_flag[0] = a.seq[0];
+            if (a.peer_flag[1]) *a.peer_flag[1] = a.seq[1];
+            const long long t0 = clock64();
+            while ((a.flag[0] && *a.flag[0] < a.expected[0]) || (a.flag[1] && *a.flag[1] < a.expected[1])) {
+                if (clock64() - t0 > 20000000000LL) { *a.error = 1; return; }  // ~10 s: the neighbour is gone; fail instead of hanging
+                __nanosleep(40);
+            }
+            __threadfence_system();
+        }
+    }
 }
+
 __global__ void k_wait_flag(const volatile int* flag, int expected, int* error) {
     const long long t0 = clock64();
     while (*flag < expected) {
@@ -252,7 +286,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_append_halo(View v, int n_store,
 __global__ void k_compact_owned(View v, int n_store, float* __restrict__ pos, float* __restrict__ vel, int* __restrict__ flags, int* __restrict__ ids,
                                 int* __restrict__ counter);
 int lgpu_preload_slab() {
-    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_push_tgt); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_signal_wait);
+    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_refresh_list); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_refresh);
     LGPU_PRELOAD(k_append_halo); LGPU_PRELOAD(k_compact_owned);
     return LGPU_OK;
 }
@@ -355,13 +389,11 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     lgpu_mark(c, 4);
     st = lgpu_launch_build_table(c, mode == 2);  // overlaps the slot-map messages in flight
     if (st) return st;
-    if (c->n > 0) CUDA_TRY(cudaMemsetAsync(S->push_tgt, 0xff, sizeof(int2) * (size_t)c->n, c->stream));
     for (int s = 0; s < 2; s++) {
         if (!S->has_nbr[s]) continue;
         k_wait_flag<<<1, 1, 0, c->stream>>>(&S->local.hdr->flag[s], ++S->rx_seq[s], &S->local.hdr->error);
         const int n = S->n_gho_out[s] + S->n_mig_in[s];
-        if (n > 0) k_build_push_tgt<<<(n + 255) / 256, 256, 0, c->stream>>>(S->inv, S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s],
-                                                                             S->local.slotmap[s], s, S->push_tgt);
+        if (n > 0) k_build_refresh_list<<<(n + 255) / 256, 256, 0, c->stream>>>(S->inv, S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s], S->ref_src[s]);
         c->launches += 2;
     }
     st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
@@ -371,31 +403,35 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     return LGPU_OK;
 }
 
-SlabPush lgpu_slab_push(lgpu_ctx* c, const float4* out_buf, bool enable) {
-    SlabPush p;
-    memset(&p, 0, sizeof(p));
-    SlabState* S = c->slab;
-    if (!S || !enable || (!S->has_nbr[0] && !S->has_nbr[1])) return p;
-    const int b = out_buf == c->x0 ? 0 : (out_buf == c->pa ? 1 : 2);
-    p.enabled = 1;
-    p.tgt = S->push_tgt;
-    p.ticket = S->push_ticket;
-    for (int s = 0; s < 2; s++) {
-        if (!S->has_nbr[s]) continue;
-        p.peer_buf[s] = S->peer[s].buf[b];
-        p.peer_flag[s] = &S->peer[s].hdr->flag[1 - s];
-        p.seq[s] = ++S->tx_seq[s];
-    }
-    return p;
+bool lgpu_slab_active(const lgpu_ctx* c) {
+    const SlabState* S = c->slab;
+    return S && (S->has_nbr[0] || S->has_nbr[1]);
 }
 
-int lgpu_slab_wait(lgpu_ctx* c, const SlabPush& push) {
+// after a solver kernel that wrote `buf`: refresh the neighbours' ghost copies, signal, wait (one launch)
+int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only) {
     SlabState* S = c->slab;
-    if (!S || (!S->has_nbr[0] && !S->has_nbr[1])) return LGPU_OK;
-    const volatile int* f0 = S->has_nbr[0] ? &S->local.hdr->flag[0] : nullptr;
-    const volatile int* f1 = S->has_nbr[1] ? &S->local.hdr->flag[1] : nullptr;
-    const int e0 = S->has_nbr[0] ? ++S->rx_seq[0] : 0, e1 = S->has_nbr[1] ? ++S->rx_seq[1] : 0;
-    k_signal_wait<<<1, 1, 0, c->stream>>>(push.peer_flag[0], push.seq[0], push.peer_flag[1], push.seq[1], f0, e0, f1, e1, &S->local.hdr->error);
+    if (!lgpu_slab_active(c)) return LGPU_OK;
+    const int b = buf == c->x0 ? 0 : (buf == c->pa ? 1 : 2);
+    RefreshArgs a;
+    memset(&a, 0, sizeof(a));
+    a.buf = buf;
+    a.w_only = w_only ? 1 : 0;
+    a.ticket = S->push_ticket;
+    a.error = &S->local.hdr->error;
+    for (int s = 0; s < 2; s++) {
+        if (!S->has_nbr[s]) continue;
+        a.src[s] = S->ref_src[s];
+        a.dst[s] = S->local.slotmap[s];
+        a.n[s] = S->n_gho_out[s] + S->n_mig_in[s];
+        a.peer_buf[s] = S->peer[s].buf[b];
+        a.peer_flag[s] = &S->peer[s].hdr->flag[1 - s];
+        a.seq[s] = ++S->tx_seq[s];
+        a.flag[s] = &S->local.hdr->flag[s];
+        a.expected[s] = ++S->rx_seq[s];
+    }
+    const int n = a.n[0] + a.n[1];
+    k_refresh<<<n > 0 ? (n + 255) / 256 : 1, 256, 0, c->stream>>>(a);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
