@@ -303,7 +303,11 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) 
     int dst = b + r;
     v.pos[dst] = v.pos_in[i];
     v.vel[dst] = v.vel_in[i];
-    v.x0[dst] = v.pstar_in[i];
+    // the w lane of a predicted position carries the particle's own sorted slot: the sand solver gets the
+    // storage slot of a staged neighbour from it (the fluid solver overwrites it with lambda)
+    float4 ps = v.pstar_in[i];
+    ps.w = __int_as_float(dst);
+    v.x0[dst] = ps;
     v.flags[dst] = v.flags_in[i];
     v.key[dst] = c;
     v.perm[dst] = mine;

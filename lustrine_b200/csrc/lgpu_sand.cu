@@ -110,9 +110,14 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     F3 deltap = f3(0.0f, 0.0f, 0.0f);
     bool touched = false;
     if (!(word & LGPU_CNT_WALK)) {
-        replay_neighbors<SOLIDS, true>(v, d, &bar, stage, cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+        // Looped replay (one group of four per iteration, the next group's codes loaded one ahead): the
+        // contact body is long, and unrolling it over the whole row made the kernel ~300 KB of code that
+        // missed the instruction cache a quarter of the time.  The old position of a sand neighbour in
+        // contact is read from the sorted storage at the slot its staged x* carries in the w lane.
+        stage_wait(&bar);
+        replay_table<SOLIDS, true>(v, d, smem_u32(stage), cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
             const bool is_sand = !(SOLIDS && (code & LGPU_SOLID_CODE));
-            sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[decode_code(d, code)]); }, deltap, touched);
+            sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
         });
     } else {
         walk<true>(v, i, f3(v.x0[i]), [&](int j, int) {
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     ps.x = fminf(fmaxf(ps.x, r), __fsub_rn(g.domainX, r));  // :307
     ps.y = fminf(fmaxf(ps.y, r), __fsub_rn(g.domainY, r));
     ps.z = fminf(fmaxf(ps.z, r), __fsub_rn(g.domainZ, r));
-    next[i] = f4(ps);
+    next[i] = f4(ps, __int_as_float(i));  // w = own sorted slot (see the replay above)
     if (sp.credits && touched) {  // :463-470: the "no gravity" bit drops at the first contact
         int a = v.flags[i];
         if (a & 2) v.flags[i] = a & ~2;

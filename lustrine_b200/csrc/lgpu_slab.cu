@@ -225,10 +225,11 @@ __global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < a.n[0] + a.n[1]) {
         const int s = t < a.n[0] ? 0 : 1, g = t - (s ? a.n[0] : 0);
-        const float4 val = a.buf[a.src[s][g]];
-        float4* dst = a.peer_buf[s] + a.dst[s][g];
+        float4 val = a.buf[a.src[s][g]];
+        const int slot = a.dst[s][g];
+        float4* dst = a.peer_buf[s] + slot;
         if (a.w_only) reinterpret_cast<float*>(dst)[3] = val.w;
-        else *dst = val;
+        else { val.w = __int_as_float(slot); *dst = val; }  // w of a full x* = the particle's slot where it is stored (sand solver)
     }
     // one system-scope fence per block, by the thread that takes the ticket: the barrier makes the block's
     // stores visible to it, the fence orders them (cumulativity) before the ticket and the flags
