@@ -74,17 +74,20 @@ struct HaloRec {
 // per context is enough.  side 0 = traffic from / to the LEFT neighbour (lower x), 1 = RIGHT.
 struct SlabHeader {
     int flag[2];        // sequence number of the last complete message from side s (written by the peer)
-    int in_cnt[2][2];   // [side][0 = migrants, 1 = ghosts] of the last halo message (written by the peer)
+    int in_cnt[2][2][2];  // [turn][side][0 = migrants, 1 = ghosts] of the halo message (written by the peer)
     int error;          // set by a wait kernel that timed out
-    int pad[25];
+    int pad[21];
 };
 struct SlabArena {
     SlabHeader* hdr;
     float4* buf[3];       // x0, pa, pb: the solver's position buffers; neighbours store their boundary
                           // particles' new values straight into this context's ghost slots
-    int* slotmap[2];      // per ghost held from side s: its sorted slot here (sent to its owner once per substep)
-    HaloRec* in_mig[2];   // migrants received from side s
-    HaloRec* in_gho[2];   // ghost copies received from side s
+    float4* rbox[2][2];   // ghost-refresh inboxes [side][turn]: the owners' new values of the ghosts held from side s, in
+                          // message order (ghost copies, then the particles that emigrated to that side)
+    // halo inboxes [side][turn]: substeps alternate between two sets, so a neighbour that is already one substep ahead
+    // never overwrites a message that has not been consumed yet (it cannot get two ahead: it waits for this slab's halo)
+    HaloRec* in_mig[2][2];  // migrants received from side s
+    HaloRec* in_gho[2][2];  // ghost copies received from side s
 };
 
 struct View {

@@ -36,8 +36,12 @@ struct SlabState {
     int tx_seq[2], rx_seq[2];
     int n_gho_out[2], n_gho_in[2], n_mig_in[2], n_mig_out[2], in_base[2], mig_in_base[2];
     int* h_counts;        // pinned: [0..7] out_cnt, [8..] SlabHeader
-    int* ref_src[2];      // ghost refresh list of side s: sorted slot here of every particle that has a ghost copy in that
-                          // neighbour (its slot there is local.slotmap[s][g], sent by the neighbour once per substep)
+    int* ref_src[2];      // ghost refresh, sending: sorted slot here of every particle that has a ghost copy in the neighbour
+                          // on side s, in message order (ghost copies sent, then migrants received from that side)
+    int* gho_slot[2];     // ghost refresh, receiving: sorted slot here of every ghost held from side s, same order as the
+                          // neighbour's ref_src (ghost copies received, then the particles that emigrated to that side)
+    int turn;             // which of the two refresh inboxes the next refresh uses
+    int halo_turn;        // which of the two halo inbox sets this substep uses
     unsigned int* push_ticket;
     bool begun;
     int n_store;
@@ -51,9 +55,9 @@ static size_t arena_layout(unsigned char* base, int cap, int halo_cap, SlabArena
     size_t off = 0;
     a->hdr = (SlabHeader*)(base + off); off += align_up(sizeof(SlabHeader), 256);
     for (int b = 0; b < 3; b++) { a->buf[b] = (float4*)(base + off); off += align_up(sizeof(float4) * (size_t)cap, 256); }
-    for (int s = 0; s < 2; s++) { a->slotmap[s] = (int*)(base + off); off += align_up(sizeof(int) * 2 * (size_t)halo_cap, 256); }
-    for (int s = 0; s < 2; s++) { a->in_mig[s] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
-    for (int s = 0; s < 2; s++) { a->in_gho[s] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
+    for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) { a->rbox[s][t] = (float4*)(base + off); off += align_up(sizeof(float4) * 2 * (size_t)halo_cap, 256); }
+    for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) { a->in_mig[s][t] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
+    for (int s = 0; s < 2; s++) for (int t = 0; t < 2; t++) { a->in_gho[s][t] = (HaloRec*)(base + off); off += align_up(sizeof(HaloRec) * (size_t)halo_cap, 256); }
     return off;
 }
 
@@ -79,7 +83,10 @@ int lgpu_slab_init(lgpu_ctx* c) {
     CUDA_TRY(cudaMalloc((void**)&S->ticket, sizeof(unsigned int) * 2));
     CUDA_TRY(cudaMemsetAsync(S->ticket, 0, sizeof(unsigned int) * 2, c->stream));
     CUDA_TRY(cudaMalloc((void**)&S->inv, sizeof(int) * (size_t)c->cap));
-    for (int s = 0; s < 2; s++) CUDA_TRY(cudaMalloc((void**)&S->ref_src[s], sizeof(int) * 2 * (size_t)S->halo_cap));
+    for (int s = 0; s < 2; s++) {
+        CUDA_TRY(cudaMalloc((void**)&S->ref_src[s], sizeof(int) * 2 * (size_t)S->halo_cap));
+        CUDA_TRY(cudaMalloc((void**)&S->gho_slot[s], sizeof(int) * 2 * (size_t)S->halo_cap));
+    }
     CUDA_TRY(cudaMalloc((void**)&S->push_ticket, sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(S->push_ticket, 0, sizeof(unsigned int), c->stream));
     CUDA_TRY(cudaMallocHost((void**)&S->h_counts, sizeof(int) * 64));
@@ -95,7 +102,7 @@ void lgpu_slab_free(lgpu_ctx* c) {
         if (S->peer_ipc[s] && S->peer_base[s]) cudaIpcCloseMemHandle(S->peer_base[s]);
         cudaFree(S->out_mig[s]); cudaFree(S->out_gho[s]); cudaFree(S->gho_src[s]); cudaFree(S->mig_src[s]);
     }
-    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->ref_src[0]); cudaFree(S->ref_src[1]); cudaFree(S->push_ticket); cudaFree(S->d_xfer);
+    cudaFree(S->arena); cudaFree(S->out_cnt); cudaFree(S->ticket); cudaFree(S->inv); cudaFree(S->ref_src[0]); cudaFree(S->ref_src[1]); cudaFree(S->gho_slot[0]); cudaFree(S->gho_slot[1]); cudaFree(S->push_ticket); cudaFree(S->d_xfer);
     cudaFreeHost(S->h_counts);
     delete S;
     c->slab = nullptr;
@@ -171,7 +178,7 @@ __device__ __forceinline__ void signal_after_all_blocks(unsigned int* ticket, vo
 // halo message: migrants + ghost copies + their counts, then the flag
 __global__ void __launch_bounds__(256) k_push_halo(const HaloRec* __restrict__ mig, const HaloRec* __restrict__ gho, const int* __restrict__ out_cnt, int side,
                                                    int halo_cap, HaloRec* __restrict__ dst_mig, HaloRec* __restrict__ dst_gho, SlabHeader* dst_hdr, int dst_side,
-                                                   unsigned int* ticket, int seq) {
+                                                   int turn, unsigned int* ticket, int seq) {
     const int nm = min(out_cnt[side], halo_cap), ng = min(out_cnt[2 + side], halo_cap);
     const uint4* s0 = reinterpret_cast<const uint4*>(mig);
     uint4* d0 = reinterpret_cast<uint4*>(dst_mig);
@@ -180,56 +187,53 @@ __global__ void __launch_bounds__(256) k_push_halo(const HaloRec* __restrict__ m
     const uint4* s1 = reinterpret_cast<const uint4*>(gho);
     uint4* d1 = reinterpret_cast<uint4*>(dst_gho);
     for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < wg; t += (long)gridDim.x * blockDim.x) d1[t] = s1[t];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { dst_hdr->in_cnt[dst_side][0] = nm; dst_hdr->in_cnt[dst_side][1] = ng; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dst_hdr->in_cnt[turn][dst_side][0] = nm; dst_hdr->in_cnt[turn][dst_side][1] = ng; }
     signal_after_all_blocks(ticket, &dst_hdr->flag[dst_side], seq);
 }
 
-// slot-map message, once per substep after the sort: for every ghost this context holds from side s
-// (ghost copies first, then the particles that emigrated to that side), its sorted slot here.  The
-// owner turns it into the per-particle store targets of the fused ghost refresh.
-__global__ void __launch_bounds__(256) k_push_slotmap(const int* __restrict__ inv, int in_base, int n_gho, const int* __restrict__ mig_src, int n_mig,
-                                                      int* __restrict__ dst, SlabHeader* dst_hdr, int dst_side, unsigned int* ticket, int seq) {
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_gho + n_mig; g += gridDim.x * blockDim.x)
-        dst[g] = inv[g < n_gho ? in_base + g : mig_src[g - n_gho]];
-    signal_after_all_blocks(ticket, &dst_hdr->flag[dst_side], seq);
-}
-// owner side: particle sent as ghost copy g (or received as migrant g - n_gho) -> its sorted slot here
-__global__ void __launch_bounds__(256) k_build_refresh_list(const int* __restrict__ inv, const int* __restrict__ gho_src, int n_gho, int mig_in_base, int n_mig,
-                                                            int* __restrict__ ref_src) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_gho + n_mig) return;
-    ref_src[g] = inv[g < n_gho ? gho_src[g] : mig_in_base + (g - n_gho)];
+// Ghost-refresh lists, built locally once per substep after the sort.  Both ends of a slab boundary
+// enumerate the shared particles in the same (message) order, so no slot numbers are exchanged:
+//   receiving end: ghost g held from side s (ghost copies received, then the particles that emigrated
+//                  to that side and stay here as ghosts) -> its sorted slot here;
+//   sending end:   particle g mirrored on side s (ghost copies sent, then the migrants received from
+//                  that side) -> its sorted slot here.
+__global__ void __launch_bounds__(256) k_build_refresh_lists(const int* __restrict__ inv, int in_base, int n_gho_in, const int* __restrict__ mig_src, int n_mig_out,
+                                                             int* __restrict__ gho_slot, const int* __restrict__ gho_src, int n_gho_out, int mig_in_base,
+                                                             int n_mig_in, int* __restrict__ ref_src) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_gho_in + n_mig_out) gho_slot[g] = inv[g < n_gho_in ? in_base + g : mig_src[g - n_gho_in]];
+    if (g < n_gho_out + n_mig_in) ref_src[g] = inv[g < n_gho_out ? gho_src[g] : mig_in_base + (g - n_gho_out)];
 }
 
-// Ghost refresh after a solver pass: copies the value every boundary particle got in the pass
-// (x* as a float4, or only lambda in the w lane) from `buf` into its ghost slot in the neighbour's
-// copy of the same buffer — peer stores over NVLink —, then the last block raises the neighbours'
-// sequence flags and waits for theirs.  The stores are NOT issued by the solver kernels themselves:
-// a store to peer memory holds up the SM's memory pipeline for microseconds, which made the passes
-// 20-45 % slower; here they come from a handful of blocks that do nothing else.
+// Ghost refresh after a solver pass, sending half: packs the value every mirrored particle got in the
+// pass (x* as a float4, or only lambda as one float) CONTIGUOUSLY into the neighbour's refresh inbox —
+// coalesced peer stores over NVLink; scattered 16- and 4-byte stores into the ghost slots ran at a
+// fraction of the link rate —, then the last block raises the neighbours' sequence flags and waits
+// for theirs.  The stores are NOT issued by the solver kernels themselves: a store to peer memory
+// holds up the SM's memory pipeline for microseconds, which made the passes 20-45 % slower.
 struct RefreshArgs {
-    const float4* buf;
+    float4* buf;             // the buffer the pass wrote (read here, ghost slots written by k_scatter_refresh)
     int w_only;
-    const int* src[2];
-    const int* dst[2];       // slot maps (written by the neighbours into this slab's arena)
-    int n[2];
-    float4* peer_buf[2];
+    const int* src[2];       // ref_src
+    int n_out[2];
+    float4* peer_box[2];     // the neighbour's inbox for this slab's values
     volatile int* peer_flag[2];
     int seq[2];
     const volatile int* flag[2];
     int expected[2];
     unsigned int* ticket;
     int* error;
+    const int* slot[2];      // gho_slot
+    int n_in[2];
+    const float4* box[2];    // this slab's inboxes
 };
 __global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.n[0] + a.n[1]) {
-        const int s = t < a.n[0] ? 0 : 1, g = t - (s ? a.n[0] : 0);
-        float4 val = a.buf[a.src[s][g]];
-        const int slot = a.dst[s][g];
-        float4* dst = a.peer_buf[s] + slot;
-        if (a.w_only) reinterpret_cast<float*>(dst)[3] = val.w;
-        else { val.w = __int_as_float(slot); *dst = val; }  // w of a full x* = the particle's slot where it is stored (sand solver)
+    if (t < a.n_out[0] + a.n_out[1]) {
+        const int s = t < a.n_out[0] ? 0 : 1, g = t - (s ? a.n_out[0] : 0);
+        const float4 val = a.buf[a.src[s][g]];
+        if (a.w_only) reinterpret_cast<float*>(a.peer_box[s])[g] = val.w;
+        else a.peer_box[s][g] = val;
     }
     // one system-scope fence per block, by the thread that takes the ticket: the barrier makes the block's
     // stores visible to it, the fence orders them (cumulativity) before the ticket and the flags
@@ -249,6 +253,20 @@ __global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
             }
             __threadfence_system();
         }
+    }
+}
+// receiving half (next kernel on the stream): inbox -> ghost slots of the same buffer
+__global__ void __launch_bounds__(256) k_scatter_refresh(RefreshArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_in[0] + a.n_in[1]) return;
+    const int s = t < a.n_in[0] ? 0 : 1, g = t - (s ? a.n_in[0] : 0);
+    const int slot = a.slot[s][g];
+    if (a.w_only) {
+        reinterpret_cast<float*>(a.buf + slot)[3] = __ldcv(reinterpret_cast<const float*>(a.box[s]) + g);
+    } else {
+        float4 val = __ldcv(a.box[s] + g);
+        val.w = __int_as_float(slot);  // w of a full x* = the particle's slot where it is stored (sand solver)
+        a.buf[slot] = val;
     }
 }
 
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_append_halo(View v, int n_store,
 __global__ void k_compact_owned(View v, int n_store, float* __restrict__ pos, float* __restrict__ vel, int* __restrict__ flags, int* __restrict__ ids,
                                 int* __restrict__ counter);
 int lgpu_preload_slab() {
-    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_push_slotmap); LGPU_PRELOAD(k_build_refresh_list); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_refresh);
+    LGPU_PRELOAD(k_push_halo); LGPU_PRELOAD(k_build_refresh_lists); LGPU_PRELOAD(k_wait_flag); LGPU_PRELOAD(k_refresh); LGPU_PRELOAD(k_scatter_refresh);
     LGPU_PRELOAD(k_append_halo); LGPU_PRELOAD(k_compact_owned);
     return LGPU_OK;
 }
@@ -321,8 +339,8 @@ int lgpu_slab_begin(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     for (int s = 0; s < 2; s++) {
         if (!S->has_nbr[s]) continue;
         const int ds = 1 - s;  // my right neighbour receives from its left
-        k_push_halo<<<64, 256, 0, c->stream>>>(S->out_mig[s], S->out_gho[s], S->out_cnt, s, S->halo_cap, S->peer[s].in_mig[ds], S->peer[s].in_gho[ds],
-                                              S->peer[s].hdr, ds, S->ticket + s, ++S->tx_seq[s]);
+        k_push_halo<<<256, 256, 0, c->stream>>>(S->out_mig[s], S->out_gho[s], S->out_cnt, s, S->halo_cap, S->peer[s].in_mig[ds][S->halo_turn],
+                                               S->peer[s].in_gho[ds][S->halo_turn], S->peer[s].hdr, ds, S->halo_turn, S->ticket + s, ++S->tx_seq[s]);
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -347,7 +365,9 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     if (H->error) { lgpu_set_error("slab: timed out waiting for a neighbouring slab's halo message"); return LGPU_ERR_CUDA; }
     if (S->h_counts[4]) { lgpu_set_error("slab: halo capacity %d exceeded (%d records dropped)", S->halo_cap, S->h_counts[4]); return LGPU_ERR_CAPACITY; }
     int m[2] = {0, 0}, g[2] = {0, 0};
-    for (int s = 0; s < 2; s++) if (S->has_nbr[s]) { m[s] = H->in_cnt[s][0]; g[s] = H->in_cnt[s][1]; }
+    const int ht = S->halo_turn;
+    S->halo_turn ^= 1;
+    for (int s = 0; s < 2; s++) if (S->has_nbr[s]) { m[s] = H->in_cnt[ht][s][0]; g[s] = H->in_cnt[ht][s][1]; }
     const int emigrated = (S->has_nbr[0] ? S->h_counts[0] : 0) + (S->has_nbr[1] ? S->h_counts[1] : 0);
     const int in_total = m[0] + m[1] + g[0] + g[1];
     if (S->n_store + in_total > c->cap) { lgpu_set_error("slab: %d + %d particles > capacity %d", S->n_store, in_total, c->cap); return LGPU_ERR_CAPACITY; }
@@ -366,8 +386,8 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     c->n_owned = c->n - c->n_ghost;
     if (in_total > 0) {
         View v = lgpu_make_view(c);
-        k_append_halo<<<lgpu_blocks(in_total), LGPU_BLOCK, 0, c->stream>>>(v, S->n_store, m[0], m[1], g[0], g[1], S->local.in_mig[0], S->local.in_mig[1],
-                                                                            S->local.in_gho[0], S->local.in_gho[1]);
+        k_append_halo<<<lgpu_blocks(in_total), LGPU_BLOCK, 0, c->stream>>>(v, S->n_store, m[0], m[1], g[0], g[1], S->local.in_mig[0][ht], S->local.in_mig[1][ht],
+                                                                            S->local.in_gho[0][ht], S->local.in_gho[1][ht]);
         c->launches++;
     }
     int st;
@@ -377,26 +397,20 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, false);  // particle ids are global: never renumbered
     if (st) return st;
-    // tell the owners where their particles sit here, and learn where mine sit in the neighbours
+    // ghost-refresh lists of this substep (local: both ends enumerate the shared particles in message order)
     for (int s = 0; s < 2; s++) {
         if (!S->has_nbr[s]) continue;
-        const int ds = 1 - s, n = S->n_gho_in[s] + S->n_mig_out[s];
-        int blocks = (n + 255) / 256;
-        blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
-        k_push_slotmap<<<blocks, 256, 0, c->stream>>>(S->inv, S->in_base[s], S->n_gho_in[s], S->mig_src[s], S->n_mig_out[s], S->peer[s].slotmap[ds],
-                                                      S->peer[s].hdr, ds, S->ticket + s, ++S->tx_seq[s]);
-        c->launches++;
+        const int n_in = S->n_gho_in[s] + S->n_mig_out[s], n_out = S->n_gho_out[s] + S->n_mig_in[s];
+        const int n = n_in > n_out ? n_in : n_out;
+        if (n > 0) {
+            k_build_refresh_lists<<<(n + 255) / 256, 256, 0, c->stream>>>(S->inv, S->in_base[s], S->n_gho_in[s], S->mig_src[s], S->n_mig_out[s], S->gho_slot[s],
+                                                                         S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s], S->ref_src[s]);
+            c->launches++;
+        }
     }
     lgpu_mark(c, 4);
-    st = lgpu_launch_build_table(c, mode == 2);  // overlaps the slot-map messages in flight
+    st = lgpu_launch_build_table(c, mode == 2);
     if (st) return st;
-    for (int s = 0; s < 2; s++) {
-        if (!S->has_nbr[s]) continue;
-        k_wait_flag<<<1, 1, 0, c->stream>>>(&S->local.hdr->flag[s], ++S->rx_seq[s], &S->local.hdr->error);
-        const int n = S->n_gho_out[s] + S->n_mig_in[s];
-        if (n > 0) k_build_refresh_list<<<(n + 255) / 256, 256, 0, c->stream>>>(S->inv, S->gho_src[s], S->n_gho_out[s], S->mig_in_base[s], S->n_mig_in[s], S->ref_src[s]);
-        c->launches += 2;
-    }
     st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
     if (st) return st;
     lgpu_mark(c, -1);
@@ -409,31 +423,39 @@ bool lgpu_slab_active(const lgpu_ctx* c) {
     return S && (S->has_nbr[0] || S->has_nbr[1]);
 }
 
-// after a solver kernel that wrote `buf`: refresh the neighbours' ghost copies, signal, wait (one launch)
+// after a solver kernel that wrote `buf`: send the mirrored particles' new values to the neighbours' inboxes,
+// signal, wait (k_refresh), then move what the neighbours sent into this slab's ghost slots (k_scatter_refresh)
 int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only) {
     SlabState* S = c->slab;
     if (!lgpu_slab_active(c)) return LGPU_OK;
-    const int b = buf == c->x0 ? 0 : (buf == c->pa ? 1 : 2);
+    const int turn = S->turn;
+    S->turn ^= 1;
     RefreshArgs a;
     memset(&a, 0, sizeof(a));
-    a.buf = buf;
+    a.buf = const_cast<float4*>(buf);
     a.w_only = w_only ? 1 : 0;
     a.ticket = S->push_ticket;
     a.error = &S->local.hdr->error;
     for (int s = 0; s < 2; s++) {
         if (!S->has_nbr[s]) continue;
         a.src[s] = S->ref_src[s];
-        a.dst[s] = S->local.slotmap[s];
-        a.n[s] = S->n_gho_out[s] + S->n_mig_in[s];
-        a.peer_buf[s] = S->peer[s].buf[b];
+        a.n_out[s] = S->n_gho_out[s] + S->n_mig_in[s];
+        a.peer_box[s] = S->peer[s].rbox[1 - s][turn];
         a.peer_flag[s] = &S->peer[s].hdr->flag[1 - s];
         a.seq[s] = ++S->tx_seq[s];
         a.flag[s] = &S->local.hdr->flag[s];
         a.expected[s] = ++S->rx_seq[s];
+        a.slot[s] = S->gho_slot[s];
+        a.n_in[s] = S->n_gho_in[s] + S->n_mig_out[s];
+        a.box[s] = S->local.rbox[s][turn];
     }
-    const int n = a.n[0] + a.n[1];
-    k_refresh<<<n > 0 ? (n + 255) / 256 : 1, 256, 0, c->stream>>>(a);
+    const int n_out = a.n_out[0] + a.n_out[1], n_in = a.n_in[0] + a.n_in[1];
+    k_refresh<<<n_out > 0 ? (n_out + 255) / 256 : 1, 256, 0, c->stream>>>(a);
     c->launches++;
+    if (n_in > 0) {
+        k_scatter_refresh<<<(n_in + 255) / 256, 256, 0, c->stream>>>(a);
+        c->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }
