@@ -109,7 +109,7 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     CUDA_TRY(dalloc(&c->lambda, cap)); CUDA_TRY(dalloc(&c->density, cap));
     CUDA_TRY(dalloc(&c->lambda_head, (size_t)LGPU_LAMBDA_HEAD));
     CUDA_TRY(dalloc(&c->counters, (size_t)4));
-    c->stage_bytes = sizeof(float) * 3 * cap;
+    c->stage_bytes = sizeof(float) * 8 * cap;  // pos 3 + vel 3 + flags 1 + ids 1 words per particle
     CUDA_TRY(cudaMalloc((void**)&c->d_stage, c->stage_bytes));
     CUDA_TRY(cudaMemsetAsync(c->cell_count, 0, sizeof(int) * C1, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->cell_start, 0, sizeof(int) * C1, c->stream));
@@ -228,27 +228,23 @@ __global__ void k_pack1_by_orig(const int* __restrict__ src, const int* __restri
     dst[orig[i]] = src[i];
 }
 
+// The device-side staging area holds all arrays of one transfer side by side (pos 3n, vel 3n, flags n,
+// ids n: 8 words per particle), so a transfer is a run of back-to-back copies and kernels with ONE
+// synchronisation at the end.
 int lgpu_put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float* vel, const int* flags, const int* ids) {
     if (n == 0) return LGPU_OK;
     const int blocks = lgpu_blocks(n);
-    CUDA_TRY(cudaMemcpyAsync(c->d_stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->d_stage, n, c->pos[0], offset);
-    if (vel) {
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->d_stage, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-        k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->d_stage, n, c->vel[0], offset);
-    }
-    int *d_flags = nullptr, *d_ids = nullptr;
-    if (flags || ids) CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (flags) {
-        d_flags = (int*)c->d_stage;
-        CUDA_TRY(cudaMemcpyAsync(d_flags, flags, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (ids) {
-        d_ids = (int*)c->d_stage + n;
-        CUDA_TRY(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    }
-    k_fill_meta<<<blocks, LGPU_BLOCK, 0, c->stream>>>(n, offset, d_flags, c->flags[0], c->orig[0], c->vel[0], vel ? 0 : 1, d_ids);
+    float* d_pos = c->d_stage;
+    float* d_vel = d_pos + 3 * (size_t)n;
+    int* d_flags = (int*)(d_vel + 3 * (size_t)n);
+    int* d_ids = d_flags + n;
+    CUDA_TRY(cudaMemcpyAsync(d_pos, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (vel) CUDA_TRY(cudaMemcpyAsync(d_vel, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (flags) CUDA_TRY(cudaMemcpyAsync(d_flags, flags, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    if (ids) CUDA_TRY(cudaMemcpyAsync(d_ids, ids, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(d_pos, n, c->pos[0], offset);
+    if (vel) k_unpack3<<<blocks, LGPU_BLOCK, 0, c->stream>>>(d_vel, n, c->vel[0], offset);
+    k_fill_meta<<<blocks, LGPU_BLOCK, 0, c->stream>>>(n, offset, flags ? d_flags : nullptr, c->flags[0], c->orig[0], c->vel[0], vel ? 0 : 1, ids ? d_ids : nullptr);
     c->launches += vel ? 3 : 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -303,25 +299,26 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
     const int n = c->n_owned;
     if (n == 0) return LGPU_OK;
     const int blocks = lgpu_blocks(n);
+    float* d_pos = c->d_stage;
+    float* d_vel = d_pos + 3 * (size_t)n;
+    int* d_flags = (int*)(d_vel + 3 * (size_t)n);
     if (pos) {
-        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->pos[0], c->orig[0], n, c->d_stage);
-        CUDA_TRY(cudaMemcpyAsync(pos, c->d_stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->pos[0], c->orig[0], n, d_pos);
+        CUDA_TRY(cudaMemcpyAsync(pos, d_pos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
     if (vel) {
-        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->vel[0], c->orig[0], n, c->d_stage);
-        CUDA_TRY(cudaMemcpyAsync(vel, c->d_stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->vel[0], c->orig[0], n, d_vel);
+        CUDA_TRY(cudaMemcpyAsync(vel, d_vel, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
     if (flags) {
-        k_pack1_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->flags[0], c->orig[0], n, (int*)c->d_stage);
-        CUDA_TRY(cudaMemcpyAsync(flags, c->d_stage, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        k_pack1_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->flags[0], c->orig[0], n, d_flags);
+        CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LGPU_OK;
 }
 
