@@ -43,6 +43,7 @@ WORKLOADS = {
     # name: (kind, cube side, iterations, dt)
     "dam_break_1m": ("fluid", 100, 4, 0.01),    # BASELINE.json configs[1]
     "dam_break_64k": ("fluid", 40, 4, 0.01),
+    "dam_break_1m_k1": ("fluid", 100, 1, 0.01),  # one solver iteration (the reference's own setting)
     "dam_break_2m": ("fluid", 126, 4, 0.01),    # weak scaling: N x 1M particles on N GPUs
     "dam_break_4m": ("fluid", 159, 4, 0.01),
     "dam_break_8m": ("fluid", 200, 4, 0.01),
