@@ -9,6 +9,8 @@
 //                    and on the last iteration also v and x                         (+24 B/particle)
 // The delta-p output is double-buffered (Jacobi); the reference's in-place loop is sequential
 // Gauss-Seidel in index order and is compared through the Jacobi oracle.
+#include <stdlib.h>
+
 #include "lgpu_neighbors.cuh"
 
 struct FluidParams {
@@ -313,10 +315,12 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_lambda_
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     const int ic = i < v.n ? i : 0;
+    pdl_trigger();
     const int word = i < v.n ? v.nbr_cnt[i] : LGPU_CNT_GHOST;
-    const float4 ci = cur[ic];
     TableRow<8> row;
     load_row_early<8, 5>(row, v, ic);
+    pdl_wait();  // everything above is independent of the previous pass; x* (and lambda in its w lane) is not
+    const float4 ci = cur[ic];
     stage_begin(v, cur, d, &bar, stage);
     const int cnt = word & LGPU_CNT_MASK;
     const bool table = !(word & (LGPU_CNT_GHOST | LGPU_CNT_WALK));
@@ -376,10 +380,12 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_fluid_deltap_
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
     const int ic = i < v.n ? i : 0;
+    pdl_trigger();
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
-    const float4 ci = cur[ic];
     TableRow<8> row;
     load_row_early<8, 5>(row, v, ic);
+    pdl_wait();  // everything above is independent of the previous pass; x* and lambda are not
+    const float4 ci = cur[ic];
     stage_begin(v, cur, d, &bar, stage);
     const int cnt = word & LGPU_CNT_MASK;
     const bool table = word != -1 && !(word & (LGPU_CNT_GHOST | LGPU_CNT_WALK));
@@ -460,14 +466,18 @@ static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     const bool slab = lgpu_slab_active(c);
+    // programmatic dependent launch between the passes (not across the refresh kernels of slab mode, not with
+    // per-launch event marks in between); LGPU_PDL=0 turns it off
+    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
+    const bool pdl = pdl_env && !slab && !c->phase_timing;
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);
-        k_fluid_lambda_fast<SOLIDS><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur);
+        CUDA_TRY(launch_pdl(k_fluid_lambda_fast<SOLIDS>, blocks, LGPU_TILE, smem, c->stream, pdl && it > 0, v, fp, cur));
         if (slab) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
-        if (it == iterations - 1) k_fluid_deltap_fast<SOLIDS, true><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
-        else k_fluid_deltap_fast<SOLIDS, false><<<blocks, LGPU_TILE, smem, c->stream>>>(v, fp, cur, next);
+        if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap_fast<SOLIDS, true>, blocks, LGPU_TILE, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
+        else CUDA_TRY(launch_pdl(k_fluid_deltap_fast<SOLIDS, false>, blocks, LGPU_TILE, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
         c->launches += 2;
         if (slab && it < iterations - 1) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;

@@ -168,6 +168,25 @@ __device__ __forceinline__ void stage_begin(const View& v, const float4* __restr
 }
 __device__ __forceinline__ void stage_wait(uint64_t* bar) { mbar_wait(bar, 0); }
 
+// Programmatic dependent launch between consecutive solver passes: a pass lets the next one start
+// launching as soon as all of its own blocks are resident (pdl_trigger at the top), and the next pass
+// runs its independent preamble — list length, table rows — before it waits for the previous pass's
+// memory (pdl_wait), so that launch latency, ramp-up and the table loads overlap the previous tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // virtual-slot mode: at most 3 ranges, unused ones have s0 = INT_MAX
 __device__ __forceinline__ int decode_virtual(const BlkDesc& d, uint32_t code) {
     const int m = ((int)code >= d.s0[1] ? 1 : 0) + ((int)code >= d.s0[2] ? 1 : 0);

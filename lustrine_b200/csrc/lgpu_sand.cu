@@ -8,6 +8,7 @@
 // next x* to the other ping-pong buffer (the reference's positions_tmp copy, :310).
 #include "lgpu_neighbors.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 struct SandParams {
     float dt, mass, diameter;
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams
     __shared__ BlkDesc d;
     __shared__ uint64_t bar;
     const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    stage_begin(v, cur, d, &bar, stage);
+    pdl_trigger();
     const int word = i < v.n ? v.nbr_cnt[i] : -1;
+    pdl_wait();  // the list length is independent of the previous pass; x* is not
+    stage_begin(v, cur, d, &bar, stage);
     if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
     if (word == -1) {
     } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
@@ -170,6 +173,8 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     const bool solids = c->n_solid > 0;
     const float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
+    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
+    const bool pdl = pdl_env && !lgpu_slab_active(c) && !c->phase_timing;  // see run_fluid_fast
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
@@ -181,7 +186,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
             CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                                \
         }                                                                                                               \
-        k_sand_iteration<PP, SS, LL><<<blocks, LGPU_TILE, smem, c->stream>>>(v, sp, cur, next);                         \
+        CUDA_TRY(launch_pdl(k_sand_iteration<PP, SS, LL>, blocks, LGPU_TILE, smem, c->stream, pdl && it > 0, v, sp, cur, next)); \
     } while (0)
         if (p.exact_math) {
             if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
