@@ -203,6 +203,7 @@ static inline void lgpu_mark(lgpu_ctx* c, int phase) {
 // copies the boundary particles' new values into the neighbours' ghost slots (peer stores over
 // NVLink), raises the neighbours' sequence flags and waits for theirs.  w_only: just lambda (w lane).
 bool lgpu_slab_active(const lgpu_ctx* c);
+bool lgpu_slab_pdl_ok(const lgpu_ctx* c);
 int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only);
 int lgpu_slab_init(lgpu_ctx* c);
 int lgpu_slab_check(lgpu_ctx* c);

@@ -16,7 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "lgpu_internal.cuh"
+#include "lgpu_neighbors.cuh"
 
 struct SlabState {
     int halo_cap;
@@ -229,9 +229,15 @@ struct RefreshArgs {
 };
 __global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();  // (programmatic dependent launch: see pdl_trigger in lgpu_neighbors.cuh)
+    int s = 0, g = 0, src = 0;
     if (t < a.n_out[0] + a.n_out[1]) {
-        const int s = t < a.n_out[0] ? 0 : 1, g = t - (s ? a.n_out[0] : 0);
-        const float4 val = a.buf[a.src[s][g]];
+        s = t < a.n_out[0] ? 0 : 1; g = t - (s ? a.n_out[0] : 0);
+        src = a.src[s][g];
+    }
+    pdl_wait();     // the list above does not depend on the solver pass; the values do
+    if (t < a.n_out[0] + a.n_out[1]) {
+        const float4 val = a.buf[src];
         if (a.w_only) reinterpret_cast<float*>(a.peer_box[s])[g] = val.w;
         else a.peer_box[s][g] = val;
     }
@@ -258,9 +264,12 @@ __global__ void __launch_bounds__(256) k_refresh(RefreshArgs a) {
 // receiving half (next kernel on the stream): inbox -> ghost slots of the same buffer
 __global__ void __launch_bounds__(256) k_scatter_refresh(RefreshArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_in[0] + a.n_in[1]) return;
-    const int s = t < a.n_in[0] ? 0 : 1, g = t - (s ? a.n_in[0] : 0);
-    const int slot = a.slot[s][g];
+    pdl_trigger();
+    const bool live = t < a.n_in[0] + a.n_in[1];
+    const int s = live && t >= a.n_in[0] ? 1 : 0, g = live ? t - (s ? a.n_in[0] : 0) : 0;
+    const int slot = live ? a.slot[s][g] : 0;
+    pdl_wait();     // k_refresh has seen the neighbours' flags: the inboxes are complete
+    if (!live) return;
     if (a.w_only) {
         reinterpret_cast<float*>(a.buf + slot)[3] = __ldcv(reinterpret_cast<const float*>(a.box[s]) + g);
     } else {
@@ -418,6 +427,19 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     return LGPU_OK;
 }
 
+// Programmatic dependent launch keeps the next solver kernel's blocks resident while k_refresh waits for the
+// neighbours.  That is only safe when every neighbour runs on ANOTHER GPU: slabs that share a device (the
+// virtual ranks of the single-GPU tests) would starve each other of SM resources and dead-lock.
+// Measured on 2 B200s: 1.5 % per substep.  Off unless LGPU_PDL_SLAB=1 until it has been run on 4 and 8 GPUs.
+bool lgpu_slab_pdl_ok(const lgpu_ctx* c) {
+    const SlabState* S = c->slab;
+    if (!S || (!S->has_nbr[0] && !S->has_nbr[1])) return true;
+    static const bool on = getenv("LGPU_PDL_SLAB") && atoi(getenv("LGPU_PDL_SLAB")) != 0;
+    if (!on) return false;
+    for (int s = 0; s < 2; s++) if (S->has_nbr[s] && !S->peer_ipc[s]) return false;
+    return true;
+}
+
 bool lgpu_slab_active(const lgpu_ctx* c) {
     const SlabState* S = c->slab;
     return S && (S->has_nbr[0] || S->has_nbr[1]);
@@ -450,10 +472,12 @@ int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only) {
         a.box[s] = S->local.rbox[s][turn];
     }
     const int n_out = a.n_out[0] + a.n_out[1], n_in = a.n_in[0] + a.n_in[1];
-    k_refresh<<<n_out > 0 ? (n_out + 255) / 256 : 1, 256, 0, c->stream>>>(a);
+    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
+    const bool pdl = pdl_env && !c->phase_timing && lgpu_slab_pdl_ok(c);
+    CUDA_TRY(launch_pdl(k_refresh, n_out > 0 ? (n_out + 255) / 256 : 1, 256, 0, c->stream, pdl, a));
     c->launches++;
     if (n_in > 0) {
-        k_scatter_refresh<<<(n_in + 255) / 256, 256, 0, c->stream>>>(a);
+        CUDA_TRY(launch_pdl(k_scatter_refresh, (n_in + 255) / 256, 256, 0, c->stream, pdl, a));
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
