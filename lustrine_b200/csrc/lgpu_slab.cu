@@ -6,13 +6,14 @@
 //
 // Per substep, between neighbouring slabs only (no collective):
 //   1. after predict: particles whose predicted cell column left the slab MIGRATE (x, v, x*, flags,
-//      id); particles in the first / last owned column are also sent as GHOST copies;
-//   2. after every solver pass but the last: the ghosts' x* (and lambda in .w) are REFRESHED from
-//      their owners.
+//      id); particles in the first / last owned column are also sent as GHOST copies (k_push_halo);
+//   2. after every solver pass but the last: the ghosts' x* (or just lambda) are REFRESHED from
+//      their owners (k_refresh packs them into the neighbour's inbox, k_scatter_refresh unpacks).
 // All traffic is written by the sender's kernels straight into the receiver's memory over
 // NVLink (peer-mapped "arena", one CUDA IPC handle per context; a plain pointer for contexts that
-// share a process), followed by a sequence-number flag; the receiver's stream waits on the flag
-// with a one-thread kernel.  Nothing goes through the host except four counters per substep.
+// share a process), followed by a sequence-number flag that the receiver's kernels poll.  Both ends
+// of a boundary enumerate the shared particles in message order, so no slot numbers travel.  Nothing
+// goes through the host except four counters per substep.
 #include <stdlib.h>
 #include <string.h>
 
