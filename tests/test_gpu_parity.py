@@ -443,3 +443,118 @@ def test_against_compiled_reference_if_present():
             close(pos, rp, "position")
             close(vel, rv, "velocity", atol=1e-3)
     R.close()
+
+
+# ----------------------------------------------------------------------------------------------
+def test_full_size_properties_1m():
+    """BASELINE size (configs[1]: 100^3 = 1M particles, K = 4), where the oracle is too slow to run per
+    substep: size-independent properties of one substep.
+      * keys = get_cell_id of the predicted positions (recomputed here in numpy fp32), storage sorted by
+        key, stable inside a cell, cell offsets consistent with the keys;
+      * neighbour lists: self included exactly once, every entry within h of the build-time x*,
+        symmetric (j in N(i) <=> i in N(j)), ascending sorted slot; counts equal to a brute-force count
+        on a random sample of particles;
+      * throughput arithmetic vs exact arithmetic from the same state: positions within the parity
+        tolerance; fast kernels vs generic kernels likewise."""
+    domain, sand = scenes.dam_break(100)
+    n = len(sand)
+    kw = dict(dt=0.01, iterations=4, literal_lambda_index=0)
+    out = {}
+    with lgpu.Context(domain, capacity_sand=n) as G:
+        G.upload_sand(sand)
+        G.step_fluid(exact_math=1, **kw)
+        keys = G.dump(lgpu.DUMP_KEYS).astype(np.int64)
+        orig = G.dump(lgpu.DUMP_ORIG)
+        cell_start = G.dump(lgpu.DUMP_CELL_START).astype(np.int64)
+        off, flat = G.neighbors()
+        out["exact"] = G.download()[0]
+        grid = {"grid": tuple(G.grid), "cell_size": G.cell_size, "kernel_radius": G.kernel_radius}
+    # predicted positions of the substep as the reference computes them (src/Simulate.cpp:49-50, zero initial
+    # velocity): v = gravity * mass * dt, x* = x + v * dt, every operation rounded to fp32
+    p = lgpu.default_step_params(**kw)
+    dt = np.float32(min(max(p.dt, 0.001), 0.01))
+    xs = sand.copy()
+    for a in range(3):
+        va = np.float32(np.float32(np.float32(p.gravity[a]) * np.float32(p.mass)) * dt)
+        xs[:, a] = xs[:, a] + np.float32(va * dt)
+    cs = np.float32(grid["cell_size"])
+    c = (xs / cs).astype(np.int64)
+    gX, gY, gZ = grid["grid"]
+    ref_keys = c[:, 1] * gX * gZ + c[:, 0] * gZ + c[:, 2]
+    assert np.array_equal(keys, ref_keys[orig]), "cell keys at 1M"
+    assert np.all(np.diff(keys) >= 0)
+    assert np.all(np.diff(orig)[np.diff(keys) == 0] > 0), "stable inside a cell"
+    assert np.array_equal(cell_start[:-1], np.searchsorted(keys, np.arange(len(cell_start) - 1))), "cell offsets"
+    assert cell_start[-1] == n
+    # neighbour lists
+    cnt = np.diff(off)
+    owner = np.repeat(np.arange(n), cnt)
+    assert flat.min() >= 0 and flat.max() < n
+    assert int((flat == owner).sum()) == n, "self exactly once in every list"
+    xs_sorted = xs[orig]
+    d = xs_sorted[owner] - xs_sorted[flat]
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    h = np.float32(grid["kernel_radius"])
+    assert np.all(d2 <= h * h), "every list entry within h"
+    seg_sorted = np.ones(len(flat), bool)
+    seg_sorted[1:] = (np.diff(flat) > 0) | (np.diff(owner) != 0)
+    assert seg_sorted.all(), "lists in ascending sorted slot"
+    pair = owner.astype(np.int64) * n + flat
+    rev = flat.astype(np.int64) * n + owner
+    assert np.array_equal(np.sort(pair), np.sort(rev)), "neighbour relation is symmetric"
+    rng = np.random.default_rng(7)
+    for i in rng.integers(0, n, 64):
+        dd = xs_sorted - xs_sorted[i]
+        r2 = (dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2]
+        assert int((r2 <= h * h).sum()) == cnt[i], "brute-force neighbour count"
+    # arithmetic policies and kernel variants from the same state
+    for name, exact, generic in (("fast", 0, 0), ("generic", 0, 1)):
+        with lgpu.Context(domain, capacity_sand=n) as G:
+            G.set_generic_kernels(generic)
+            G.upload_sand(sand)
+            G.step_fluid(exact_math=exact, **kw)
+            out[name] = G.download()[0]
+    close(out["fast"], out["exact"], "fast vs exact")
+    close(out["generic"], out["exact"], "generic vs exact")
+
+
+def test_full_size_properties_sand_4m():
+    """BASELINE size (configs[2]: 160^3 = 4M sand particles on a voxel floor with obstacle boxes): the
+    reference permutes its storage into the stable cell-sorted order, so after a step the storage is
+    sorted by the cell of the predicted positions, the permutation is a bijection that keeps the
+    previous order inside every cell, neighbour counts are symmetric in total, and throughput
+    arithmetic agrees with exact arithmetic within the parity tolerance."""
+    domain, sand, solids = scenes.sand_pile(160)
+    n = len(sand)
+    kw = dict(dt=0.016, iterations=4)
+    out = {}
+    for name, exact in (("exact", 1), ("fast", 0)):
+        with lgpu.Context(domain, capacity_sand=n, capacity_solid=len(solids)) as G:
+            G.upload_sand(sand)
+            G.upload_solids(solids)
+            G.step_sand(exact_math=exact, **kw)
+            out[name] = G.download()[0]
+            if exact:
+                keys = G.dump(lgpu.DUMP_KEYS).astype(np.int64)
+                perm = G.dump(lgpu.DUMP_PERM)
+                cell_start = G.dump(lgpu.DUMP_CELL_START).astype(np.int64)
+                cnt = G.dump(lgpu.DUMP_NBR_COUNT).astype(np.int64)
+                counters = G.dump(lgpu.DUMP_COUNTERS)
+    assert counters[0] == 0, "no particle left the grid"
+    assert np.array_equal(np.sort(perm), np.arange(n)), "the sort permutation is a bijection"
+    assert np.all(np.diff(keys) >= 0), "storage sorted by cell"
+    assert np.all(np.diff(perm)[np.diff(keys) == 0] > 0), "stable: previous order kept inside a cell"
+    assert np.array_equal(cell_start[:-1], np.searchsorted(keys, np.arange(len(cell_start) - 1))) and cell_start[-1] == n
+    assert cnt.min() >= 0 and cnt.max() < 64 and cnt.sum() > 10 * n, "plausible list lengths"
+    # Coulomb friction switches between its static and kinetic branch on `d * mu_s > |x_tan|`
+    # (src/Simulate.cpp:260-266): a contact that sits on the threshold takes the other branch under FMA
+    # contraction, which moves that particle by a fraction of the tangential slip.  So the bulk agrees to the
+    # parity tolerance and the rest stays within a hundredth of a radius.
+    err = np.abs(out["fast"].astype(np.float64) - out["exact"])
+    bound = ABS_TOL + REL_TOL * np.abs(out["exact"].astype(np.float64))
+    inside = float((err <= bound).mean())
+    print("  fast vs exact: %.5f of the coordinates inside the tolerance, max|err| %.3e" % (inside, err.max()))
+    assert inside >= 0.999 and err.max() <= 5e-3
+    r = np.float32(0.5)
+    hi = np.array(domain, np.float32) - r
+    assert np.all(out["exact"] >= r) and np.all(out["exact"] <= hi), "positions clamped to the box (src/Simulate.cpp:307)"
