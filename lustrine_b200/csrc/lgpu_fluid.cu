@@ -469,7 +469,7 @@ static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int
     // programmatic dependent launch between the passes and, in slab mode, through the refresh kernels (not with
     // per-launch event marks in between); LGPU_PDL=0 turns it off
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && lgpu_slab_pdl_ok(c);
+    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         lgpu_mark(c, 6);

@@ -474,7 +474,7 @@ int lgpu_slab_refresh(lgpu_ctx* c, const float4* buf, bool w_only) {
     }
     const int n_out = a.n_out[0] + a.n_out[1], n_in = a.n_in[0] + a.n_in[1];
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && lgpu_slab_pdl_ok(c);
+    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);
     CUDA_TRY(launch_pdl(k_refresh, n_out > 0 ? (n_out + 255) / 256 : 1, 256, 0, c->stream, pdl, a));
     c->launches++;
     if (n_in > 0) {
