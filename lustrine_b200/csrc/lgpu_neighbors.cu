@@ -1,6 +1,8 @@
 // lgpu_neighbors.cu — builds the per-particle neighbour table once per substep.
 // Replaces the list construction of find_neighbors_uniform_grid (src/neighbors/Neighbors.cpp:386-448)
 // and find_neighbors_uniform_grid_v1 (:306-361).
+#include <stdlib.h>
+
 #include "lgpu_neighbors.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -8,6 +10,7 @@
 // needs staged (one thread per block; a few thousand threads in all)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks, int stage_slots) {
+    pdl_trigger();  // the table build may start its own loads (they do not depend on the descriptors)
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_blocks) return;
     const Geom& g = v.g;
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_build_table(c
     const float4 x0i = v.x0[ic];
     const int key = v.key[ic];
     const int flags = g.slab ? v.flags[ic] : 0;
+    pdl_wait();  // launched as a programmatic dependent of k_block_ranges: the descriptors are needed from here on
     stage_begin(v, v.x0, d, &bar, stage);
     // per stencil column: the candidates are the sorted slots [cb, ce) — the three cells z-1..z+1
     // of a column are contiguous in the sorted storage
@@ -265,8 +269,10 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
         g_attr_done = true;
     }
     k_block_ranges<<<(nb + 127) / 128, 128, 0, c->stream>>>(v, nb, c->stage_slots);
-    if (sand_order) k_build_table<true><<<nb, LGPU_TILE, smem, c->stream>>>(v);
-    else k_build_table<false><<<nb, LGPU_TILE, smem, c->stream>>>(v);
+    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
+    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph;
+    if (sand_order) CUDA_TRY(launch_pdl(k_build_table<true>, nb, LGPU_TILE, smem, c->stream, pdl, v));
+    else CUDA_TRY(launch_pdl(k_build_table<false>, nb, LGPU_TILE, smem, c->stream, pdl, v));
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
