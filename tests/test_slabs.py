@@ -122,6 +122,28 @@ def test_distributed_host_logic_gloo_world2(tmp_path):
     assert out.stdout.count("slab-rank-") == 2 and out.stdout.count("-ok") == 2, out.stdout
 
 
+def test_slab_capacity_counts_the_ghost_columns_twice():
+    """Storage of a substep = previous slots (owned + dead ghost copies) + incoming ghost copies and migrants."""
+    cs = slabs.cell_size()
+    domain, pos = scenes.dam_break(16)
+    grid = slabs.grid_dims(domain, cs)
+    for world in (2, 4, 8):
+        plan = slabs.plan_slabs(slabs.cell_x(pos, cs), grid[0], world)
+        owned = slabs.deal(pos, plan, cs)
+        cap = slabs.slab_capacity(pos, plan, owned, cs, grid[0], factor=1.0)
+        hist = np.bincount(slabs.cell_x(pos, cs), minlength=grid[0])
+        worst = 0
+        for (lo, hi), o in zip(plan, owned):
+            ghosts = (hist[lo - 1] if lo > 0 else 0) + (hist[hi] if hi < grid[0] else 0)
+            worst = max(worst, len(o) + 2 * ghosts)
+        assert cap == worst + 4096
+        assert cap >= max(len(o) for o in owned)
+    # thin slabs (a few columns each): the ghost columns dominate and a plain 1.5 x owned would not hold a substep
+    plan = slabs.plan_slabs(slabs.cell_x(pos, cs), grid[0], 8)
+    owned = slabs.deal(pos, plan, cs)
+    assert slabs.slab_capacity(pos, plan, owned, cs, grid[0], factor=1.5) > int(1.5 * max(len(o) for o in owned)) + 4096
+
+
 # ------------------------------------------------------------------ the protocol on one GPU
 REL_TOL, ABS_TOL = 1e-5, 1e-5
 
