@@ -401,7 +401,7 @@ def main():
         cb, n, seconds = run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s=max(args.cpu_budget * 6.0, 60.0))
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "particle-substeps/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * seconds / steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "kind": kind, "solver_iterations": K, "dt": dt,
                            "note": "CPU reference on a bounded sample of the workload: " + cb["sample"]},
                 "cpu_baseline": cb,
