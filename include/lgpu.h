@@ -142,8 +142,12 @@ LGPU_API int lgpu_last_step_ms(lgpu_ctx* ctx, int phase, float* ms);
 LGPU_API long lgpu_launch_count(const lgpu_ctx* ctx);
 /* Enables per-phase event timing (adds event records to every step). */
 LGPU_API int lgpu_set_phase_timing(lgpu_ctx* ctx, int on);
-/* 1 = replay each step as a CUDA graph (re-captured when n / mode / iterations change). */
+/* 1 = run each step as a CUDA graph: the launches of the substep are captured from the context's stream
+ * (cudaStreamBeginCapture) and replayed with one cudaGraphLaunch while the particle count, the mode and the
+ * step parameters are unchanged; otherwise the instantiated graph is updated in place or rebuilt.  Not
+ * available in slab mode (LGPU_ERR_ARG).  lgpu_graph_stats: how often a step was captured / replayed. */
 LGPU_API int lgpu_set_use_graph(lgpu_ctx* ctx, int on);
+LGPU_API int lgpu_graph_stats(const lgpu_ctx* ctx, long* captures, long* replays);
 /* Tuning / test hook: capacity (in particles) of the shared-memory stage a thread block may use for
  * its neighbourhood; blocks that need more read their neighbours through L1/L2 instead ("virtual
  * slots").  Clamped to the compiled maximum; results do not depend on it. */

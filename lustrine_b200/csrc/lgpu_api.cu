@@ -66,8 +66,21 @@ template <class T> static cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
 }
 
+int lgpu_scratch_reserve(lgpu_ctx* c, size_t bytes) {
+    if (bytes <= c->scratch_bytes) return LGPU_OK;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr; c->scratch_bytes = 0;
+    bytes = (bytes + (bytes >> 2) + 4095) & ~(size_t)4095;  // head room: the next request rarely reallocates
+    CUDA_TRY(cudaMalloc((void**)&c->scratch, bytes));
+    c->scratch_bytes = bytes;
+    return LGPU_OK;
+}
+
+static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device);
 extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     if (!cfg || !out) return LGPU_ERR_ARG;
+    *out = nullptr;
     if (cfg->domain[0] <= 0 || cfg->domain[1] <= 0 || cfg->domain[2] <= 0 || cfg->particle_radius <= 0.0f ||
         cfg->capacity_sand < 0 || cfg->capacity_solid < 0 || cfg->kernel_radius_scale <= 0.0f) {
         lgpu_set_error("lgpu_create: bad configuration");
@@ -78,6 +91,19 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     CUDA_TRY(cudaSetDevice(device));
     lgpu_ctx* c = new lgpu_ctx();
     memset(c, 0, sizeof(*c));
+    const int st = create_impl(cfg, c, device);
+    if (st != LGPU_OK) {  // nothing leaks: lgpu_destroy frees whatever was allocated so far (the context is zero-filled)
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        lgpu_destroy(c);
+        memcpy(g_err, keep, sizeof(keep));
+        return st;
+    }
+    *out = c;
+    return LGPU_OK;
+}
+
+static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     c->cfg = *cfg;
     c->device = device;
     make_geom(*cfg, &c->g);
@@ -97,11 +123,16 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     if (!c->g.slab) {  // slab mode: x0 / pa / pb live in the peer-visible arena (lgpu_slab_init)
         CUDA_TRY(dalloc(&c->x0, cap)); CUDA_TRY(dalloc(&c->pa, cap)); CUDA_TRY(dalloc(&c->pb, cap));
     }
+    // every kernel of the step is loaded, and the staged ones opted into their dynamic shared memory, on THIS
+    // device (both are per device; a process may hold contexts on several GPUs)
+    if (lgpu_preload_grid() | lgpu_preload_neighbors() | lgpu_preload_fluid() | lgpu_preload_sand()) return LGPU_ERR_CUDA;
     if (c->g.slab) { int st = lgpu_slab_init(c); if (st) return st; }
-    CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap)); CUDA_TRY(dalloc(&c->rank_in, cap));
-    CUDA_TRY(dalloc(&c->tmp_id, cap)); CUDA_TRY(dalloc(&c->key, cap));
+    // key_in / rank_in / tmp_id double as scan input / output over the PARTICLES in lgpu_remove_in_cells and
+    // lgpu_aabb_first_k: the scan writes starts[n] (one past the end) and one status word per 4096 elements
+    CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap + 4)); CUDA_TRY(dalloc(&c->rank_in, cap + 4));
+    CUDA_TRY(dalloc(&c->tmp_id, cap + 4)); CUDA_TRY(dalloc(&c->key, cap));
     CUDA_TRY(dalloc(&c->cell_count, C1)); CUDA_TRY(dalloc(&c->cell_start, C1));
-    CUDA_TRY(dalloc(&c->scan_state, C1 / 4096 + 4));
+    CUDA_TRY(dalloc(&c->scan_state, (C1 > cap + 4 ? C1 : cap + 4) / 4096 + 4));
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
     CUDA_TRY(dalloc(&c->nbr16, cap * (size_t)(c->M / 4))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
@@ -122,14 +153,14 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     for (int k = 0; k < LGPU_MAX_MARKS; k++) CUDA_TRY(cudaEventCreate(&c->ev_pool[k]));
     c->solids_sorted = true;  // no solids yet
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *out = c;
     return LGPU_OK;
 }
 
 extern "C" void lgpu_destroy(lgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->scratch);
     for (int k = 0; k < 2; k++) { cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->flags[k]); cudaFree(c->orig[k]); }
     cudaFree(c->pstar_unsorted); cudaFree(c->perm);
     if (!c->g.slab) { cudaFree(c->x0); cudaFree(c->pa); cudaFree(c->pb); }
@@ -140,9 +171,10 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->counters); cudaFree(c->d_stage);
     lgpu_slab_free(c);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    for (int k = 0; k < 2; k++) cudaEventDestroy(c->ev[k]);
-    for (int k = 0; k < LGPU_MAX_MARKS; k++) cudaEventDestroy(c->ev_pool[k]);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    for (int k = 0; k < 2; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    for (int k = 0; k < LGPU_MAX_MARKS; k++) if (c->ev_pool[k]) cudaEventDestroy(c->ev_pool[k]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
     delete c;
 }
 
@@ -179,8 +211,15 @@ extern "C" long lgpu_launch_count(const lgpu_ctx* c) { return c ? c->launches : 
 extern "C" int lgpu_set_phase_timing(lgpu_ctx* c, int on) { if (!c) return LGPU_ERR_ARG; c->phase_timing = on != 0; return LGPU_OK; }
 extern "C" int lgpu_set_use_graph(lgpu_ctx* c, int on) {
     if (!c) return LGPU_ERR_ARG;
+    if (on && c->g.slab) { lgpu_set_error("lgpu_set_use_graph: slab mode reads the migration counts on the host every substep; no graph"); return LGPU_ERR_ARG; }
     c->use_graph = on != 0;
     if (!on && c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return LGPU_OK;
+}
+extern "C" int lgpu_graph_stats(const lgpu_ctx* c, long* captures, long* replays) {
+    if (!c) return LGPU_ERR_ARG;
+    if (captures) *captures = c->graph_captures;
+    if (replays) *replays = c->graph_replays;
     return LGPU_OK;
 }
 extern "C" int lgpu_set_stage_slots(lgpu_ctx* c, int slots) {
@@ -281,14 +320,14 @@ extern "C" int lgpu_upload_solids(lgpu_ctx* c, int n, const float* pos) {
     c->n_solid = c->n_solid_uploaded = n;
     c->solids_sorted = false;
     if (n > 0) {
-        float* stage;
-        CUDA_TRY(cudaMalloc((void**)&stage, sizeof(float) * 3 * n));
+        int st = lgpu_scratch_reserve(c, sizeof(float) * 3 * (size_t)n);
+        if (st) return st;
+        float* stage = (float*)c->scratch;
         CUDA_TRY(cudaMemcpyAsync(stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
         k_unpack3<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(stage, n, c->solid_pos_unsorted, 0);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(stage);
     }
     return lgpu_sort_solids(c);
 }
@@ -345,6 +384,45 @@ static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     return LGPU_OK;
 }
 
+// The substep as a CUDA graph: its launches are captured from the stream once (cudaStreamBeginCapture ..
+// cudaStreamEndCapture around enqueue_step) and replayed with one cudaGraphLaunch while the particle count,
+// the mode, the storage and the step parameters stay the same; when only parameters or counts change the
+// instantiated graph is updated in place (cudaGraphExecUpdate), otherwise it is instantiated again.
+static int step_as_graph(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
+    const long sig[5] = {mode, c->n, c->n_in, c->n_solid, (long)(size_t)c->pos[0]};
+    if (c->graph_exec && memcmp(sig, c->graph_sig, sizeof(sig)) == 0 && memcmp(&p, &c->last_params, sizeof(p)) == 0) {
+        CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
+        c->launches += c->graph_sig[5];
+        c->graph_replays++;
+        return LGPU_OK;
+    }
+    const long launches0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int st = enqueue_step(c, p, mode);
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);  // always ended, also when a launch failed
+    if (st) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return st; }
+    if (ce != cudaSuccess) { lgpu_set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(ce)); return LGPU_ERR_CUDA; }
+    if (c->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(c->graph_exec, graph, &info) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphExecDestroy(c->graph_exec);
+            c->graph_exec = nullptr;
+        }
+    }
+    if (!c->graph_exec) {
+        const cudaError_t ie = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        if (ie != cudaSuccess) { cudaGraphDestroy(graph); c->graph_exec = nullptr; lgpu_set_error("cudaGraphInstantiate -> %s", cudaGetErrorString(ie)); return LGPU_ERR_CUDA; }
+    }
+    cudaGraphDestroy(graph);
+    memcpy(c->graph_sig, sig, sizeof(sig));
+    c->graph_sig[5] = c->launches - launches0;
+    c->graph_captures++;
+    CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
+    return LGPU_OK;
+}
+
 static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
     if (!c || !p) return LGPU_ERR_ARG;
     if (c->g.slab) {
@@ -353,11 +431,12 @@ static int run_step(lgpu_ctx* c, const lgpu_step_params* p, int mode) {
     }
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->solids_sorted) { int st = lgpu_sort_solids(c); if (st) return st; }
-    c->last_params = *p;
     c->last_mode = mode;
     c->n_marks = 0;
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    int st = enqueue_step(c, *p, mode);
+    // (per-launch event marks cannot be recorded inside a capture: phase timing runs eagerly)
+    int st = (c->use_graph && !c->phase_timing) ? step_as_graph(c, *p, mode) : enqueue_step(c, *p, mode);
+    c->last_params = *p;
     if (st) return st;
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     c->grid_valid = true;

@@ -456,13 +456,6 @@ template <bool SOLIDS>
 static int run_fluid_fast(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
     const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda_fast<SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     const bool slab = lgpu_slab_active(c);
@@ -491,13 +484,6 @@ template <class P, bool POLY6, bool SOLIDS>
 static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
     const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda<P, POLY6, SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     const bool slab = lgpu_slab_active(c);
@@ -617,9 +603,10 @@ int lgpu_eval_kernel(lgpu_ctx* c, const lgpu_step_params* p, int which, const fl
     if (n == 0) return LGPU_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     const int width = (which == 1 || which == 3) ? 3 : 1;
-    float *d_in, *d_out;
-    CUDA_TRY(cudaMalloc(&d_in, sizeof(float) * n * width));
-    CUDA_TRY(cudaMalloc(&d_out, sizeof(float) * n * width));
+    const size_t words = ((size_t)n * width + 3) & ~(size_t)3;
+    { int st = lgpu_scratch_reserve(c, sizeof(float) * 2 * words); if (st) return st; }
+    float* d_in = (float*)c->scratch;
+    float* d_out = d_in + words;
     CUDA_TRY(cudaMemcpyAsync(d_in, in, sizeof(float) * n * width, cudaMemcpyHostToDevice, c->stream));
     lgpu_step_params q = *p;
     q.sph_kernel = 0;
@@ -630,20 +617,32 @@ int lgpu_eval_kernel(lgpu_ctx* c, const lgpu_step_params* p, int which, const fl
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, d_out, sizeof(float) * n * width, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(d_in); cudaFree(d_out);
     return LGPU_OK;
 }
 
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
 template <class P, bool POLY6, bool SOLIDS> static int preload_fluid_variant() {
+    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda<P, POLY6, SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap<P, POLY6, SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGPU_PRELOAD((k_fluid_lambda<P, POLY6, SOLIDS>));
     LGPU_PRELOAD((k_fluid_deltap<P, POLY6, SOLIDS, true>));
     LGPU_PRELOAD((k_fluid_deltap<P, POLY6, SOLIDS, false>));
     return LGPU_OK;
 }
+template <bool SOLIDS> static int preload_fluid_fast() {
+    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_lambda_fast<SOLIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_fluid_deltap_fast<SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return LGPU_OK;
+}
+// per device (cudaFuncSetAttribute applies to the current device only): called by lgpu_create
 int lgpu_preload_fluid() {
     int st = 0;
+    st |= preload_fluid_fast<true>(); st |= preload_fluid_fast<false>();
     LGPU_PRELOAD(k_fluid_lambda_fast<true>); LGPU_PRELOAD(k_fluid_lambda_fast<false>);
     LGPU_PRELOAD((k_fluid_deltap_fast<true, true>)); LGPU_PRELOAD((k_fluid_deltap_fast<true, false>));
     LGPU_PRELOAD((k_fluid_deltap_fast<false, true>)); LGPU_PRELOAD((k_fluid_deltap_fast<false, false>));

@@ -368,13 +368,11 @@ int lgpu_sort_solids(lgpu_ctx* c) {
     c->n_solid = n;
     CUDA_TRY(cudaMemsetAsync(c->solid_cell_start, 0, sizeof(int) * ((size_t)C + 2), c->stream));
     if (n > 0) {
-        // reuse the sand scratch (key_in / rank_in / tmp_id are dead between steps) when it is large
-        // enough, otherwise allocate temporaries
-        int *keys, *ranks, *tmp, *counts;
-        CUDA_TRY(cudaMalloc(&keys, sizeof(int) * n));
-        CUDA_TRY(cudaMalloc(&ranks, sizeof(int) * n));
-        CUDA_TRY(cudaMalloc(&tmp, sizeof(int) * n));
-        CUDA_TRY(cudaMalloc(&counts, sizeof(int) * ((size_t)C + 2)));
+        const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
+        int st0 = lgpu_scratch_reserve(c, sizeof(int) * (3 * n4 + (size_t)C + 2));
+        if (st0) return st0;
+        int* keys = (int*)c->scratch;
+        int *ranks = keys + n4, *tmp = ranks + n4, *counts = tmp + n4;  // (counts is 16-byte aligned: the scan loads int4)
         CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)C + 2), c->stream));
         k_solid_keys<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->g, c->solid_pos_unsorted, n, keys, ranks, counts, c->counters);
         int st = lgpu_launch_scan_cells(c, counts, c->solid_cell_start, C + 1, false);
@@ -387,7 +385,6 @@ int lgpu_sort_solids(lgpu_ctx* c) {
         CUDA_TRY(cudaMemcpyAsync(&kept, c->solid_cell_start + C, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->n_solid = kept;  // slab mode: the solids inside this context's columns
-        cudaFree(keys); cudaFree(ranks); cudaFree(tmp); cudaFree(counts);
     }
     c->solids_sorted = true;
     return LGPU_OK;

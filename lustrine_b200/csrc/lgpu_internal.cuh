@@ -166,15 +166,21 @@ struct lgpu_ctx {
     int n_marks;
     bool phase_timing;
     long launches;
-    // graphs
+    // scratch: one growable device buffer for the per-call temporaries of the query / upload paths
+    unsigned char* scratch;
+    size_t scratch_bytes;
+    // graphs: the launches of one substep captured once (cudaStreamBeginCapture) and replayed
     bool use_graph;
     cudaGraphExec_t graph_exec;
-    int graph_sig[4];
+    long graph_sig[6];       // mode, n, n_in, n_solid, storage pointer, launches per step
+    long graph_captures, graph_replays;
     lgpu_step_params last_params;
     int last_mode;  // 0 none, 1 fluid, 2 sand
 };
 
 void lgpu_set_error(const char* fmt, ...);
+// at least `bytes` of device scratch (contents undefined); grows by reallocation after a stream sync
+int lgpu_scratch_reserve(lgpu_ctx* c, size_t bytes);
 
 #define CUDA_TRY(expr)                                                                      \
     do {                                                                                    \

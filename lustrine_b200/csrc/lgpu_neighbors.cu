@@ -257,17 +257,11 @@ __global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_build_table(c
     v.nbr_cnt[i] = word;
 }
 
-static bool g_attr_done = false;
 int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
     if (c->n == 0) return LGPU_OK;  // (slab mode: the solver drivers still run the refresh protocol)
     View v = lgpu_make_view(c);
     const int nb = (c->n + LGPU_TILE - 1) / LGPU_TILE;
     const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
-    if (!g_attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(k_build_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_build_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_attr_done = true;
-    }
     k_block_ranges<<<(nb + 127) / 128, 128, 0, c->stream>>>(v, nb, c->stage_slots);
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
     const bool pdl = pdl_env && !c->phase_timing && !c->use_graph;
@@ -280,7 +274,12 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
 
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+// Loads every kernel of this file on the CURRENT device and opts the staged ones into their dynamic
+// shared memory.  cudaFuncSetAttribute is per device: lgpu_create calls this for every context.
 int lgpu_preload_neighbors() {
+    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
+    CUDA_TRY(cudaFuncSetAttribute(k_build_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_build_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGPU_PRELOAD(k_block_ranges); LGPU_PRELOAD(k_build_table<true>); LGPU_PRELOAD(k_build_table<false>);
     return LGPU_OK;
 }

@@ -98,9 +98,15 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     CUDA_TRY(cudaSetDevice(c->device));
     View v = lgpu_make_view(c);
     const int n = c->n_owned;
-    int *d_cells, *d_counts;
-    CUDA_TRY(cudaMalloc((void**)&d_cells, sizeof(int) * n_cells));
-    CUDA_TRY(cudaMalloc((void**)&d_counts, sizeof(int) * n_cells));
+    // all temporaries of this call come from the context's scratch buffer (no per-frame cudaMalloc / cudaFree):
+    // sink cells, their counts / offsets, the evicted slots (<= n), dead slots (<= n), moves (<= n pairs)
+    const size_t nc4 = ((size_t)n_cells + 3) & ~(size_t)3, n4 = ((size_t)n + 3) & ~(size_t)3;
+    { int st = lgpu_scratch_reserve(c, sizeof(int) * (2 * nc4 + 4 * n4)); if (st) return st; }
+    int* d_cells = (int*)c->scratch;
+    int* d_counts = d_cells + nc4;
+    int* d_list = d_counts + nc4;
+    int* d_dead = d_list + n4;
+    int* d_moved = d_dead + n4;
     CUDA_TRY(cudaMemcpyAsync(d_cells, cell_ids, sizeof(int) * n_cells, cudaMemcpyHostToDevice, c->stream));
     k_sink_counts<<<lgpu_blocks(n_cells), LGPU_BLOCK, 0, c->stream>>>(v, d_cells, n_cells, d_counts);
     std::vector<int> counts(n_cells), offsets(n_cells);
@@ -109,9 +115,7 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     int total = 0;
     for (int t = 0; t < n_cells; t++) { offsets[t] = total; total += counts[t]; }
     c->launches++;
-    if (total == 0) { cudaFree(d_cells); cudaFree(d_counts); return LGPU_OK; }
-    int* d_list;
-    CUDA_TRY(cudaMalloc((void**)&d_list, sizeof(int) * total));
+    if (total == 0) return LGPU_OK;
     CUDA_TRY(cudaMemcpyAsync(d_counts, offsets.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice, c->stream));
     k_sink_list<<<lgpu_blocks(n_cells), LGPU_BLOCK, 0, c->stream>>>(v, d_cells, d_counts, n_cells, d_list);
     std::vector<int> list(total);
@@ -153,12 +157,9 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     std::vector<int> moved;
     for (auto& kv : new_slot_of) { moved.push_back(kv.first); moved.push_back(kv.second); }
     const int n_dead = (int)dead.size(), n_moved = (int)moved.size() / 2;
-    int *d_dead = nullptr, *d_moved = nullptr;
     int* inv = c->tmp_id;      // scratch, dead between steps
     int* keep = c->key_in;
     int* dst = c->rank_in;
-    CUDA_TRY(cudaMalloc((void**)&d_dead, sizeof(int) * (n_dead ? n_dead : 1)));
-    CUDA_TRY(cudaMalloc((void**)&d_moved, sizeof(int) * (n_moved ? 2 * n_moved : 1)));
     if (n_dead) CUDA_TRY(cudaMemcpyAsync(d_dead, dead.data(), sizeof(int) * n_dead, cudaMemcpyHostToDevice, c->stream));
     if (n_moved) CUDA_TRY(cudaMemcpyAsync(d_moved, moved.data(), sizeof(int) * 2 * n_moved, cudaMemcpyHostToDevice, c->stream));
     k_invert_orig<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->orig[0], n, inv);
@@ -177,7 +178,6 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     c->n_owned = c->n = c->n_in = n - n_dead;
     c->grid_valid = false;
     if (removed) *removed = n_dead;
-    cudaFree(d_cells); cudaFree(d_counts); cudaFree(d_list); cudaFree(d_dead); cudaFree(d_moved);
     return LGPU_OK;
 }
 
@@ -206,6 +206,7 @@ extern "C" int lgpu_aabb_first_k(lgpu_ctx* c, const float center[3], const float
     *out_n = 0;
     const int n = c->n_owned;
     if (n == 0 || k == 0) return LGPU_OK;
+    if (k > n) k = n;  // (the output staging area holds 8 floats per particle of capacity)
     CUDA_TRY(cudaSetDevice(c->device));
     View v = lgpu_make_view(c);
     int* flag = c->key_in;   // scratch, dead between steps

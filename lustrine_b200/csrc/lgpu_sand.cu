@@ -181,11 +181,6 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         lgpu_mark(c, 7);
 #define LGPU_SAND_LAUNCH(PP, SS, LL)                                                                                    \
     do {                                                                                                                \
-        static bool attr = false;                                                                                       \
-        if (!attr) {                                                                                                    \
-            CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<PP, SS, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr = true;                                                                                                \
-        }                                                                                                               \
         CUDA_TRY(launch_pdl(k_sand_iteration<PP, SS, LL>, blocks, LGPU_TILE, smem, c->stream, pdl && it > 0, v, sp, cur, next)); \
     } while (0)
         if (p.exact_math) {
@@ -208,6 +203,9 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
 template <class P, bool SOLIDS> static int preload_sand_variant() {
+    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
+    CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<P, SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<P, SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, true>));
     LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, false>));
     return LGPU_OK;

@@ -92,7 +92,7 @@ int lgpu_slab_init(lgpu_ctx* c) {
     CUDA_TRY(cudaMemsetAsync(S->push_ticket, 0, sizeof(unsigned int), c->stream));
     CUDA_TRY(cudaMallocHost((void**)&S->h_counts, sizeof(int) * 64));
     // no kernel of the step may be loaded lazily while a neighbour waits for this context (see lgpu_grid.cu)
-    int st = lgpu_preload_grid() | lgpu_preload_neighbors() | lgpu_preload_fluid() | lgpu_preload_sand() | lgpu_preload_slab();
+    int st = lgpu_preload_slab();  // (the kernels of the step itself were loaded by lgpu_create)
     return st ? LGPU_ERR_CUDA : LGPU_OK;
 }
 

@@ -201,7 +201,12 @@ int get_sink_despawned(int index) { return Lustrine::get_sink_despawned(simulati
 void set_simulate_function(int index) {  // :666-677
     switch (index) {
         case 0: simulation->simulate_fun = simulate_sand; break;
-        case 1: simulation->simulate_fun = simulate_sand_v3; break;
+        case 1:
+            // the reference selects simulate_sand_v3 here; that variant is not built on this path
+            // (lustrine_b200/host/Simulate.cpp): say so and keep the current function
+            std::cout << "lustrine_b200: set_simulate_function(1) = simulate_sand_v3 is not implemented on the B200 path; "
+                      << "the simulate function is left unchanged\n";
+            break;
         default: std::cout << "Unreckognized input for simulate func " << index << "\n";
     }
 }
@@ -225,7 +230,7 @@ void b200_set_solver_options(int fluid_iterations, int literal_lambda_index, int
 void b200_set_simulate_function(int index) {
     switch (index) {
         case 0: simulation->simulate_fun = simulate_sand; break;
-        case 1: simulation->simulate_fun = simulate_sand_v3; break;
+        case 1: set_simulate_function(1); break;  // refused with a diagnostic, see above
         case 2: simulation->simulate_fun = simulate_fluid; break;
         case 3: simulation->simulate_fun = simulate_sand_credits; break;
         default: break;

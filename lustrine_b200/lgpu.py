@@ -51,7 +51,7 @@ SYMBOLS = [
     "lgpu_default_step_params", "lgpu_create", "lgpu_destroy", "lgpu_last_error", "lgpu_get_grid",
     "lgpu_upload_sand", "lgpu_upload_solids", "lgpu_append_sand", "lgpu_download_sand", "lgpu_num_sand",
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
-    "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
+    "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_graph_stats", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
     "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_upload", "lgpu_slab_download",
     "lgpu_slab_step_begin", "lgpu_slab_step_end",
@@ -89,6 +89,7 @@ def lib():
         L.lgpu_launch_count.restype = C.c_long
         L.lgpu_set_phase_timing.argtypes = [vp, c_i]
         L.lgpu_set_use_graph.argtypes = [vp, c_i]
+        L.lgpu_graph_stats.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.lgpu_set_stage_slots.argtypes = [vp, c_i]
         L.lgpu_set_generic_kernels.argtypes = [vp, c_i]
         L.lgpu_cell_count.argtypes = [vp, C.POINTER(c_i * 3), C.POINTER(c_i * 3), c_i, C.POINTER(c_i)]
@@ -256,6 +257,12 @@ class Context:
 
     def set_use_graph(self, on):
         _check(self.L.lgpu_set_use_graph(self._h, int(on)), "lgpu_set_use_graph")
+
+    def graph_stats(self):
+        """(steps captured into a CUDA graph, steps replayed from it)."""
+        a, b = C.c_long(), C.c_long()
+        _check(self.L.lgpu_graph_stats(self._h, C.byref(a), C.byref(b)), "lgpu_graph_stats")
+        return a.value, b.value
 
     # ---- spatial slabs (one context per GPU; see lustrine_b200/slabs.py) ----
     def slab_export(self):

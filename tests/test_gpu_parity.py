@@ -561,16 +561,20 @@ def test_full_size_properties_sand_4m():
 
 
 def test_cuda_graph_replay_is_identical():
-    """lgpu_set_use_graph: the substep replayed as a CUDA graph gives bit-identical results (fluid and sand)."""
+    """lgpu_set_use_graph: the substep captured with cudaStreamBeginCapture and replayed with cudaGraphLaunch gives
+    bit-identical results (fluid and sand), and the replay really happens (lgpu_graph_stats)."""
     domain, sand = scenes.dam_break(20)
     res = []
     for graph in (0, 1):
         with lgpu.Context(domain, capacity_sand=len(sand)) as G:
             G.set_use_graph(graph)
             G.upload_sand(sand)
-            for _ in range(4):
+            for _ in range(5):
                 G.step_fluid(dt=0.01, iterations=3, literal_lambda_index=0, exact_math=0)
             res.append(G.download())
+            captures, replays = G.graph_stats()
+            print("  fluid graph=%d: %d captures, %d replays" % (graph, captures, replays))
+            assert (captures, replays) == ((1, 4) if graph else (0, 0))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     domain, sand, solids = scenes.sand_pile(12, drop=1.0)
     res = []
@@ -578,7 +582,14 @@ def test_cuda_graph_replay_is_identical():
         with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
             G.set_use_graph(graph)
             G.upload_sand(sand); G.upload_solids(solids)
-            for _ in range(4):
-                G.step_sand(dt=0.016, iterations=4, exact_math=0)
+            for k in range(6):
+                # the player moves on steps 2 and 3 (the parameters change: the instantiated graph is updated in
+                # place), then stands still (replays)
+                player = (18.0 + min(k, 3), 4.0, 18.0)
+                G.step_sand(dt=0.016, iterations=4, exact_math=0, attract_flag=1, attract_radius=6.0, player_position=player)
             res.append(G.download())
+            captures, replays = G.graph_stats()
+            print("  sand graph=%d: %d captures, %d replays" % (graph, captures, replays))
+            assert (captures, replays) == ((4, 2) if graph else (0, 0))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2]), "attracted flags"
