@@ -357,6 +357,20 @@ void lo_find_neighbors_v1(lo_sim* s) {
 
 /* ================= fluid: src/Simulate.cpp:27-115 ================= */
 
+/* simulation->W / simulation->gradW (src/Simulation.hpp:139-140): function pointers in the reference */
+static inline float sim_W(const lo_sim* s, float r) { return s->sph_kernel ? lo_poly6_kernel(s, r) : lo_cubic_kernel(s, r); }
+static inline v3 sim_gradW(const lo_sim* s, v3 d) {
+    if (!s->sph_kernel) return cubic_grad(s, d);
+    float in[3], out[3];
+    v3_store(in, d);
+    lo_spiky_kernel(s, in, out);
+    return v3_load(out);
+}
+/* s_coor through simulation->W (src/Simulate.cpp:7-9) */
+static inline float sim_s_coor(const lo_sim* s, float rl) {
+    return -s->s_corr_k * powf(sim_W(s, rl) / sim_W(s, s->s_corr_dq), s->s_corr_n);
+}
+
 void lo_fluid_predict(lo_sim* s, float dt) {
     dt = clampf(dt, 0.001f, 0.01f); /* :31 */
     s->time_step = dt;
@@ -375,16 +389,16 @@ void lo_fluid_lambda(lo_sim* s) { /* :58-88 */
         float density = 0.0f;
         for (long t = s->nbr_offsets[i]; t < s->nbr_offsets[i + 1]; t++) {
             v3 ij = v3_sub(pi, v3_load(pstar(s, s->nbr[t])));
-            density += s->mass * lo_cubic_kernel(s, v3_length(ij));
+            density += s->mass * sim_W(s, v3_length(ij));
         }
-        density += s->mass * lo_cubic_kernel(s, 0.0f);
+        density += s->mass * sim_W(s, 0.0f);
         s->densities[i] = density;
         float constraint_i = (float)((double)(density / s->rest_density) - 1.0); /* :69 */
         float sum = 0.0f;
         v3 gi = v3_make(0.0f, 0.0f, 0.0f);
         for (long t = s->nbr_offsets[i]; t < s->nbr_offsets[i + 1]; t++) {
             v3 d = v3_sub(pi, v3_load(pstar(s, s->nbr[t])));
-            v3 g = v3_scale(cubic_grad(s, d), -(s->mass / s->rest_density));
+            v3 g = v3_scale(sim_gradW(s, d), -(s->mass / s->rest_density));
             sum += v3_dot(g, g);
             gi = v3_sub(gi, g);
         }
@@ -414,8 +428,8 @@ void lo_fluid_deltap(lo_sim* s, int jacobi, int literal_lambda_index) { /* :90-1
             v3 ij = v3_sub(pi, v3_load(pstar(s, s->nbr[t])));
             /* F4: the reference reads lambdas[j] with j the loop counter */
             float lj = literal_lambda_index ? s->lambdas[t - b] : (s->nbr[t] < s->n_sand ? s->lambdas[s->nbr[t]] : 0.0f);
-            float w = (s->lambdas[i] + lj) + lo_s_coor(s, v3_length(ij));
-            f = v3_add(f, v3_scale(cubic_grad(s, ij), w));
+            float w = (s->lambdas[i] + lj) + sim_s_coor(s, v3_length(ij));
+            f = v3_add(f, v3_scale(sim_gradW(s, ij), w));
         }
         f = v3_div(f, s->rest_density);
         v3 p = v3_add(pi, f);

@@ -42,6 +42,9 @@ typedef struct lo_sim {
     float* scratch3;
     int* scratchi;
     long violations; /* keys outside [0, num_grid_cells) seen (the reference has no clamp, F10) */
+    int sph_kernel;  /* which functions Simulation::W / gradW point at: 0 = cubic_kernel / cubic_kernel_grad (what
+                        init_simulation wires, src/Lustrine.cpp:247-248), 1 = poly6_kernel(float) / spiky_kernel
+                        (src/Kernels.cpp:43-67; never wired by the reference itself) */
 } lo_sim;
 
 lo_sim* lo_create(int X, int Y, int Z, float radius, float diameter, float kernel_radius_scale,

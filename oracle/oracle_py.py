@@ -55,6 +55,7 @@ class LoSim(C.Structure):
         ("cell_counts", ip), ("cell_start", ip), ("cell_items", ip),
         ("solid_cell_start", ip), ("solid_cell_items", ip), ("solid_grid_built", c_i),
         ("scratch3", fp), ("scratchi", ip), ("violations", C.c_long),
+        ("sph_kernel", c_i),
     ]
 
 
@@ -176,6 +177,7 @@ def ref_lib(which="lit"):
         L.refh_get_solid.argtypes = [vp, vp]
         L.refh_set_fun.argtypes = [vp, c_i, c_i, c_i]
         L.refh_set_scalars.argtypes = [vp, vp, c_f, c_f, c_f, c_f, c_f, c_f]
+        L.refh_set_kernel.argtypes = [vp, c_i]
         L.refh_set_player.argtypes = [vp, vp, c_i, c_i, c_f, c_f, c_f, c_f]
         L.refh_step.restype = C.c_double
         L.refh_step.argtypes = [vp, c_f, c_i, c_i]
@@ -247,6 +249,10 @@ class RefSim:
 
     def set_fun(self, which, iterations=1, literal_lambda_index=True):
         self.L.refh_set_fun(self.h, which, iterations, int(literal_lambda_index))
+
+    def set_kernel(self, which):
+        """0 = cubic spline (the reference's wiring), 1 = Simulation::W / gradW pointed at poly6_kernel / spiky_kernel."""
+        self.L.refh_set_kernel(self.h, int(which))
 
     def set_player(self, pos=None, attract=False, blow=False, attract_radius=1.5, blow_radius=2.0,
                    attract_coeff=1000.0, blow_coeff=500.0):

@@ -218,6 +218,15 @@ void refh_set_fun(void* hv, int which, int jacobi_iterations, int literal_lambda
     }
 }
 
+// Points Simulation::W / gradW at the poly6 / spiky pair of src/Kernels.cpp:43-67 (which 1) or back at the cubic
+// spline (0).  spiky_kernel takes a non-const reference, so it needs an adapter to fit gradW_fun.
+static glm::vec3 spiky_as_gradW(const Lustrine::Simulation* s, const glm::vec3& r) { glm::vec3 t = r; return Lustrine::spiky_kernel(s, t); }
+void refh_set_kernel(void* hv, int which) {
+    Lustrine::Simulation& s = ((Handle*)hv)->sim;
+    if (which == 1) { s.W = static_cast<Lustrine::W_fun>(Lustrine::poly6_kernel); s.gradW = spiky_as_gradW; }
+    else { s.W = static_cast<Lustrine::W_fun>(Lustrine::cubic_kernel); s.gradW = Lustrine::cubic_kernel_grad; }
+}
+
 void refh_set_scalars(void* hv, const float* gravity, float rest_density, float mass, float relaxation_epsilon,
                       float s_corr_dq, float s_corr_k, float s_corr_n) {
     Lustrine::Simulation& s = ((Handle*)hv)->sim;

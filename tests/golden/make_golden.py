@@ -20,11 +20,12 @@ import oracle_py as O  # noqa: E402
 import scenes  # noqa: E402
 
 
-def fluid_case(n_side, steps, literal_gs):
+def fluid_case(n_side, steps, literal_gs, sph_kernel=0):
     domain, sand = scenes.dam_break(n_side)
     solids = scenes.floor_plate(3 * n_side, 2 * n_side)
     R = O.RefSim(*domain, n_sand=len(sand), n_solid=len(solids))
     R.set_sand(sand); R.set_solid(solids)
+    R.set_kernel(sph_kernel)  # 1: Simulation::W / gradW = poly6_kernel / spiky_kernel (src/Kernels.cpp:43-67)
     R.set_fun(R.FLUID if literal_gs else R.FLUID_JACOBI, 1, True)
     out = {"domain": np.array(domain, np.int32), "sand": sand, "solids": solids}
     for s in range(steps):
@@ -80,6 +81,7 @@ def counting_sort_case():
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "fluid_literal_8.npz"), **fluid_case(8, 3, True))
     np.savez_compressed(os.path.join(HERE, "fluid_jacobi_8.npz"), **fluid_case(8, 3, False))
+    np.savez_compressed(os.path.join(HERE, "fluid_poly6_jacobi_8.npz"), **fluid_case(8, 3, False, sph_kernel=1))
     np.savez_compressed(os.path.join(HERE, "sand_8.npz"), **sand_case(8, 3))
     np.savez_compressed(os.path.join(HERE, "kernel_tables.npz"), **kernel_tables())
     np.savez_compressed(os.path.join(HERE, "counting_sort.npz"), **counting_sort_case())

@@ -31,9 +31,13 @@ def test_wrapper_symbols_exported():
         assert re.search(r"_ZN8Lustrine\d+%s" % cxx, out), "C++ API function %s not exported" % cxx
 
 
-def run_scenario(w, steps, flags=None, with_source_sink=False):
+def run_scenario(w, steps, flags=None, with_source_sink=False, host_sync=0):
     data = w.init((30, 30, 30), 0.5, sand=[((10, 10, 10), (5.0, 8.0, 5.0))],
                   solids=[((24, 1, 24), (0.0, 0.0, 0.0), 2), ((4, 3, 4), (8.0, 1.0, 8.0), 2)], subdivision=1)
+    if host_sync:
+        # 1 = SYNC_RESIDENT (device state authoritative, host arrays refreshed after every step), 2 = SYNC_LAZY
+        # (nothing downloaded until simulation_bind_positions_copy) — lustrine_b200 only, lustrine/Lustrine.hpp
+        w.L.b200_set_host_sync(host_sync)
     trace = {"n0": (data.num_sand_particles, data.num_solid_particles, data.start_solid_index, data.end_solid_index), "pos": [], "n": [], "q": []}
     if with_source_sink:
         w.add_source((2, 2, 2), (14.0, 22.0, 14.0), (0.0, -1.0, 0.0), 0.05, 48)
@@ -50,8 +54,9 @@ def run_scenario(w, steps, flags=None, with_source_sink=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scenario", ["sand", "attract_blow", "source_sink"])
-def test_wrapper_matches_reference(scenario):
+@pytest.mark.parametrize("scenario,host_sync", [("sand", 0), ("attract_blow", 0), ("source_sink", 0),
+                                                ("attract_blow", 1), ("source_sink", 1), ("attract_blow", 2), ("source_sink", 2)])
+def test_wrapper_matches_reference(scenario, host_sync):
     if not O.have_ref():
         pytest.skip("oracle/_ref not built")
     steps = 24
@@ -60,7 +65,7 @@ def test_wrapper_matches_reference(scenario):
         flags = [(False, False)] * 4 + [(True, False)] * 6 + [(False, False)] * 4 + [(False, True)] * 4 + [(False, False)] * 6
     kw = dict(steps=steps, flags=flags, with_source_sink=scenario == "source_sink")
     ref = run_scenario(Wrapper(O.REF_LIT_SO), **kw)
-    got = run_scenario(Wrapper(OURS), **kw)
+    got = run_scenario(Wrapper(OURS), host_sync=host_sync, **kw)
     assert got["n0"] == ref["n0"]
     assert got["n"] == ref["n"], "particle counts per step"
     assert got["q"] == ref["q"], "query_cell_num_particles per step"

@@ -117,11 +117,12 @@ def test_kernel_tables():
 
 
 # ----------------------------------------------------------------------------------------------
-def compare_fluid_substep(P, G, iterations, literal, exact, check_lists=True):
+def compare_fluid_substep(P, G, iterations, literal, exact, check_lists=True, sph=0):
     n = P.n
     force_state(P, G)
+    P.s.sph_kernel = sph  # 1: Simulation::W / gradW = poly6_kernel / spiky_kernel (src/Kernels.cpp:43-67)
     P.L.lo_step_fluid(P.p, 0.01, iterations, 1, int(literal))
-    G.step_fluid(dt=0.01, iterations=iterations, literal_lambda_index=int(literal), exact_math=int(exact))
+    G.step_fluid(dt=0.01, iterations=iterations, literal_lambda_index=int(literal), exact_math=int(exact), sph_kernel=sph)
     orig = G.dump(lgpu.DUMP_ORIG)
     assert np.array_equal(np.sort(orig), np.arange(n))
     # keys and sort order: bit-exact
@@ -166,6 +167,19 @@ def test_fluid_modes(iterations, literal, exact):
     for step in range(3):
         print("substep", step)
         compare_fluid_substep(P, G, iterations, literal, exact)
+    G.close(); P.close()
+
+
+@pytest.mark.parametrize("iterations,literal,with_solids", [(1, True, False), (1, True, True), (3, False, True)])
+def test_fluid_poly6_spiky_solver(iterations, literal, with_solids):
+    """sph_kernel=1: the solver with W = poly6_kernel(float), gradW = spiky_kernel (src/Kernels.cpp:43-67; selectable,
+    never wired by the reference itself) against the port's poly6 step, which tests/test_oracle.py pins
+    against the compiled reference with Simulation::W / gradW pointed at those functions."""
+    domain, sand = scenes.dam_break(14)
+    P, G = make_pair(domain, sand, scenes.floor_plate(30, 20) if with_solids else None)
+    for step in range(3):
+        print("substep", step)
+        compare_fluid_substep(P, G, iterations, literal, True, sph=1)
     G.close(); P.close()
 
 
@@ -234,9 +248,10 @@ def test_small_stage_uses_virtual_slots_or_walk(slots):
     G.close(); P.close()
 
 
-def test_fluid_free_running_horizon():
-    # 10 free-running substeps (no teacher forcing), K=1 literal vs the Jacobi oracle
-    domain, sand = scenes.dam_break(20)
+@pytest.mark.parametrize("n_side", [20, 40])
+def test_fluid_free_running_horizon(n_side):
+    # 10 free-running substeps (no teacher forcing), K=1 literal vs the Jacobi oracle; 8 000 and 64 000 particles
+    domain, sand = scenes.dam_break(n_side)
     P, G = make_pair(domain, sand)
     for step in range(10):
         P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
@@ -352,8 +367,10 @@ def test_sand_attract_blow_and_credits():
     G.close(); P.close()
 
 
-def test_sand_free_running_horizon():
-    domain, sand, solids = scenes.sand_pile(14, drop=2.0)
+@pytest.mark.parametrize("n_side", [14, 40])
+def test_sand_free_running_horizon(n_side):
+    # 10 free-running steps; 2 744 and 64 000 particles
+    domain, sand, solids = scenes.sand_pile(n_side, drop=2.0)
     P, G = make_pair(domain, sand, solids)
     for step in range(10):
         P.L.lo_step_sand(P.p, 0.016, 4, 0)
@@ -366,6 +383,75 @@ def test_sand_free_running_horizon():
 
 
 # ----------------------------------------------------------------------------------------------
+def aabb_first_k_numpy(pos, center, half, k):
+    """particle_collide_with_player + the first-k loop of set_particles_box_colliders_positions
+    (src/BulletPhysics.cpp:602-606,623-642): particles in index order with |p - player| <= half on every axis,
+    stopping once k proxy boxes are placed."""
+    d = np.abs(pos - np.asarray(center, np.float32)[None, :])
+    inside = np.all(d <= np.asarray(half, np.float32)[None, :], axis=1)
+    return pos[np.nonzero(inside)[0][:k]]
+
+
+@pytest.mark.parametrize("mode", ["sand", "fluid"])
+def test_aabb_first_k_matches_the_reference_scan(mode):
+    """lgpu_aabb_first_k (the feed of the Bullet proxy boxes): same particles, same order, same
+    truncation as the reference's host loop over simulation.positions — after a sand step (storage permuted
+    by the sort) and after fluid steps (storage order kept, device order sorted)."""
+    domain, sand, solids = scenes.sand_pile(16, drop=1.0)
+    with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
+        G.upload_sand(sand); G.upload_solids(solids)
+        for _ in range(3):
+            if mode == "sand":
+                G.step_sand(dt=0.016, iterations=4, exact_math=1)
+            else:
+                G.step_fluid(dt=0.01, iterations=1, literal_lambda_index=1, exact_math=1)
+        pos, _, _ = G.download()  # the reference's storage order
+        center = pos.mean(axis=0) + np.float32(0.3)
+        scale = np.array([2.0, 3.0, 2.0], np.float32) + np.float32(0.5 * 4.0)  # player_box_scale + 4 r (:604)
+        half = scale * np.float32(0.5)
+        hits = len(aabb_first_k_numpy(pos, center, half, 10 ** 9))
+        assert hits > 100, "the scene must have more candidates than proxy boxes"
+        for k in (100, 7, 1, hits, hits + 50):
+            want = aabb_first_k_numpy(pos, center, half, k)
+            got = G.aabb_first_k(center, half, k)
+            assert got.shape == want.shape and np.array_equal(got, want), "k=%d" % k
+        far = G.aabb_first_k((-50.0, -50.0, -50.0), half, 100)
+        assert far.shape == (0, 3)
+        assert G.aabb_first_k(center, half, 0).shape == (0, 3)
+
+
+def test_queries_on_a_dense_domain_with_capacity_equal_to_n():
+    """More particles than grid cells (n > C + 16k) and capacity == n: the scans of lgpu_remove_in_cells and
+    lgpu_aabb_first_k run over the PARTICLES (scan status words and scratch were sized by the cell
+    count).  Run under compute-sanitizer by tools/gpu_round.sh."""
+    domain = (40, 40, 40)
+    sand = scenes.lattice(38, 38, 38, origin=(1.0, 1.0, 1.0), jitter=0.02)
+    with lgpu.Context(domain, capacity_sand=len(sand)) as G:
+        assert len(sand) > G.num_cells + 16384
+        G.upload_sand(sand)
+        G.step_sand(dt=0.016, iterations=1, exact_math=1)
+        pos, _, _ = G.download()
+        center, half = (20.0, 20.0, 20.0), (6.0, 5.0, 4.0)
+        want = aabb_first_k_numpy(pos, center, half, 100)
+        assert np.array_equal(G.aabb_first_k(center, half, 100), want)
+        # sink over the bottom cell layers: every particle whose cell is listed goes, the others stay (as a set)
+        cs = np.float32(G.cell_size)
+        cell = (pos / cs).astype(np.int32)  # get_cell_id: IEEE division, truncation
+        gx, gy, gz = G.grid
+        ids = cell[:, 1] * gx * gz + cell[:, 0] * gz + cell[:, 2]
+        sink = np.array([y * gx * gz + x * gz + z for y in range(2) for x in range(gx) for z in range(gz)], np.int32)
+        doomed = np.isin(ids, sink)
+        assert G.cell_count((0, 0, 0), (gx - 1, 1, gz - 1), False) == int(doomed.sum())
+        removed = G.remove_in_cells(sink)
+        assert removed == int(doomed.sum()) and G.n == len(sand) - removed
+        left, _, _ = G.download()
+        a = np.sort(left.view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel())
+        b = np.sort(pos[~doomed].view([("x", "f4"), ("y", "f4"), ("z", "f4")]).ravel())
+        assert np.array_equal(a, b), "survivors"
+        G.step_sand(dt=0.016, iterations=1, exact_math=1)  # the state is still steppable
+        assert G.download()[0].shape == (len(sand) - removed, 3)
+
+
 def test_edge_cases():
     # empty, single particle, ragged block, particles on the domain faces, coincident particles
     with lgpu.Context((20, 20, 20), capacity_sand=16) as G:

@@ -43,15 +43,20 @@ def test_kernel_tables_golden():
     P.close()
 
 
-@pytest.mark.parametrize("name,jacobi", [("fluid_literal_8.npz", 0), ("fluid_jacobi_8.npz", 1)])
-def test_fluid_golden(name, jacobi):
+@pytest.mark.parametrize("name,jacobi,sph", [("fluid_literal_8.npz", 0, 0), ("fluid_jacobi_8.npz", 1, 0), ("fluid_poly6_jacobi_8.npz", 1, 1)])
+def test_fluid_golden(name, jacobi, sph):
     g = gold(name)
     P = O.PortSim(*[int(x) for x in g["domain"]], capacity=len(g["sand"]), n_solid=len(g["solids"]))
     P.set_sand(g["sand"]); P.set_solid(g["solids"])
+    P.s.sph_kernel = sph  # 1: W / gradW = poly6 / spiky (src/Kernels.cpp:43-67)
     for s in range(3):
         P.L.lo_step_fluid(P.p, 0.01, 1, jacobi, 1)
         off, flat = P.neighbors()
-        assert np.array_equal(P.keys, g["keys_%d" % s])
+        # the fixture's keys are get_cell_id of the reference's positions_star AFTER the step; with the cubic spline no
+        # particle of this scene changes cell inside a step, so they are also the keys of the grid build
+        assert np.array_equal(P.cell_ids(P.positions_star), g["keys_%d" % s])
+        if not sph:
+            assert np.array_equal(P.keys, g["keys_%d" % s])
         assert np.array_equal(off, g["nbr_off_%d" % s]) and np.array_equal(flat, g["nbr_%d" % s])
         assert np.array_equal(P.lambdas, g["lambda_%d" % s])
         assert np.array_equal(P.positions, g["pos_%d" % s]) and np.array_equal(P.velocities, g["vel_%d" % s])
@@ -102,7 +107,7 @@ needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (
 
 
 @needs_ref
-@pytest.mark.parametrize("mode", ["fluid_lit", "fluid_jac", "fluid_jac4_fixed", "sand", "credits"])
+@pytest.mark.parametrize("mode", ["fluid_lit", "fluid_jac", "fluid_jac4_fixed", "fluid_poly6_jac", "sand", "credits"])
 def test_port_vs_compiled_reference(mode):
     n_side = 12
     if mode in ("sand", "credits"):
@@ -115,10 +120,12 @@ def test_port_vs_compiled_reference(mode):
     flags = np.full(len(sand), 2, np.int32) if mode == "credits" else None
     R.set_sand(sand, None, flags); R.set_solid(solids)
     P.set_sand(sand, None, flags); P.set_solid(solids)
+    if "poly6" in mode:  # Simulation::W / gradW pointed at poly6_kernel / spiky_kernel (src/Kernels.cpp:43-67)
+        R.set_kernel(1); P.s.sph_kernel = 1
     for step in range(4):
-        if mode == "fluid_lit":
+        if mode in ("fluid_lit", "fluid_poly6_lit"):
             R.set_fun(R.FLUID); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 1, 0, 1)
-        elif mode == "fluid_jac":
+        elif mode in ("fluid_jac", "fluid_poly6_jac"):
             R.set_fun(R.FLUID_JACOBI, 1, True); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 1, 1, 1)
         elif mode == "fluid_jac4_fixed":
             R.set_fun(R.FLUID_JACOBI, 4, False); R.step(0.01); P.L.lo_step_fluid(P.p, 0.01, 4, 1, 0)
