@@ -147,17 +147,36 @@ def step_kwargs(kind, K, dt, exact, literal=0):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
-    """Times the reference's own CPU step on a bounded sample of the workload.  Uses the compiled
-    unmodified reference (oracle/_ref/libref_time.so, the reference's Release flags) when present,
-    else the plain-C port.  Single-threaded: the reference has no threading."""
+def workload_config(workload, kind, n, n_solid, domain, grid_cells, K, dt, literal, reset_every):
+    """The keys that NAME the workload: identical in the B200 arm and in the reference arm."""
+    return {"workload": workload, "kind": kind, "particles": int(n), "solid_particles": int(n_solid), "domain": [int(x) for x in domain],
+            "grid_cells": int(grid_cells), "solver_iterations": int(K), "dt": dt,
+            "literal_lambda_index": int(literal) if kind == "fluid" else None, "scene_reset_every": int(reset_every)}
+
+
+def grid_cells_of(domain, radius=0.5, scale=3.1):
+    """(int)(D / h) + 1 per axis, h = 3.1 r in fp32 (reference src/Lustrine.cpp:253-266)."""
+    h = np.float32(scale) * np.float32(radius)
+    g = [int(np.float32(d) / h) + 1 for d in domain]
+    return g[0] * g[1] * g[2]
+
+
+def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s, literal=0, stock=False):
+    """Times the reference's own CPU step.  Uses the compiled unmodified reference (oracle/_ref/libref_time.so, the
+    reference's Release flags) when present, else the plain-C port.  Single-threaded: the reference has no threading.
+    The scene is the workload's own (exactly `side`^3 particles) whenever the whole run fits the budget; otherwise
+    a smaller cube of the same scene family.  stock=True: the unmodified simulate_fluid (one in-place Gauss-Seidel
+    iteration, lambdas[loop counter]) instead of the K-iteration Jacobi loop of oracle/ref_harness.cpp."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    # K=4 fluid: ~2.5e5 particle-substeps/s on one core; sand: ~5e5 (BASELINE.md §2)
-    est = 2.0e5 if kind == "fluid" else 4.5e5
-    n_target = int(est * budget_s / max(steps + warmup, 1))
-    # (the reference sizes every array by the domain volume, SURVEY F17: samples above 100^3 need tens of GB of host memory)
-    sample_side = int(max(8, min(side, 100, round(n_target ** (1.0 / 3.0)))))
+    # K=4 fluid: ~3.8e5 particle-substeps/s on one core of the GPU boxes; sand: ~5e5 (BENCH_r01.json, BASELINE.md §2)
+    est = (3.5e5 if K > 1 else 4.5e5) if kind == "fluid" else 4.5e5
+    full_n = side ** 3
+    sample_side = side
+    # (the reference sizes every array by the domain volume, SURVEY F17: scenes above ~110^3 need tens of GB of host memory)
+    if full_n * (steps + warmup) / est > budget_s or side > 110:
+        n_target = est * budget_s / max(steps + warmup, 1)
+        sample_side = int(max(8, min(side, 100, int(n_target ** (1.0 / 3.0)))))
     domain, sand, solids = make_scene(kind, sample_side)
     if kind == "sand" and solids is not None and len(solids) > 60000:
         # one Bullet box per solid voxel is created by the reference's init: keep the floor modest
@@ -175,7 +194,10 @@ def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
             if solids is not None:
                 R.set_solid(solids)
             if kind == "fluid":
-                R.set_fun(R.FLUID_JACOBI if K != 1 else R.FLUID, K, True)
+                if stock:
+                    R.set_fun(R.FLUID)
+                else:
+                    R.set_fun(R.FLUID_JACOBI, K, bool(literal))
             else:
                 R.set_fun(R.SAND)
             R.step(dt, warmup)
@@ -189,7 +211,7 @@ def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
                 P.set_solid(solids)
             def one():
                 if kind == "fluid":
-                    P.L.lo_step_fluid(P.p, dt, K, 1 if K != 1 else 0, 1)
+                    P.L.lo_step_fluid(P.p, dt, 1 if stock else K, 0 if stock else 1, 1 if stock else int(literal))
                 else:
                     P.L.lo_step_sand(P.p, dt, K, 0)
             for _ in range(warmup):
@@ -204,13 +226,16 @@ def run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s):
         os.dup2(saved, 1)
         os.close(devnull)
     value = n * steps / seconds
-    sample = ("%s scene, %d^3 = %d particles, %d substeps (%d warm-up), %d solver iterations, dt=%g; %s"
-              % (kind, sample_side, n, steps, warmup, K, dt,
-                 "unmodified reference sources, -O3 -mavx2 -ffast-math -mfma -march=skylake"
-                 + ("; K>1 loop = oracle/ref_harness.cpp simulate_fluid_jacobi over the reference's own neighbour search and kernels" if (kind == "fluid" and K != 1) else "")
-                 if kind_name == "reference" else "plain-C port of the reference, -O2"))
+    how = ("unmodified reference sources, -O3 -mavx2 -ffast-math -mfma -march=skylake" if kind_name == "reference" else "plain-C port of the reference, -O2")
+    if kind == "fluid":
+        how += ("; stock simulate_fluid (src/Simulate.cpp:27-115): ONE in-place iteration, lambdas[loop counter]" if stock else
+                "; K-iteration loop = oracle/ref_harness.cpp simulate_fluid_jacobi over the reference's own neighbour search and kernels, lambdas[%s]"
+                % ("loop counter" if literal else "neighbour"))
+    sample = ("%s scene, %d^3 = %d particles%s, %d substeps (%d warm-up), %d solver iterations, dt=%g; %s"
+              % (kind, sample_side, n, "" if sample_side == side else " (the workload has %d^3: bounded sample)" % side, steps, warmup,
+                 1 if stock else K, dt, how))
     return {"value": value, "unit": "particle-substeps/s", "cores": 1, "kind": kind_name, "sample": sample,
-            "seconds": seconds, "host_cores_available": os.cpu_count()}, n, seconds
+            "seconds": seconds, "host_cores_available": os.cpu_count(), "exact_workload_size": sample_side == side}, n, seconds, (domain, solids)
 
 
 def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src, domain, sand, solids, rank, world, local_rank):
@@ -219,6 +244,21 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
     import torch.distributed as dist
     from lustrine_b200 import lgpu, slabs
     n_total = len(sand)
+    # Weak-scaling reference measured in this same run: the scene with 1/N of the particles (cube of side / N^(1/3)) on ONE
+    # GPU — every rank runs it on its own device at the same time, the slowest rank counts.
+    single = None
+    if kind == "fluid" and not args.no_extras:
+        s1 = int(round(side / world ** (1.0 / 3.0)))
+        name1 = "dam_break_1gpu_%d" % s1
+        WORKLOADS[name1] = (kind, s1, K, dt)
+        fl = Flusher()
+        r1, G1, _ = single_gpu_workload(name1, args, local_rank, fl, hbm_gbs, peak_src, min(steps, 20), 3)
+        G1.close()
+        del fl
+        torch.cuda.empty_cache()
+        t1 = torch.tensor([r1["ms_per_step"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+        single = {"workload": name1, "particles": s1 ** 3, "ms_per_step": float(t1.item()), "value": s1 ** 3 / (float(t1.item()) * 1e-3)}
     S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank)
     G = S.G
     mode = 1 if kind == "fluid" else 2
@@ -287,7 +327,9 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
     cells_per_particle = info["local_cells"] / max(n_local, 1)
     step_bytes = fluid_bytes_per_particle(K, cells_per_particle) if kind == "fluid" else sand_bytes_per_particle(K, cells_per_particle)
     if kind == "fluid":
-        cand = {"fluid_lambda": phase[6] / K, "fluid_deltap": phase[7] / K}
+        cand = {"fluid_deltap": phase[7] / K}
+        if K > 1:
+            cand["fluid_lambda"] = phase[6] / (K - 1)   # (the first lambda pass runs inside the table build)
     else:
         cand = {"sand_iteration": phase[7] / K}
     dom = max(cand, key=lambda k: cand[k])
@@ -341,21 +383,194 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
                "path": "lgpu_slab_upload + lgpu_step + lgpu_slab_download with pinned host buffers on every rank"}
     plan = S.slabs
     line = {"metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "kind": kind, "particles": n_total,
-                       "scaling_note": "the default N-GPU workload (N > 1) is the fixed 16M scene of BASELINE configs[3]; the 1-GPU line is the 1M scene of configs[1]", "particles_per_gpu": [int(g[1].item()) for g in gathered],
-                       "domain": list(domain), "solver_iterations": K, "dt": dt,
-                       "partition": "x-slabs of whole cell columns, one-column ghost layer, migration + ghost refresh written peer-to-peer over NVLink",
-                       "slabs": [list(x) for x in plan], "collective": "none on the data path",
-                       "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
-                       "literal_lambda_index": 0 if kind == "fluid" else None, "scene_reset_every": args.reset_every,
-                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
-                       "timing": "CUDA events on the launching stream around every substep (barrier before each), summed, max over ranks",
-                       "wall_ms_per_step_incl_flush_and_barriers": t_wall * 1e3 / steps},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(workload, kind, n_total, 0 if solids is None else len(solids), domain, grid_cells_of(domain), K, dt, 0, args.reset_every),
+            "notes": {"scaling_note": "every line is throughput (particle-substeps/s), so value(N) / (N * value(1)) is a weak-scaling efficiency; the 1-GPU "
+                                      "line is the 1M scene of BASELINE configs[1], the N-GPU lines (N > 1) the 16M scene of configs[3] (%d particles per GPU "
+                                      "here); weak_efficiency below compares like with like" % (n_total // world),
+                      "particles_per_gpu": [int(g[1].item()) for g in gathered],
+                      "partition": "x-slabs of whole cell columns, one-column ghost layer, migration + ghost refresh written peer-to-peer over NVLink",
+                      "slabs": [list(x) for x in plan], "collective": "none on the data path",
+                      "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
+                      "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
+                      "timing": "CUDA events on the launching stream around every substep (barrier before each), summed, max over ranks",
+                      "wall_ms_per_step_incl_flush_and_barriers": t_wall * 1e3 / steps},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": None, "e2e": e2e,
             "gpu_launches": int(sum(g[0].item() for g in gathered)), "clocks": sampler.result()}
+    if single is not None:
+        line["single_gpu_same_load"] = single
+        line["weak_efficiency"] = single["ms_per_step"] / ms_per_step   # T(1 GPU, particles / N) / T(N GPUs, particles)
     S.close()
     return line
+
+
+class Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed substeps (outside the event bracket)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def __call__(self):
+        self.buf.zero_()
+        self.torch.cuda.synchronize()
+
+
+def timed_substeps(G, step, params, steps, warmup, flush, reset=None, reset_every=0):
+    """`warmup` untimed substeps, then `steps` substeps each bracketed by CUDA events on the launching stream (summed),
+    L2 flushed between them.  reset(): puts the scene back (outside the bracket) every `reset_every` substeps."""
+    for k in range(warmup):
+        if reset and reset_every and k % reset_every == 0:
+            reset()
+        step(params)
+    G.sync()
+    dev_ms = 0.0
+    timed_substeps.launches = 0
+    for k in range(steps):
+        if reset and reset_every and k % reset_every == 0:
+            reset()
+        flush()
+        l0 = G.launch_count()
+        step(params)
+        G.sync()
+        timed_substeps.launches += G.launch_count() - l0   # kernels of the substeps themselves (not the scene re-uploads)
+        dev_ms += G.last_step_ms(0)
+    return dev_ms / steps
+
+
+def phase_times(G, step, params, flush, reset, n_phases=9, reps=20):
+    """Per-kernel-kind device times (ms per substep): event marks around every launch (a separate short pass)."""
+    G.set_phase_timing(True)
+    phase = np.zeros(n_phases)
+    reset()
+    for _ in range(reps):
+        flush()
+        step(params)
+        G.sync()
+        for ph in range(n_phases):
+            phase[ph] += G.last_step_ms(ph)
+    G.set_phase_timing(False)
+    return phase / reps
+
+
+def rooflines(kind, K, n, num_cells, phase, ms_per_step, hbm_gbs, peak_src, workload):
+    """roofline of the dominant solver kernel and of the whole substep (algorithmic bytes: SURVEY §8d)."""
+    cells_per_particle = num_cells / max(n, 1)
+    if kind == "fluid":
+        step_bytes = fluid_bytes_per_particle(K, cells_per_particle)
+        # the first density + lambda pass runs inside the table build (phase 4): K - 1 separate lambda launches
+        cand = {"fluid_deltap": phase[7] / K}
+        if K > 1:
+            cand["fluid_lambda"] = phase[6] / (K - 1)
+    else:
+        step_bytes = sand_bytes_per_particle(K, cells_per_particle)
+        cand = {"sand_iteration": phase[7] / K}
+    dom = max(cand, key=lambda k: cand[k])
+    dom_ms = cand[dom]
+    dom_bytes = KERNEL_BYTES[dom] * n
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = load_traffic(workload, "k_" + dom)
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": achieved / hbm_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                "note": "sparse stencil: ~19 neighbour interactions per particle per launch are gathered from a shared-memory stage of the "
+                        "particle's brick; the kernel is bound by that gather (LDS wavefronts + issue slots), not by HBM (DESIGN.md §5)"}
+    step_achieved = step_bytes * n / (ms_per_step * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": step_achieved / hbm_gbs,
+                     "algorithmic_bytes_per_particle_substep": step_bytes,
+                     "phases_ms": {"predict_key_hist": phase[1], "scan": phase[2], "scatter_reorder": phase[3],
+                                   "neighbour_table" + ("_and_first_lambda" if kind == "fluid" else ""): phase[4],
+                                   "lambda_total": phase[6], "deltap_or_contact_total": phase[7],
+                                   "sum": float(phase[1:5].sum() + phase[6] + phase[7])}}
+    return roofline, roofline_step
+
+
+def single_gpu_workload(workload, args, device, flush, hbm_gbs, peak_src, steps, warmup, free_run_steps=0):
+    """One workload on one GPU through the C ABI with the state resident in HBM.  Returns (dict of results, context, scene)."""
+    from lustrine_b200 import lgpu
+    kind, side, K, dt = WORKLOADS[workload]
+    domain, sand, solids = make_scene(kind, side)
+    n = len(sand)
+    G = lgpu.Context(domain, capacity_sand=n, capacity_solid=0 if solids is None else len(solids), device=device)
+    G.upload_sand(sand)
+    if solids is not None:
+        G.upload_solids(solids)
+    params = lgpu.default_step_params(**step_kwargs(kind, K, dt, args.exact, args.literal))
+    step = G.step_fluid if kind == "fluid" else G.step_sand
+    reset = lambda: G.upload_sand(sand)
+    ms = timed_substeps(G, step, params, steps, warmup, flush, reset, args.reset_every)
+    launches = timed_substeps.launches
+    phase = phase_times(G, step, params, flush, reset)
+    counters = G.dump(lgpu.DUMP_COUNTERS)
+    roofline, roofline_step = rooflines(kind, K, n, G.num_cells, phase, ms, hbm_gbs, peak_src, workload)
+    out = {"ms_per_step": ms, "value": n / (ms * 1e-3), "roofline": roofline, "roofline_step": roofline_step,
+           "table_overflows": int(counters[1]), "key_violations": int(counters[0]), "launches": int(launches),
+           "config": workload_config(workload, kind, n, 0 if solids is None else len(solids), domain, G.num_cells, K, dt,
+                                     args.literal if kind == "fluid" else 0, args.reset_every)}
+    if free_run_steps:
+        # the scene left to itself (no re-upload): the column collapses, lists lengthen, warps diverge
+        reset()
+        G.sync()
+        fr_ms = timed_substeps(G, step, params, free_run_steps, 0, flush)
+        c2 = G.dump(lgpu.DUMP_COUNTERS)
+        # the second half alone: the collapsed regime
+        tail_ms = timed_substeps(G, step, params, max(free_run_steps // 4, 1), 0, flush)
+        out["free_run"] = {"substeps": free_run_steps, "ms_per_step": fr_ms, "value": n / (fr_ms * 1e-3),
+                           "ms_per_step_after": tail_ms, "table_overflows": int(c2[1]) - int(counters[1]),
+                           "key_violations": int(c2[0]) - int(counters[0]),
+                           "note": "reset-every 0: %d free-running substeps from the initial scene (SURVEY §8d config 2), then %d more "
+                                   "(ms_per_step_after); table_overflows = particle-substeps whose list exceeded 32 entries and re-walked"
+                                   % (free_run_steps, max(free_run_steps // 4, 1))}
+    return out, G, (domain, sand, solids, params, step, kind, K, dt)
+
+
+def wrapper_e2e(workload, steps, sync_mode):
+    """The same metric through the reference-facing plugin boundary with HOST buffers: LustrineWrapper's C entry points
+    on liblustrine_b200.so — init_grid_box + init_simulation, then per step Wrapper::simulate(dt, attract, blow)
+    followed by simulation_bind_positions_copy into a pinned caller buffer (reference src/LustrineWrapper.cpp:343-379).
+    sync_mode 0 = SYNC_FULL: the host arrays of Lustrine::Simulation stay authoritative, every step uploads
+    positions / velocities / attracted and downloads them again; 2 = SYNC_LAZY: the state stays on the device and only
+    the positions come back (what the game does)."""
+    import torch
+    from wrapper_driver import Wrapper
+    kind, side, K, dt = WORKLOADS[workload]
+    lib = os.path.join(ROOT, "lustrine_b200", "lib", "liblustrine_b200.so")
+    if not os.path.exists(lib):
+        raise RuntimeError("liblustrine_b200.so is missing: run __graft_entry__.build()")
+    os.environ.setdefault("LUSTRINE_B200_QUIET", "1")
+    W = Wrapper(lib)
+    domain = (3 * side, 2 * side, 2 * side) if kind == "fluid" else (3 * side, side + side // 2, 3 * side)
+    sand_pos = (1.0, 1.0, 1.0) if kind == "fluid" else (float(side), 8.0, float(side))
+    solids = [] if kind == "fluid" else [((3 * side, 2, 3 * side), (0.0, 0.0, 0.0), 2)]
+    data = W.init(domain, 0.5, sand=[((side, side, side), sand_pos)], solids=solids, subdivision=1)
+    n = data.num_sand_particles
+    if kind == "fluid":
+        W.L.b200_set_simulate_function(2)       # Simulation::simulate_fun = simulate_fluid (SURVEY F1: set through the public field)
+        W.L.b200_set_solver_options(K, 0, 0)    # K iterations, lambdas[neighbour], throughput arithmetic
+    else:
+        W.L.b200_set_solver_options(1, 0, 0)
+    W.L.b200_set_host_sync(sync_mode)
+    out = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        W.L.simulate(dt, False, False)
+        W.L.simulation_bind_positions_copy(out.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        W.L.simulate(dt, False, False)
+        W.L.simulation_bind_positions_copy(out.data_ptr())
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    checksum = float(out.double().sum())
+    W.L.cleanup_simulation()
+    h2d = n * 28 if sync_mode == 0 else 0
+    d2h = n * (28 + 12) if sync_mode == 0 else n * 12
+    return {"value": n / (ms * 1e-3), "unit": "particle-substeps/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": steps, "particles": int(n), "position_checksum": checksum,
+            "path": "LustrineWrapper C API on liblustrine_b200.so: simulate(dt, attract, blow) + simulation_bind_positions_copy(pinned buffer), "
+                    + ("SYNC_FULL (host arrays authoritative: positions, velocities, attracted uploaded and downloaded every step)" if sync_mode == 0
+                       else "SYNC_LAZY (state resident on the device, positions copied out every step)")}
 
 
 def main():
@@ -369,13 +584,15 @@ def main():
     ap.add_argument("--literal", type=int, default=0, help="fluid: 1 = lambdas[loop counter] as in the reference (single GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip free_run / stock_pair / secondary workloads (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--free-run", type=int, default=200, help="free-running substeps of the free_run leg")
     ap.add_argument("--reset-every", type=int, default=20,
                     help="re-upload the initial scene every R substeps (outside the timed bracket); 0 = free run")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner,
-    # torchrun notices) is sent to stderr instead
+    # torchrun notices, the wrapper's init banner) is sent to stderr instead
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
@@ -389,7 +606,7 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
 
     # BASELINE.json: 1 GPU = the 1M dam break (configs[1]); 2 / 4 / 8 GPUs = the 16M dam break partitioned
-    # into 2 / 4 / 8 slabs (configs[3]: the same scene at every N > 1, i.e. strong scaling among them)
+    # into 2 / 4 / 8 slabs (configs[3])
     workload = args.workload or ("dam_break_1m" if args.gpus <= 1 else "dam_break_16m")
     kind, side, K, dt = WORKLOADS[workload]
     metric = "particle-substeps/s"
@@ -398,12 +615,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb, n, seconds = run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s=max(args.cpu_budget * 6.0, 60.0))
+        cb, n, seconds, (domain, solids) = run_cpu_reference(kind, side, K, dt, steps, warmup, budget_s=420.0, literal=args.literal)
+        full_domain = (3 * side, 2 * side, 2 * side) if kind == "fluid" else (3 * side, side + side // 2, 3 * side)
+        n_solid_full = 0 if kind == "fluid" else 3 * side * 2 * 3 * side + 2 * (side // 4) * 4 * (side // 4)   # make_scene: floor + two boxes
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "particle-substeps/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * seconds / steps,
-                "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "kind": kind, "solver_iterations": K, "dt": dt,
-                           "note": "CPU reference on a bounded sample of the workload: " + cb["sample"]},
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(workload, kind, side ** 3, n_solid_full, full_domain,
+                                          grid_cells_of(full_domain), K, dt, args.literal, args.reset_every),
+                "notes": {"sample": cb["sample"], "exact_workload_size": cb["exact_workload_size"],
+                          "timing": "steady_clock around the reference's simulate_fun on one host core (the reference has no threading)"},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -421,9 +642,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     hbm_gbs, peak_src = load_peaks()
-    domain, sand, solids = make_scene(kind, side)
-    n = len(sand)
     if world > 1:
+        domain, sand, solids = make_scene(kind, side)
         result = run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_src, domain, sand, solids, rank, world, local_rank)
         if rank == 0:
             emit(result)
@@ -431,152 +651,91 @@ def main():
         dist.destroy_process_group()
         return 0
 
-    G = lgpu.Context(domain, capacity_sand=n, capacity_solid=0 if solids is None else len(solids), device=local_rank)
-    G.upload_sand(sand)
-    if solids is not None:
-        G.upload_solids(solids)
-    kw = step_kwargs(kind, K, dt, args.exact, args.literal)
-    params = lgpu.default_step_params(**kw)
-    step = G.step_fluid if kind == "fluid" else G.step_sand
-
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def flush_l2():
-        flush_buf.zero_()
-        torch.cuda.synchronize()
-
-    def maybe_reset(k):
-        # The scene is put back to its initial state every --reset-every substeps, outside the timed
-        # bracket, so that every timed substep runs in the regime the CPU baseline is timed in (the first
-        # substeps of the dam break; with --literal 1 the column would otherwise collapse into a degenerate
-        # pile within a few hundred substeps).
-        if args.reset_every and k % args.reset_every == 0:
-            G.upload_sand(sand)
-
-    for k in range(warmup):
-        maybe_reset(k)
-        step(params)
-    G.sync()
-
-    # timed region: K substeps, each bracketed by CUDA events on the launching stream, L2 flushed
-    # (outside the event bracket) between substeps
+    flush = Flusher()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = G.launch_count()
-    torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    for k in range(steps):
-        maybe_reset(k)
-        flush_l2()
-        step(params)
-        G.sync()
-        dev_ms += G.last_step_ms(0)
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    launches = G.launch_count() - launches0
+    main_res, G, scene = single_gpu_workload(workload, args, local_rank, flush, hbm_gbs, peak_src, steps, warmup,
+                                             free_run_steps=0 if args.no_extras else args.free_run)
     sampler.stop_flag = True
     sampler.join()
-    ms_per_step = dev_ms / steps
-    value = n / (ms_per_step * 1e-3)
+    domain, sand, solids, params, step, kind, K, dt = scene
+    n = len(sand)
+    ms_per_step, value = main_res["ms_per_step"], main_res["value"]
 
-    # back-to-back throughput without the flush (what a game loop sees); reported, not the headline
-    G.upload_sand(sand)
-    G.sync()
-    t0 = time.perf_counter()
-    for _ in range(min(steps, args.reset_every or steps)):
-        step(params)
-    G.sync()
-    pipelined_ms = (time.perf_counter() - t0) * 1e3 / min(steps, args.reset_every or steps)
-
-    # per-kernel timing pass (phase timing adds event records, so it is a separate short pass)
-    G.set_phase_timing(True)
-    phase = np.zeros(8)
-    PH = 20
-    G.upload_sand(sand)
-    for _ in range(PH):
-        flush_l2()
-        step(params)
+    # back-to-back throughput without the flush (what a game loop sees), eager and as a CUDA graph; reported, not the headline
+    def pipelined(use_graph):
+        G.set_use_graph(use_graph)
+        G.upload_sand(sand)
+        for _ in range(3):
+            step(params)
         G.sync()
-        for ph in range(8):
-            phase[ph] += G.last_step_ms(ph)
-    phase /= PH
-    G.set_phase_timing(False)
-    counters = G.dump(lgpu.DUMP_COUNTERS)
+        reps = min(steps, args.reset_every or steps)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step(params)
+        G.sync()
+        G.set_use_graph(0)
+        return (time.perf_counter() - t0) * 1e3 / reps
+    pipelined_ms = pipelined(0)
+    pipelined_graph_ms = pipelined(1)
 
-    cells_per_particle = G.num_cells / n
-    if kind == "fluid":
-        step_bytes = fluid_bytes_per_particle(K, cells_per_particle)
-        cand = {"fluid_lambda": phase[6] / K, "fluid_deltap": phase[7] / K}
-    else:
-        step_bytes = sand_bytes_per_particle(K, cells_per_particle)
-        cand = {"sand_iteration": phase[7] / K}
-    dom = max(cand, key=lambda k: cand[k])
-    dom_ms = cand[dom]
-    dom_bytes = KERNEL_BYTES[dom] * n
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic, traffic_src = load_traffic(workload, "k_" + dom)
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                "frac": achieved / hbm_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
-                "note": "sparse stencil: ~19 neighbour interactions per particle per launch are gathered from the shared-memory stage; "
-                        "the traffic above the algorithmic bytes is the neighbour table (42 MB per launch at 1M particles); the kernel is "
-                        "bound by the shared-memory gather and its block prologue, not by HBM (DESIGN.md §5)"}
-    step_achieved = step_bytes * n / (ms_per_step * 1e-3) / 1e9
-    roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": step_achieved / hbm_gbs,
-                     "algorithmic_bytes_per_particle_substep": step_bytes,
-                     "phases_ms": {"predict_key_hist": phase[1], "scan": phase[2], "scatter_reorder": phase[3],
-                                   "neighbour_table": phase[4], "lambda_total": phase[6], "deltap_or_contact_total": phase[7],
-                                   "sum": float(phase[1:5].sum() + phase[6] + phase[7])}}
+    extras = {}
+    if not args.no_extras and kind == "fluid":
+        # stock pair: the reference's OWN semantics — one solver iteration, lambdas[loop counter] — in parity
+        # arithmetic and in throughput arithmetic (the CPU side of the pair is timed with cpu_baseline below)
+        sp = {}
+        for name, exact in (("b200_exact", 1), ("b200_fast", 0)):
+            p1 = lgpu.default_step_params(dt=dt, iterations=1, literal_lambda_index=1, exact_math=exact)
+            G.upload_sand(sand)
+            ms1 = timed_substeps(G, step, p1, 20, 3, flush, lambda: G.upload_sand(sand), args.reset_every)
+            sp[name] = {"ms_per_step": ms1, "value": n / (ms1 * 1e-3)}
+        extras["stock_pair"] = {"config": "K=1, literal_lambda_index=1 (src/Simulate.cpp:27-115 as shipped), %d particles" % n, **sp}
+    G.close()
 
-    # ---------------- e2e through the C ABI with host buffers ----------------
+    if not args.no_extras and workload == "dam_break_1m":
+        # BASELINE configs[2]: the 4M sand pile on voxel solids (driver-visible record of the sand solver)
+        sec_steps = max(10, min(steps, 40))
+        sec, G2, scene2 = single_gpu_workload("sand_pile_4m", args, local_rank, flush, hbm_gbs, peak_src, sec_steps, 5)
+        G2.close()
+        sec_line = {"value": sec["value"], "unit": "particle-substeps/s", "ms_per_step": sec["ms_per_step"], "steps": sec_steps,
+                    "config": sec["config"], "roofline": sec["roofline"], "roofline_step": sec["roofline_step"],
+                    "table_overflows": sec["table_overflows"], "cpu_baseline": None}
+        if not args.no_cpu_baseline:
+            cbs, _, _, _ = run_cpu_reference("sand", 160, 4, 0.016, steps=2, warmup=1, budget_s=args.cpu_budget)
+            sec_line["cpu_baseline"] = cbs
+        extras["secondary"] = {"sand_pile_4m": sec_line}
+
+    # ---------------- e2e through the plugin boundary with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        pos_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        vel_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        flg_h = torch.empty((n,), dtype=torch.int32).pin_memory()
-        G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-        e_steps = min(steps, args.reset_every or 50)
-        G.upload_sand(sand)
-        G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-        for _ in range(3):
-            G.upload_from(n, pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-            step(params)
-            G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            G.upload_from(n, pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-            step(params)
-            G.download_into(pos_h.data_ptr(), vel_h.data_ptr(), flg_h.data_ptr())
-        torch.cuda.synchronize()
-        e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-        checksum = float(pos_h.double().sum())
-        e2e = {"value": n / (e_ms * 1e-3), "unit": "particle-substeps/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": n * 28, "steps": e_steps,
-               "position_checksum": checksum,
-               "path": "lgpu_upload_sand + lgpu_step + lgpu_download_sand on pinned host buffers"}
+        e_steps = min(steps, 20)
+        e2e = wrapper_e2e(workload, e_steps, 0)
+        if not args.no_extras:
+            extras["e2e_device_resident"] = wrapper_e2e(workload, e_steps, 2)
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cpu_baseline, _, _ = run_cpu_reference(kind, side, K, dt, steps=3, warmup=1, budget_s=args.cpu_budget)
+        cpu_baseline, _, _, _ = run_cpu_reference(kind, side, K, dt, steps=3, warmup=1, budget_s=max(args.cpu_budget, 14.0), literal=args.literal)
+        if "stock_pair" in extras:
+            cs, _, _, _ = run_cpu_reference(kind, side, 1, dt, steps=3, warmup=1, budget_s=max(args.cpu_budget, 14.0), stock=True)
+            extras["stock_pair"]["cpu_reference"] = cs
 
     line = {"metric": metric, "value": value, "unit": "particle-substeps/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload, "kind": kind, "particles": n, "solid_particles": 0 if solids is None else len(solids),
-                       "domain": list(domain), "grid_cells": G.num_cells, "solver_iterations": K, "dt": dt,
-                       "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
-                       "literal_lambda_index": args.literal if kind == "fluid" else None,
-                       "scene_reset_every": args.reset_every,
-                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
-                       "timing": "CUDA events on the launching stream around every substep, summed",
-                       "wall_ms_per_step_incl_flush": t_wall * 1e3 / steps, "pipelined_ms_per_step_no_flush": pipelined_ms,
-                       "table_overflows": int(counters[1]), "key_violations": int(counters[0])},
-            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": sampler.result()}
+            "config": main_res["config"],
+            "notes": {"arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
+                      "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
+                      "timing": "CUDA events on the launching stream around every substep, summed",
+                      "pipelined_ms_per_step_no_flush": pipelined_ms, "pipelined_ms_per_step_no_flush_cuda_graph": pipelined_graph_ms,
+                      "table_overflows": main_res["table_overflows"], "key_violations": main_res["key_violations"]},
+            "roofline": main_res["roofline"], "roofline_step": main_res["roofline_step"], "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": main_res["launches"], "clocks": sampler.result()}
+    if "free_run" in main_res:
+        line["free_run"] = main_res["free_run"]
+    line.update(extras)
     emit(line)
-    G.close()
     return 0
 
 

@@ -6,7 +6,7 @@
 
 #include <vector>
 
-#include "lgpu_neighbors.cuh"
+#include "lgpu_fluid.cuh"
 
 static thread_local char g_err[512] = "";
 void lgpu_set_error(const char* fmt, ...) {
@@ -111,7 +111,11 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     c->cap_solid = cfg->capacity_solid;
     c->M = cfg->max_neighbors > 0 ? cfg->max_neighbors : LGPU_DEFAULT_MAX_NEIGHBORS;
     c->M = (c->M + 3) & ~3;
-    c->stage_slots = LGPU_STAGE_SLOTS;  // the table stores groups of four 16-bit codes
+    c->stage_slots = LGPU_STAGE_SLOTS;
+    // brick grid of the staged kernels (lgpu_neighbors.cuh); persistent kernels launch two blocks per SM
+    c->nbY = (c->g.gY + LGPU_BY - 1) / LGPU_BY; c->nbX = (c->g.gX + LGPU_BX - 1) / LGPU_BX; c->nbZ = (c->g.gZ + LGPU_BZ - 1) / LGPU_BZ;
+    c->NB = c->nbY * c->nbX * c->nbZ;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
     if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     const size_t cap = (size_t)c->cap, C1 = (size_t)c->g.C + 2;  // + trash cell (slab mode) + end
@@ -136,7 +140,10 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
     CUDA_TRY(dalloc(&c->nbr16, cap * (size_t)(c->M / 4))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
-    CUDA_TRY(dalloc(&c->blk, cap / LGPU_TILE + 2));
+    // a non-empty brick holds at least one particle, and there are at most NB bricks
+    CUDA_TRY(dalloc(&c->brick_work, (size_t)c->NB)); CUDA_TRY(dalloc(&c->brick_ctl, (size_t)(8 + LGPU_MAX_PASSES)));
+    CUDA_TRY(dalloc(&c->brick_desc, (size_t)(c->NB < c->cap ? c->NB : c->cap) + 1));
+    CUDA_TRY(cudaMemsetAsync(c->brick_ctl, 0, sizeof(int) * (8 + LGPU_MAX_PASSES), c->stream));
     CUDA_TRY(dalloc(&c->lambda, cap)); CUDA_TRY(dalloc(&c->density, cap));
     CUDA_TRY(dalloc(&c->lambda_head, (size_t)LGPU_LAMBDA_HEAD));
     CUDA_TRY(dalloc(&c->counters, (size_t)4));
@@ -167,7 +174,7 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_state);
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
-    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->blk); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
+    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->brick_work); cudaFree(c->brick_ctl); cudaFree(c->brick_desc); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
     lgpu_slab_free(c);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -190,7 +197,9 @@ View lgpu_make_view(lgpu_ctx* c) {
     v.key_in = c->key_in; v.rank_in = c->rank_in; v.tmp_id = c->tmp_id; v.key = c->key;
     v.cell_count = c->cell_count; v.cell_start = c->cell_start;
     v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
-    v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt; v.blk = c->blk;
+    v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt;
+    v.nbY = c->nbY; v.nbX = c->nbX; v.nbZ = c->nbZ; v.NB = c->NB; v.stage_slots = c->stage_slots;
+    v.brick_work = c->brick_work; v.brick_ctl = c->brick_ctl; v.brick_desc = c->brick_desc;
     v.lambda = c->lambda; v.density = c->density; v.lambda_head = c->lambda_head;
     v.counters = c->counters;
     return v;
@@ -225,6 +234,7 @@ extern "C" int lgpu_graph_stats(const lgpu_ctx* c, long* captures, long* replays
 extern "C" int lgpu_set_stage_slots(lgpu_ctx* c, int slots) {
     if (!c || slots < 1) return LGPU_ERR_ARG;
     c->stage_slots = slots < LGPU_STAGE_SLOTS ? slots : LGPU_STAGE_SLOTS;
+    if (c->stage_slots < LGPU_DUMMY_SLOTS) c->stage_slots = LGPU_DUMMY_SLOTS;
     return LGPU_OK;
 }
 extern "C" int lgpu_set_generic_kernels(lgpu_ctx* c, int on) {
@@ -364,8 +374,17 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
 // ---------------- step drivers ----------------
 extern "C" int lgpu_slab_step_begin(lgpu_ctx* c, const lgpu_step_params* p, int mode);
 extern "C" int lgpu_slab_step_end(lgpu_ctx* c);
+int lgpu_begin_passes(lgpu_ctx* c) {
+    // work-list counters and the work cursors of this substep's staged kernels
+    c->pass = 0;
+    CUDA_TRY(cudaMemsetAsync(c->brick_ctl, 0, sizeof(int) * (8 + LGPU_MAX_PASSES), c->stream));
+    return LGPU_OK;
+}
+
 static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     int st;
+    st = lgpu_begin_passes(c);
+    if (st) return st;
     lgpu_mark(c, 1);
     st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
     if (st) return st;
@@ -376,7 +395,7 @@ static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     st = lgpu_launch_reorder(c, mode == 2);
     if (st) return st;
     lgpu_mark(c, 4);
-    st = lgpu_launch_build_table(c, mode == 2);
+    st = lgpu_launch_build_table(c, mode == 2, p, mode == 1 ? lgpu_fluid_lambda_mode(c, p) : LM_NONE);  // (fluid: + the first lambda pass)
     if (st) return st;
     st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);  // marks 6 / 7 per launch
     if (st) return st;
@@ -494,30 +513,6 @@ __global__ void k_dump_pstar(const float4* __restrict__ src, int n, float* __res
     dst[3 * i] = a.x; dst[3 * i + 1] = a.y; dst[3 * i + 2] = a.z;
 }
 
-// neighbour lists as the solver passes see them: decoded from the 16-bit table where the row is
-// valid, re-walked otherwise
-template <bool SAND>
-__global__ void __launch_bounds__(LGPU_TILE) k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
-    __shared__ BlkDesc d;
-    int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    if (threadIdx.x < (int)(sizeof(BlkDesc) / sizeof(int))) ((int*)&d)[threadIdx.x] = ((const int*)&v.blk[blockIdx.x])[threadIdx.x];
-    __syncthreads();
-    if (i >= v.n_owned) return;
-    long t = offsets[i];
-    const int word = v.nbr_cnt[i];
-    if (!(word & LGPU_CNT_WALK)) {
-        const int cnt = word & LGPU_CNT_MASK;
-        for (int k = 0; k < cnt; k++) {
-            uint2 w = v.nbr16[(size_t)(k >> 2) * v.cap + i];
-            uint32_t pair = (k & 2) ? w.y : w.x;
-            uint32_t code = (k & 1) ? pair >> 16 : pair & 0xffffu;
-            int j = decode_code(d, code);
-            flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j];
-        }
-    } else {
-        walk<SAND>(v, i, f3(v.x0[i]), [&](int j, int) { flat[t++] = j >= 0 ? j : v.n + v.solid_orig[~j]; });
-    }
-}
 __global__ void k_dump_cnt(const int* __restrict__ word, int n, int* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = word[i] & LGPU_CNT_MASK;
@@ -571,11 +566,7 @@ extern "C" int lgpu_dump(lgpu_ctx* c, int what, void* out, size_t out_bytes) {
             CUDA_TRY(cudaMalloc((void**)&d_off, sizeof(long) * (n + 1)));
             CUDA_TRY(cudaMalloc((void**)&d_flat, bytes));
             CUDA_TRY(cudaMemcpy(d_off, off.data(), sizeof(long) * (n + 1), cudaMemcpyHostToDevice));
-            View v = lgpu_make_view(c);
-            const int nblk = (int)((n + LGPU_TILE - 1) / LGPU_TILE);
-            if (c->last_mode == 2) k_dump_nbr<true><<<nblk, LGPU_TILE, 0, c->stream>>>(v, d_off, d_flat);
-            else k_dump_nbr<false><<<nblk, LGPU_TILE, 0, c->stream>>>(v, d_off, d_flat);
-            CUDA_TRY(cudaGetLastError());
+            { int st = lgpu_launch_dump_nbr(c, c->last_mode == 2, d_off, d_flat); if (st) return st; }
             CUDA_TRY(cudaMemcpyAsync(out, d_flat, bytes, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             cudaFree(d_off); cudaFree(d_flat);

@@ -11,35 +11,48 @@
 #define LGPU_LAMBDA_HEAD 4096  // lambdas[loop counter] table: first slots in reference order
 #define LGPU_BLOCK 128
 #define LGPU_MAX_MARKS 96
-#ifndef LGPU_BLOCKS_PER_SM
-#define LGPU_BLOCKS_PER_SM 3     // resident blocks per SM the hot staged kernels are compiled for (register cap)
-#endif
 
-// ---- staged neighbour table (lgpu_stage.cuh) ----
-#ifndef LGPU_TILE
-#define LGPU_TILE 384            // particles per thread block of the table / solver kernels
+// ---- brick-staged neighbour table (lgpu_brick.cuh) ----
+// The solver passes and the table build run over BRICKS of LGPU_BY x LGPU_BX cell columns x LGPU_BZ cells (z is the
+// fastest cell coordinate, so every column of a brick is ONE contiguous run of the cell-sorted storage).  A brick's
+// neighbourhood is the brick plus a one-cell shell: (BY+2)(BX+2) runs of BZ+2 cells, staged in shared memory with one
+// 1-D bulk copy (TMA) per run.  2.8 x the brick's own particles are staged (a 384-particle run of the sorted order
+// needed 9 x).
+#define LGPU_BY 4
+#define LGPU_BX 4
+#ifndef LGPU_BZ
+#define LGPU_BZ 8
+#endif
+#define LGPU_HX (LGPU_BX + 2)
+#define LGPU_HCOLS ((LGPU_BY + 2) * (LGPU_BX + 2))  // 36 halo columns
+#define LGPU_HB (LGPU_BZ + 3)                       // cell boundaries of a halo column (BZ + 2 cells)
+#define LGPU_OWN_COLS (LGPU_BY * LGPU_BX)           // 16
+#ifndef LGPU_NCW
+#define LGPU_NCW 15                                 // consumer warps of a block (+ 1 producer warp)
+#endif
+#define LGPU_BRICK_THREADS ((LGPU_NCW + 1) * 32)
+#ifndef LGPU_NSTAGE
+#define LGPU_NSTAGE 2                               // stage buffers of a block: the next brick is staged while this one is worked on
 #endif
 #ifndef LGPU_STAGE_SLOTS
-#define LGPU_STAGE_SLOTS 4608    // float4 slots of the shared-memory stage (72 KB, three blocks per SM); slot 0 = far-away dummy
+#define LGPU_STAGE_SLOTS 3072    // float4 slots of ONE stage buffer (48 KB; two buffers per block, two blocks per SM)
 #endif
-#define LGPU_VIRTUAL_SLOTS 32767 // a neighbourhood larger than the stage is addressed with the same codes (< 0x8000), read from L1/L2
-#define LGPU_SOLID_CODE 0x8000u  // table code of a solid neighbour: 0x8000 | run << 11 | offset in the run's window
+#define LGPU_DUMMY_SLOTS 8       // stage slots 0..7: far-away dummies (padding of sand rows)
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
 #define LGPU_CNT_GHOST (1 << 29)  // nbr_cnt flag: ghost particle of a neighbouring slab (not updated here)
 #define LGPU_CNT_MASK 0x0fffffff
+#define LGPU_MAX_PASSES 40        // work cursors of one substep (table build + 2 K solver passes)
 
-// Per thread block of LGPU_TILE consecutive sorted particles: the (merged) contiguous ranges of the
-// sorted storage that cover the 27-cell neighbourhoods of all its particles.  Cell ids are linear
-// (y-major, z fastest) and the storage is sorted by cell id, so for each of the 9 (dy,dx) stencil
-// columns the cells [key_first + off - 1, key_last + off + 1] are ONE contiguous particle range.
-struct BlkDesc {
-    int nr;            // number of copy ranges (<= 9)
-    int mode;          // 0 = staged in shared memory; 1 = virtual slots (too large for the stage: same codes,
-                       // at most 3 ranges, neighbours read through L1/L2); 2 = re-walk the stencil
-    int g0[9], len[9], s0[9];  // copy m: sorted slots [g0, g0+len) -> stage slots [s0, s0+len)
-    int slotbase[9];   // stage slot of sorted particle j reached through stencil column r = slotbase[r] + j
-    int sbase[9];      // first sorted solid slot of stencil column r's window
+// One non-empty brick of this substep (written by the table build's producer warps, read by every later pass).
+struct BrickDesc {
+    int brick;                                // brick id = (by * nbX + bx) * nbZ + bz
+    int mode;                                 // 0 = staged; 2 = neighbourhood larger than the stage: its particles re-walk the stencil
+    int n_own;                                // particles of the brick itself
+    int n_slots;                              // stage slots of the neighbourhood (dummies included)
+    int g0[LGPU_HCOLS], len[LGPU_HCOLS];      // halo column hc: sorted sand slots [g0, g0 + len)
+    int sg0[LGPU_HCOLS], slen[LGPU_HCOLS];    // ... sorted solid slots
+    int own_g0[LGPU_OWN_COLS], own_len[LGPU_OWN_COLS];  // the brick's own runs (inner columns, own cells)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -105,6 +118,12 @@ struct View {
     int n_solid;
     int cap;      // row stride of the neighbour table
     int M;        // neighbour table width
+    // bricks (lgpu_brick.cuh)
+    int nbY, nbX, nbZ, NB;    // brick grid
+    int stage_slots;          // stage capacity in use (<= LGPU_STAGE_SLOTS; test hook lgpu_set_stage_slots)
+    int* brick_work;          // [NB] non-empty bricks: full ones from the front, sparse ones from the back
+    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [8 + pass] work cursor of each pass
+    BrickDesc* brick_desc;    // [work index]
     // unsorted (pre-reorder) buffers, indexed by the storage slot of the previous step
     float4 *pos_in, *vel_in, *pstar_in;
     int *flags_in, *orig_in;
@@ -118,11 +137,10 @@ struct View {
     float4* solid_pos;
     int *solid_orig, *solid_cell_start;
     // neighbour table: 16-bit codes in list order, four per uint2, group-major: codes 4g..4g+3 of
-    // particle i at nbr16[g * cap + i].  code < 0x8000: stage slot of the block (0 = dummy);
-    // code >= 0x8000: solid, see LGPU_SOLID_CODE.
+    // particle i at nbr16[g * cap + i].  A code is the stage slot of the neighbour in the particle's brick
+    // (sand and solids alike; slots below LGPU_DUMMY_SLOTS are far-away dummies).
     uint2* nbr16;
     int* nbr_cnt;      // list length | LGPU_CNT_* flags
-    BlkDesc* blk;
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;  // [0] key violations, [1] table overflows
 };
@@ -135,7 +153,12 @@ struct lgpu_ctx {
     bool own_stream;
     int n, n_owned, n_solid, n_solid_uploaded, cap, cap_solid, M;
     int n_in, n_ghost;
-    int stage_slots;      // blocks whose neighbourhood needs more stage slots use virtual slots (<= LGPU_STAGE_SLOTS)
+    int stage_slots;      // bricks whose neighbourhood needs more stage slots re-walk the stencil (<= LGPU_STAGE_SLOTS)
+    int nbY, nbX, nbZ, NB;
+    int num_sms;
+    int pass;             // solver pass counter of the substep being enqueued (selects the work cursor)
+    int *brick_work, *brick_ctl;
+    BrickDesc* brick_desc;
     bool generic_kernels; // test hook: run the fast-arithmetic fluid step with the generic kernels (lgpu_set_generic_kernels)
     bool grid_valid;      // cell_start/key describe the current storage
     bool solids_sorted;
@@ -150,7 +173,6 @@ struct lgpu_ctx {
     int *solid_orig, *solid_cell_start;
     uint2* nbr16;
     int* nbr_cnt;
-    BlkDesc* blk;
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;
     float4* pstar_final;  // where the last step left x* (for dumps)
@@ -227,7 +249,9 @@ int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p);
 int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts);
 int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig);
 int lgpu_sort_solids(lgpu_ctx* c);
-int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order);
+int lgpu_begin_passes(lgpu_ctx* c);
+int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order, const lgpu_step_params& p, int lambda_mode);
+int lgpu_launch_dump_nbr(lgpu_ctx* c, bool sand, const long* d_off, int* d_flat);
 int lgpu_launch_fluid_solver(lgpu_ctx* c, const lgpu_step_params& p);
 int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p);
 

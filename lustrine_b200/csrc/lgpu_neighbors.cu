@@ -1,72 +1,38 @@
 // lgpu_neighbors.cu — builds the per-particle neighbour table once per substep.
 // Replaces the list construction of find_neighbors_uniform_grid (src/neighbors/Neighbors.cpp:386-448)
-// and find_neighbors_uniform_grid_v1 (:306-361).
+// and find_neighbors_uniform_grid_v1 (:306-361).  In the fluid step the same kernel goes on to the first
+// density + lambda pass (src/Simulate.cpp:58-88) on the neighbours it has just found: the predicted
+// positions are already staged, one stage fill and one kernel launch less per substep.
 #include <stdlib.h>
 
-#include "lgpu_neighbors.cuh"
+#include "lgpu_fluid.cuh"
 
 // ------------------------------------------------------------------------------------------
-// block descriptors: which contiguous ranges of the sorted storage a block of LGPU_TILE particles
-// needs staged (one thread per block; a few thousand threads in all)
+// work list: the non-empty bricks of this substep (one thread per brick)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks, int stage_slots) {
-    pdl_trigger();  // the table build may start its own loads (they do not depend on the descriptors)
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= num_blocks) return;
+// Full bricks are appended from the front of brick_work and sparse ones (surface, spray) from the back, so that
+// the persistent blocks take the heavy bricks first and the light ones even out the tail.
+__global__ void __launch_bounds__(128) k_brick_list(View v) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= v.NB) return;
     const Geom& g = v.g;
-    const int first = b * LGPU_TILE, last = min(v.n, first + LGPU_TILE) - 1;
-    const int kf = v.key[first], kl = v.key[last];
-    BlkDesc d;
-    int lo[9], hi[9];
+    const int by = b / (v.nbX * v.nbZ);
+    const int rem = b - by * (v.nbX * v.nbZ);
+    const int bx = rem / v.nbZ, bz = rem - bx * v.nbZ;
+    const int z0 = bz * LGPU_BZ, z1 = min(z0 + LGPU_BZ, g.gZ);
+    int n = 0;
 #pragma unroll
-    for (int r = 0; r < 9; r++) {
-        const int off = (r / 3 - 1) * g.gXZ + (r % 3 - 1) * g.gZ;
-        int clo = kf + off - 1, chi = kl + off + 1;
-        if (chi < 0 || clo > g.C - 1) { lo[r] = hi[r] = 0; d.sbase[r] = 0; continue; }
-        clo = max(clo, 0);
-        chi = min(chi, g.C - 1);
-        lo[r] = v.cell_start[clo];
-        hi[r] = v.cell_start[chi + 1];
-        d.sbase[r] = v.n_solid ? v.solid_cell_start[clo] : 0;
-    }
-    // merge overlapping / abutting ranges (they are already ascending in r) and hand out stage slots
-    int nr = 0, slots = 1;  // slot 0 = dummy
-    int cur_lo = 0, cur_hi = 0;
-    bool open = false;
-    int member_of[9];
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        member_of[r] = -1;
-        if (hi[r] <= lo[r]) continue;
-        if (open && lo[r] <= cur_hi) {
-            cur_hi = max(cur_hi, hi[r]);
-        } else {
-            if (open) { d.g0[nr] = cur_lo; d.len[nr] = cur_hi - cur_lo; d.s0[nr] = slots; slots += cur_hi - cur_lo; nr++; }
-            cur_lo = lo[r]; cur_hi = hi[r]; open = true;
+    for (int q = 0; q < LGPU_OWN_COLS; q++) {
+        const int cy = by * LGPU_BY + q / LGPU_BX, cx = bx * LGPU_BX + q % LGPU_BX;
+        if (cy < g.gY && cx < g.gX) {
+            const int base = cy * g.gXZ + cx * g.gZ;
+            n += v.cell_start[base + z1] - v.cell_start[base + z0];
         }
-        member_of[r] = nr;
     }
-    if (open) { d.g0[nr] = cur_lo; d.len[nr] = cur_hi - cur_lo; d.s0[nr] = slots; slots += cur_hi - cur_lo; nr++; }
-    d.mode = 0;
-    if (slots > stage_slots) {
-        // Too large for the stage (dense neighbour columns).  Virtual slots: one range per stencil
-        // row dy spanning its three columns, same 16-bit codes, neighbours read through L1/L2.
-        nr = 0; slots = 1;
-        for (int t = 0; t < 3; t++) {
-            int a = 0x7fffffff, e = 0;
-            for (int r = 3 * t; r < 3 * t + 3; r++) {
-                member_of[r] = -1;
-                if (hi[r] > lo[r]) { a = min(a, lo[r]); e = max(e, hi[r]); member_of[r] = nr; }
-            }
-            if (e > a) { d.g0[nr] = a; d.len[nr] = e - a; d.s0[nr] = slots; slots += e - a; nr++; }
-        }
-        d.mode = slots <= LGPU_VIRTUAL_SLOTS ? 1 : 2;
-    }
-    for (int m = nr; m < 9; m++) { d.g0[m] = 0; d.len[m] = 0; d.s0[m] = 0x7fffffff; }
-#pragma unroll
-    for (int r = 0; r < 9; r++) d.slotbase[r] = member_of[r] >= 0 ? d.s0[member_of[r]] - d.g0[member_of[r]] : 0;
-    d.nr = nr;
-    v.blk[b] = d;
+    if (n == 0) return;
+    // (warp-aggregated by the compiler; the order inside the two lists does not affect any result)
+    if (n >= 256) v.brick_work[atomicAdd(&v.brick_ctl[0], 1)] = b;
+    else v.brick_work[v.NB - 1 - atomicAdd(&v.brick_ctl[1], 1)] = b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -74,7 +40,7 @@ __global__ void __launch_bounds__(128) k_block_ranges(View v, int num_blocks, in
 // ------------------------------------------------------------------------------------------
 // Appends 16-bit codes to a table row.  Four consecutive codes share one 8-byte group and the groups
 // are strided by the capacity (nbr16 layout in lgpu_internal.cuh): the codes are packed in a 64-bit
-// shift register and every fourth emit stores one group — coalesced across the warp.
+// shift register and every fourth emit stores one group.
 struct RowWriter {
     uint2* col;       // next group of this particle's row
     size_t stride;    // capacity
@@ -111,175 +77,209 @@ struct RowWriter {
     }
 };
 
-// Out-of-line paths of the table build: tiles in virtual-slot mode (candidates read from the global
-// storage) and particles with solids in their 27 cells or a very dense column (the reference's nested
-// order over the global storage).
+// Out-of-line path of the table build: particles with solids in their neighbourhood or a very dense column walk the
+// stencil over the global storage in the reference's nested order (per cell: sand then solids in the fluid lists,
+// solids then sand in the sand lists) and translate what they find into stage slots of their brick.
 template <bool SAND>
-__device__ __noinline__ int2 build_row_virtual(const View& v, const BlkDesc& d, int i, F3 xi, int key, uint32_t pad) {
-    const Geom& g = v.g;
-    RowWriter w;
-    w.init(v, i);
-    const uint32_t self_code = (uint32_t)(d.slotbase[4] + i);
-    const CellCoord c = decode_cell(g, key);
-    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
-    for (int r = 0; r < 9; r++) {
-        const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
-        if (y < 0 || y >= g.gY || x < 0 || x >= g.gX) continue;
-        const int base = y * g.gXZ + x * g.gZ;
-        const int b = v.cell_start[base + zlo], e = v.cell_start[base + zhi + 1];
-        const uint32_t first = (uint32_t)(d.slotbase[r] + b);
-        for (int u = b; u < e; u++) {
-            if (!within_h(g, xi, f3(v.x0[u]))) continue;
-            const uint32_t code = first + (uint32_t)(u - b);
-            if (SAND && code == self_code) continue;
-            w.emit(code);
-        }
-    }
-    w.finish(pad);
-    return make_int2(w.cnt, w.bad ? 1 : 0);
-}
-template <bool SAND>
-__device__ __noinline__ int2 build_row_walk(const View& v, const BlkDesc& d, int i, F3 xi, uint32_t pad) {
+__device__ __noinline__ int2 build_row_walk(const View& v, const BrickInfo& info, int i, F3 xi, int ly, int lx, uint32_t pad) {
     RowWriter w;
     w.init(v, i);
     walk<SAND>(v, i, xi, [&](int j, int r) {
-        if (j >= 0) w.emit((uint32_t)(d.slotbase[r] + j));
-        else {
-            int off = ~j - d.sbase[r];
-            if (off >= LGPU_SOLID_WINDOW) { w.bad = true; off = 0; }
-            w.emit(LGPU_SOLID_CODE | ((uint32_t)r << 11) | (uint32_t)off);
-        }
+        const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;  // halo column of stencil column r = 3 (dy + 1) + (dx + 1)
+        if (j >= 0) w.emit((uint32_t)(info.col_s0[hc] + (j - info.col_g0[hc])));
+        else w.emit((uint32_t)(info.scol_s0[hc] + (~j - info.scol_g0[hc])));
     });
     w.finish(pad);
     return make_int2(w.cnt, w.bad ? 1 : 0);
 }
 
-template <bool SAND>
-__global__ void __launch_bounds__(LGPU_TILE, LGPU_BLOCKS_PER_SM) k_build_table(const __grid_constant__ View v) {
-    extern __shared__ float4 stage[];
-    __shared__ BlkDesc d;
-    __shared__ uint64_t bar;
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * LGPU_TILE + tid;
-    const int ic = i < v.n ? i : 0;
-    const Geom& g = v.g;
-    // the thread's own loads first (position, key, the cell offsets of its nine stencil columns):
-    // they overlap the descriptor load and the bulk copies
-    const float4 x0i = v.x0[ic];
-    const int key = v.key[ic];
-    const int flags = g.slab ? v.flags[ic] : 0;
-    pdl_wait();  // launched as a programmatic dependent of k_block_ranges: the descriptors are needed from here on
-    stage_begin(v, v.x0, d, &bar, stage);
-    // per stencil column: the candidates are the sorted slots [cb, ce) — the three cells z-1..z+1
-    // of a column are contiguous in the sorted storage
-    const CellCoord c = decode_cell(g, key);
-    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, g.gZ - 1);
-    int cb[9], ce[9];
-    bool slow = false;  // solids in the 27 cells, or a column with more than 32 candidates
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-        const int y = c.y + r / 3 - 1, x = c.x + r % 3 - 1;
-        cb[r] = ce[r] = 0;
-        if (y >= 0 && y < g.gY && x >= 0 && x < g.gX) {
-            const int base = y * g.gXZ + x * g.gZ;
-            cb[r] = v.cell_start[base + zlo]; ce[r] = v.cell_start[base + zhi + 1];
-            if (ce[r] - cb[r] > 32) slow = true;
-            if (v.n_solid && v.solid_cell_start[base + zhi + 1] > v.solid_cell_start[base + zlo]) slow = true;
-        }
-    }
-    stage_wait(&bar);  // every thread waits: no bulk copy may outlive the block
-    if (i >= v.n) return;
-    if (flags & LGPU_FLAG_GHOST) {  // ghost of a neighbouring slab: read by others, never updated here
-        v.nbr_cnt[i] = LGPU_CNT_GHOST;
-        return;
-    }
-    const F3 xi = f3(x0i);
-    if (d.mode == 2) {
-        // neighbourhood beyond the 16-bit code space: count only, the solver passes re-walk the stencil
-        int cnt = 0;
-        walk<SAND>(v, i, xi, [&](int, int) { cnt++; });
-        v.nbr_cnt[i] = cnt | LGPU_CNT_WALK;
-        atomicAdd(&v.counters[1], 1ULL);
-        return;
-    }
-    const uint32_t self_code = (uint32_t)(d.slotbase[4] + i);
-    // padding: sand = the far-away dummy (no contact); fluid = the particle itself (zero separation:
-    // every term of the branch-free fluid bodies vanishes)
-    const uint32_t pad = SAND ? 0u : self_code;
-    int cnt;
-    bool bad;
-    if (slow) {
-        const int2 r = build_row_walk<SAND>(v, d, i, xi, pad);
-        cnt = r.x; bad = r.y != 0;
-    } else if (d.mode != 0) {
-        const int2 r = build_row_virtual<SAND>(v, d, i, xi, key, pad);
-        cnt = r.x; bad = r.y != 0;
-    } else {
-        RowWriter w;
-        w.init(v, i);
-        // No solid in the 27 cells: the reference order is simply ascending sorted slot over the 9
-        // columns (fluid: self included; sand: self skipped — SURVEY F7).  Per column: test the
-        // candidates with the Exact predicate into a hit mask, then emit the hits.
+template <bool SAND, int LM>
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, int* cursor) {
+    extern __shared__ unsigned char smem_raw[];
+    brick_loop<true>(v, v.x0, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int q, int i, int slot) {
+        const Geom& g = v.g;
         const uint32_t stage_addr = smem_u32(stage);
+        const float4 x0i = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : v.x0[i];
+        const F3 xi = f3(x0i);
+        int word;
+        const int flags = g.slab ? v.flags[i] : 0;
+        if (flags & LGPU_FLAG_GHOST) {  // ghost of a neighbouring slab: read by others, never updated here
+            word = LGPU_CNT_GHOST;
+        } else if (info.mode != 0) {
+            // neighbourhood larger than the stage: count only, the solver passes re-walk the stencil
+            int cnt = 0;
+            walk<SAND>(v, i, f3(v.x0[i]), [&](int, int) { cnt++; });
+            word = cnt | LGPU_CNT_WALK;
+            atomicAdd(&v.counters[1], 1ULL);
+        } else {
+            const int ly = q / LGPU_BX, lx = q % LGPU_BX;
+            const int hown = (ly + 1) * LGPU_HX + lx + 1;
+            // the particle's cell along its own run: boundary index tz with cs[hown][tz] <= slot < cs[hown][tz + 1]
+            int tz = 1;
 #pragma unroll
-        for (int r = 0; r < 9; r++) {
-            const int n = ce[r] - cb[r];
-            if (n == 0) continue;
-            const uint32_t first = (uint32_t)(d.slotbase[r] + cb[r]);
-            // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at
-            // bit n-1-t.  The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has
-            // the exact sign and is +0 on equality), so a test costs the 8 separately rounded
-            // operations of the reference's predicate plus one FADD and one funnel shift.
-            uint32_t out = 0;
-            const uint32_t a = slot_addr(stage_addr, first);
+            for (int t = 2; t <= LGPU_BZ; t++) tz += slot >= info.cs[hown][t] ? 1 : 0;
+            // per stencil column: the candidates are the stage slots [cb, ce) — the three cells z-1..z+1 of a column are
+            // contiguous in the sorted storage and therefore in the stage
+            int cb[9], ce[9];
+            bool slow = false;  // solids in the neighbouring columns, or a column with more than 32 candidates
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;
+                cb[r] = info.cs[hc][tz - 1]; ce[r] = info.cs[hc][tz + 2];
+                if (ce[r] - cb[r] > 32) slow = true;
+            }
+            if (v.n_solid) {
+                // (one compare per column: the solid range of a halo column spans the brick's z extent)
+#pragma unroll
+                for (int r = 0; r < 9; r++) {
+                    const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;
+                    if (info.scol_len[hc] > 0) slow = true;
+                }
+            }
+            const uint32_t self_code = (uint32_t)slot;
+            // padding: sand = a far-away dummy (no contact); fluid = the particle itself (zero separation: every term of
+            // the branch-free fluid bodies vanishes)
+            const uint32_t pad = SAND ? 0u : self_code;
+            int cnt;
+            bool bad;
+            if (slow) {
+                const int2 r = build_row_walk<SAND>(v, info, i, xi, ly, lx, pad);
+                cnt = r.x; bad = r.y != 0;
+            } else {
+                RowWriter w;
+                w.init(v, i);
+                // No solid near: the reference order is simply ascending sorted slot over the 9 columns (fluid: self
+                // included; sand: self skipped — SURVEY F7).  Per column: test the candidates with the Exact predicate
+                // into a hit mask, then emit the hits.
+#pragma unroll
+                for (int r = 0; r < 9; r++) {
+                    const int n = ce[r] - cb[r];
+                    if (n == 0) continue;
+                    const uint32_t first = (uint32_t)cb[r];
+                    // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at bit n-1-t.
+                    // The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has the exact sign and is
+                    // +0 on equality), so a test costs the 8 separately rounded operations of the reference's
+                    // predicate (src/neighbors/Neighbors.cpp:433-435) plus one FADD and one funnel shift.
+                    uint32_t out = 0;
+                    const uint32_t a = slot_addr(stage_addr, first);
 #pragma unroll 4
-            for (int t = 0; t < n; t++) {
-                const float4 pj = lds128(a + 16u * (uint32_t)t);
-                const F3 dd = vsub<Exact>(xi, f3(pj));
-                out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
+                    for (int t = 0; t < n; t++) {
+                        const float4 pj = lds128(a + 16u * (uint32_t)t);
+                        const F3 dd = vsub<Exact>(xi, f3(pj));
+                        out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
+                    }
+                    uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
+                    const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
+                    if (SAND && r == 4) m &= ~(1u << (top - self_code));
+                    const int hits = __popc(m);
+                    if (w.cnt + hits > w.M) { w.cnt += hits; w.bad = true; continue; }  // row too long: the solver passes re-walk
+                    while (m) {  // ascending candidate = descending bit
+                        const uint32_t k = 31u - (uint32_t)__clz(m);
+                        m ^= 1u << k;
+                        w.emit_unchecked(top - k);
+                    }
+                }
+                w.finish(pad);
+                cnt = w.cnt; bad = w.bad;
             }
-            uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
-            const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
-            if (SAND && r == 4) m &= ~(1u << (top - self_code));
-            const int hits = __popc(m);
-            if (w.cnt + hits > w.M) { w.cnt += hits; w.bad = true; continue; }  // row too long: the solver passes re-walk
-            while (m) {  // ascending candidate = descending bit
-                const uint32_t k = 31u - (uint32_t)__clz(m);
-                m ^= 1u << k;
-                w.emit_unchecked(top - k);
-            }
+            word = cnt;
+            if (cnt > v.M || bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
         }
-        w.finish(pad);
-        cnt = w.cnt; bad = w.bad;
-    }
-    int word = cnt;
-    if (cnt > v.M || bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
-    v.nbr_cnt[i] = word;
+        v.nbr_cnt[i] = word;
+        if (!SAND && LM != LM_NONE) {
+            // first density + lambda pass on the list just written (the thread re-reads its own row)
+            if (!(word & LGPU_CNT_GHOST)) fluid_lambda_particle<LM>(v, fp, info, stage, v.x0, i, word, xi);
+        }
+    });
 }
 
-int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order) {
+static int brick_grid(const lgpu_ctx* c) { return 2 * c->num_sms; }
+
+template <bool SAND, int LM>
+static int launch_build(lgpu_ctx* c, const View& v, const FluidParams& fp, bool pdl) {
+    CUDA_TRY(launch_pdl(k_build_table<SAND, LM>, brick_grid(c), LGPU_BRICK_THREADS, LGPU_BRICK_SMEM, c->stream, pdl, v, fp, c->brick_ctl + 8 + c->pass));
+    return LGPU_OK;
+}
+
+// lambda_mode: LM_* for the fluid step (the build kernel also runs the first density + lambda pass), LM_NONE otherwise
+int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order, const lgpu_step_params& p, int lambda_mode) {
     if (c->n == 0) return LGPU_OK;  // (slab mode: the solver drivers still run the refresh protocol)
     View v = lgpu_make_view(c);
-    const int nb = (c->n + LGPU_TILE - 1) / LGPU_TILE;
-    const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
-    k_block_ranges<<<(nb + 127) / 128, 128, 0, c->stream>>>(v, nb, c->stage_slots);
+    FluidParams fp = lgpu_make_fluid_params(c->g, p);
+    k_brick_list<<<(c->NB + 127) / 128, 128, 0, c->stream>>>(v);
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
     const bool pdl = pdl_env && !c->phase_timing && !c->use_graph;
-    if (sand_order) CUDA_TRY(launch_pdl(k_build_table<true>, nb, LGPU_TILE, smem, c->stream, pdl, v));
-    else CUDA_TRY(launch_pdl(k_build_table<false>, nb, LGPU_TILE, smem, c->stream, pdl, v));
+    int st;
+    if (sand_order) st = launch_build<true, LM_NONE>(c, v, fp, pdl);
+    else switch (lambda_mode) {
+        case LM_FAST: st = launch_build<false, LM_FAST>(c, v, fp, pdl); break;
+        case LM_EXACT: st = launch_build<false, LM_EXACT>(c, v, fp, pdl); break;
+        case LM_POLY6: st = launch_build<false, LM_POLY6>(c, v, fp, pdl); break;
+        case LM_GENERIC: st = launch_build<false, LM_GENERIC>(c, v, fp, pdl); break;
+        default: st = launch_build<false, LM_NONE>(c, v, fp, pdl); break;
+    }
+    if (st) return st;
+    c->pass++;
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
 }
 
+// Neighbour lists as the solver passes see them (tests, lgpu_dump): one block per brick of the work list; codes are
+// translated back to sorted slots through the brick's descriptor, rows the table does not hold are re-walked.
+template <bool SAND>
+__global__ void __launch_bounds__(128) k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
+    __shared__ BrickInfo info;
+    const int n_full = v.brick_ctl[0], n_work = n_full + v.brick_ctl[1];
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        __syncthreads();
+        const BrickDesc& d = v.brick_desc[w];
+        if (threadIdx.x == 0) {
+            int s = LGPU_DUMMY_SLOTS;
+            for (int hc = 0; hc < LGPU_HCOLS; hc++) { info.col_g0[hc] = d.g0[hc]; info.col_s0[hc] = s; info.col_len[hc] = d.len[hc]; s += d.len[hc]; }
+            for (int hc = 0; hc < LGPU_HCOLS; hc++) { info.scol_g0[hc] = d.sg0[hc]; info.scol_s0[hc] = s; info.scol_len[hc] = d.slen[hc]; s += d.slen[hc]; }
+        }
+        __syncthreads();
+        for (int q = 0; q < LGPU_OWN_COLS; q++) {
+            for (int t = threadIdx.x; t < d.own_len[q]; t += blockDim.x) {
+                const int i = d.own_g0[q] + t;
+                if (v.g.slab ? (v.flags[i] & LGPU_FLAG_GHOST) != 0 : false) continue;
+                long o = offsets[i];
+                const int word = v.nbr_cnt[i];
+                if (!(word & LGPU_CNT_WALK)) {
+                    const int cnt = word & LGPU_CNT_MASK;
+                    for (int k = 0; k < cnt; k++) {
+                        const uint2 g4 = v.nbr16[(size_t)(k >> 2) * v.cap + i];
+                        const uint32_t pair = (k & 2) ? g4.y : g4.x;
+                        const int code = (int)((k & 1) ? pair >> 16 : pair & 0xffffu);
+                        const int j = decode_code(info, code);
+                        flat[o++] = j >= 0 ? j : v.n + v.solid_orig[~j];
+                    }
+                } else {
+                    walk<SAND>(v, i, f3(v.x0[i]), [&](int j, int) { flat[o++] = j >= 0 ? j : v.n + v.solid_orig[~j]; });
+                }
+            }
+        }
+    }
+}
+int lgpu_launch_dump_nbr(lgpu_ctx* c, bool sand, const long* d_off, int* d_flat) {
+    View v = lgpu_make_view(c);
+    if (sand) k_dump_nbr<true><<<2 * c->num_sms, 128, 0, c->stream>>>(v, d_off, d_flat);
+    else k_dump_nbr<false><<<2 * c->num_sms, 128, 0, c->stream>>>(v, d_off, d_flat);
+    CUDA_TRY(cudaGetLastError());
+    return LGPU_OK;
+}
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
+template <bool SAND, int LM> static int preload_build() {
+    CUDA_TRY(cudaFuncSetAttribute(k_build_table<SAND, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LGPU_BRICK_SMEM));
+    return LGPU_OK;
+}
 // Loads every kernel of this file on the CURRENT device and opts the staged ones into their dynamic
 // shared memory.  cudaFuncSetAttribute is per device: lgpu_create calls this for every context.
 int lgpu_preload_neighbors() {
-    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
-    CUDA_TRY(cudaFuncSetAttribute(k_build_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_build_table<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGPU_PRELOAD(k_block_ranges); LGPU_PRELOAD(k_build_table<true>); LGPU_PRELOAD(k_build_table<false>);
-    return LGPU_OK;
+    int st = preload_build<true, LM_NONE>() | preload_build<false, LM_NONE>() | preload_build<false, LM_FAST>() |
+             preload_build<false, LM_EXACT>() | preload_build<false, LM_POLY6>() | preload_build<false, LM_GENERIC>();
+    LGPU_PRELOAD(k_brick_list); LGPU_PRELOAD(k_dump_nbr<true>); LGPU_PRELOAD(k_dump_nbr<false>);
+    return st ? LGPU_ERR_CUDA : LGPU_OK;
 }

@@ -91,62 +91,58 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
     }
 }
 
-template <class P, bool SOLIDS, bool LAST>
-__global__ void __launch_bounds__(LGPU_TILE) k_sand_iteration(View v, SandParams sp, const float4* __restrict__ cur, float4* __restrict__ next) {
-    extern __shared__ float4 stage[];
-    __shared__ BlkDesc d;
-    __shared__ uint64_t bar;
-    const int i = blockIdx.x * LGPU_TILE + threadIdx.x;
-    pdl_trigger();
-    const int word = i < v.n ? v.nbr_cnt[i] : -1;
-    pdl_wait();  // the list length is independent of the previous pass; x* is not
-    stage_begin(v, cur, d, &bar, stage);
-    if (word == -1 || (word & (LGPU_CNT_GHOST | LGPU_CNT_WALK))) stage_wait(&bar);  // (the table path waits after its row loads)
-    if (word == -1) {
-    } else if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
-        if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
-    } else {
-    const float4 ci = cur[i];
-    const Geom& g = v.g;
-    const F3 pi = f3(ci);
-    const F3 xi_old = f3(v.pos[i]);
-    F3 deltap = f3(0.0f, 0.0f, 0.0f);
-    bool touched = false;
-    if (!(word & LGPU_CNT_WALK)) {
-        // Looped replay (one group of four per iteration, the next group's codes loaded one ahead): the
-        // contact body is long, and unrolling it over the whole row made the kernel ~300 KB of code that
-        // missed the instruction cache a quarter of the time.  The old position of a sand neighbour in
-        // contact is read from the sorted storage at the slot its staged x* carries in the w lane.
-        stage_wait(&bar);
-        replay_table<SOLIDS, true>(v, d, smem_u32(stage), cur, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
-            const bool is_sand = !(SOLIDS && (code & LGPU_SOLID_CODE));
-            sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
-        });
-    } else {
-        walk<true>(v, i, f3(v.x0[i]), [&](int j, int) {
-            const bool is_sand = j >= 0;
-            sand_pair<P>(sp, pi, xi_old, is_sand ? f3(cur[j]) : f3(v.solid_pos[~j]), is_sand, [&]() { return f3(v.pos[j]); }, deltap, touched);
-        });
-    }
-    F3 ps = P::exact ? vadd<Exact>(pi, deltap) : f3(pi.x + deltap.x, pi.y + deltap.y, pi.z + deltap.z);  // :288
-    const float r = g.radius;
-    ps.x = fminf(fmaxf(ps.x, r), __fsub_rn(g.domainX, r));  // :307
-    ps.y = fminf(fmaxf(ps.y, r), __fsub_rn(g.domainY, r));
-    ps.z = fminf(fmaxf(ps.z, r), __fsub_rn(g.domainZ, r));
-    next[i] = f4(ps, __int_as_float(i));  // w = own sorted slot (see the replay above)
-    if (sp.credits && touched) {  // :463-470: the "no gravity" bit drops at the first contact
-        int a = v.flags[i];
-        if (a & 2) v.flags[i] = a & ~2;
-    }
-    if (LAST) {  // :316-319, always Exact
-        // Written to the step-boundary storage (the pre-reorder buffers, free since k_reorder):
-        // other threads still read the OLD sorted positions v.pos[j] in this launch.
-        v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(ps, xi_old), sp.dt));
-        v.pos_in[i] = f4(ps);
-        v.flags_in[i] = v.flags[i];
-        v.orig_in[i] = v.orig[i];
-    }
-    }
+template <class P, bool LAST>
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_sand_iteration(const __grid_constant__ View v, const __grid_constant__ SandParams sp,
+                                                                          const float4* cur, float4* next, int* cursor) {
+    extern __shared__ unsigned char smem_raw[];
+    brick_loop<false>(v, cur, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int, int i, int slot) {
+        const int word = v.nbr_cnt[i];
+        if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+            if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
+            return;
+        }
+        const Geom& g = v.g;
+        const uint32_t stage_addr = smem_u32(stage);
+        const float4 ci = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
+        const F3 pi = f3(ci);
+        const F3 xi_old = f3(v.pos[i]);
+        F3 deltap = f3(0.0f, 0.0f, 0.0f);
+        bool touched = false;
+        if (!(word & LGPU_CNT_WALK) && info.mode == 0) {
+            // Looped replay (one group of four per iteration, the next group's codes loaded one ahead): the
+            // contact body is long, and unrolling it over the whole row made the kernel ~300 KB of code that
+            // missed the instruction cache a quarter of the time.  The old position of a sand neighbour in
+            // contact is read from the sorted storage at the slot its staged x* carries in the w lane.
+            const uint32_t solid_base = (uint32_t)info.solid_base;
+            replay_table<true>(v, stage_addr, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+                const bool is_sand = code < solid_base;
+                sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
+            });
+        } else {
+            walk<true>(v, i, f3(v.x0[i]), [&](int j, int) {
+                const bool is_sand = j >= 0;
+                sand_pair<P>(sp, pi, xi_old, is_sand ? f3(cur[j]) : f3(v.solid_pos[~j]), is_sand, [&]() { return f3(v.pos[j]); }, deltap, touched);
+            });
+        }
+        F3 ps = P::exact ? vadd<Exact>(pi, deltap) : f3(pi.x + deltap.x, pi.y + deltap.y, pi.z + deltap.z);  // :288
+        const float r = g.radius;
+        ps.x = fminf(fmaxf(ps.x, r), __fsub_rn(g.domainX, r));  // :307
+        ps.y = fminf(fmaxf(ps.y, r), __fsub_rn(g.domainY, r));
+        ps.z = fminf(fmaxf(ps.z, r), __fsub_rn(g.domainZ, r));
+        next[i] = f4(ps, __int_as_float(i));  // w = own sorted slot (see the replay above)
+        if (sp.credits && touched) {  // :463-470: the "no gravity" bit drops at the first contact
+            int a = v.flags[i];
+            if (a & 2) v.flags[i] = a & ~2;
+        }
+        if (LAST) {  // :316-319, always Exact
+            // Written to the step-boundary storage (the pre-reorder buffers, free since k_reorder):
+            // other threads still read the OLD sorted positions v.pos[j] in this launch.
+            v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(ps, xi_old), sp.dt));
+            v.pos_in[i] = f4(ps);
+            v.flags_in[i] = v.flags[i];
+            v.orig_in[i] = v.orig[i];
+        }
+    });
 }
 
 // largest fp32 x with sqrt_rn(x) <= d  (so that `sqrt(d2) > d` <=> `d2 > x`, bit-exactly)
@@ -167,31 +163,27 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     sp.d2_contact_max = contact_threshold(c->g.diameter);
     sp.cc_half = p.collision_coeff * p.mass / (p.mass + p.mass);  // src/Simulate.cpp:246, left to right
     sp.credits = p.credits;
-    const int K = p.iterations < 1 ? 1 : p.iterations;
-    const int blocks = (c->n + LGPU_TILE - 1) / LGPU_TILE > 0 ? (c->n + LGPU_TILE - 1) / LGPU_TILE : 1;
-    const size_t smem = sizeof(float4) * LGPU_STAGE_SLOTS;
-    const bool solids = c->n_solid > 0;
+    int K = p.iterations < 1 ? 1 : p.iterations;
+    if (1 + K > LGPU_MAX_PASSES) K = LGPU_MAX_PASSES - 1;
+    const int grid = 2 * c->num_sms;
+    const size_t smem = LGPU_BRICK_SMEM;
     const float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);  // see run_fluid_fast
+    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);  // see run_fluid
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
+        int* cursor = c->brick_ctl + 8 + c->pass;
         lgpu_mark(c, 7);
-#define LGPU_SAND_LAUNCH(PP, SS, LL)                                                                                    \
-    do {                                                                                                                \
-        CUDA_TRY(launch_pdl(k_sand_iteration<PP, SS, LL>, blocks, LGPU_TILE, smem, c->stream, pdl && it > 0, v, sp, cur, next)); \
-    } while (0)
         if (p.exact_math) {
-            if (solids) { if (last) LGPU_SAND_LAUNCH(Exact, true, true); else LGPU_SAND_LAUNCH(Exact, true, false); }
-            else { if (last) LGPU_SAND_LAUNCH(Exact, false, true); else LGPU_SAND_LAUNCH(Exact, false, false); }
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Exact, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Exact, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
         } else {
-            if (solids) { if (last) LGPU_SAND_LAUNCH(Fast, true, true); else LGPU_SAND_LAUNCH(Fast, true, false); }
-            else { if (last) LGPU_SAND_LAUNCH(Fast, false, true); else LGPU_SAND_LAUNCH(Fast, false, false); }
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Fast, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Fast, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
         }
-#undef LGPU_SAND_LAUNCH
-        c->launches++;
+        c->pass++; c->launches++;
         if (!last && lgpu_slab_active(c)) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;
     }
@@ -202,17 +194,13 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
 
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
-template <class P, bool SOLIDS> static int preload_sand_variant() {
-    const int smem = (int)(sizeof(float4) * LGPU_STAGE_SLOTS);
-    CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<P, SOLIDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_sand_iteration<P, SOLIDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, true>));
-    LGPU_PRELOAD((k_sand_iteration<P, SOLIDS, false>));
+template <class P> static int preload_sand_variant() {
+    const int smem = (int)LGPU_BRICK_SMEM;
+    CUDA_TRY(cudaFuncSetAttribute((k_sand_iteration<P, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute((k_sand_iteration<P, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return LGPU_OK;
 }
 int lgpu_preload_sand() {
-    int st = 0;
-    st |= preload_sand_variant<Exact, true>(); st |= preload_sand_variant<Exact, false>();
-    st |= preload_sand_variant<Fast, true>(); st |= preload_sand_variant<Fast, false>();
+    int st = preload_sand_variant<Exact>() | preload_sand_variant<Fast>();
     return st ? LGPU_ERR_CUDA : LGPU_OK;
 }

@@ -17,7 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "lgpu_neighbors.cuh"
+#include "lgpu_fluid.cuh"
 
 struct SlabState {
     int halo_cap;
@@ -342,6 +342,7 @@ int lgpu_slab_begin(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
         return LGPU_ERR_ARG;
     }
     S->n_store = c->n_in = c->n;  // the step-boundary storage: last step's sorted slots (ghost slots are dead)
+    { int st0 = lgpu_begin_passes(c); if (st0) return st0; }
     CUDA_TRY(cudaMemsetAsync(S->out_cnt, 0, sizeof(int) * 8, c->stream));
     lgpu_mark(c, 1);
     int st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
@@ -419,7 +420,7 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
         }
     }
     lgpu_mark(c, 4);
-    st = lgpu_launch_build_table(c, mode == 2);
+    st = lgpu_launch_build_table(c, mode == 2, p, mode == 1 ? lgpu_fluid_lambda_mode(c, p) : LM_NONE);
     if (st) return st;
     st = mode == 1 ? lgpu_launch_fluid_solver(c, p) : lgpu_launch_sand_solver(c, p);
     if (st) return st;

@@ -407,7 +407,7 @@ def test_aabb_first_k_matches_the_reference_scan(mode):
                 G.step_fluid(dt=0.01, iterations=1, literal_lambda_index=1, exact_math=1)
         pos, _, _ = G.download()  # the reference's storage order
         center = pos.mean(axis=0) + np.float32(0.3)
-        scale = np.array([2.0, 3.0, 2.0], np.float32) + np.float32(0.5 * 4.0)  # player_box_scale + 4 r (:604)
+        scale = np.array([4.0, 5.0, 4.0], np.float32) + np.float32(0.5 * 4.0)  # player_box_scale + 4 r (:604)
         half = scale * np.float32(0.5)
         hits = len(aabb_first_k_numpy(pos, center, half, 10 ** 9))
         assert hits > 100, "the scene must have more candidates than proxy boxes"
