@@ -111,8 +111,9 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     c->cap_solid = cfg->capacity_solid;
     c->M = cfg->max_neighbors > 0 ? cfg->max_neighbors : LGPU_DEFAULT_MAX_NEIGHBORS;
     c->M = (c->M + 3) & ~3;
+    if (c->M > 4 * LGPU_MG) c->M = 4 * LGPU_MG;  // a row is at most LGPU_MG groups of four codes; longer lists re-walk the stencil
     c->stage_slots = LGPU_STAGE_SLOTS;
-    // brick grid of the staged kernels (lgpu_neighbors.cuh); persistent kernels launch two blocks per SM
+    // brick grid of the staged kernels (lgpu_neighbors.cuh); persistent kernels launch one block per SM
     c->nbY = (c->g.gY + LGPU_BY - 1) / LGPU_BY; c->nbX = (c->g.gX + LGPU_BX - 1) / LGPU_BX; c->nbZ = (c->g.gZ + LGPU_BZ - 1) / LGPU_BZ;
     c->NB = c->nbY * c->nbX * c->nbZ;
     CUDA_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -139,10 +140,13 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     CUDA_TRY(dalloc(&c->scan_state, (C1 > cap + 4 ? C1 : cap + 4) / 4096 + 4));
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
-    CUDA_TRY(dalloc(&c->nbr16, cap * (size_t)(c->M / 4))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
+    // table blocks: a meta word and LGPU_MG code words per own particle, rows padded to an even count per brick
+    const size_t nonempty = (size_t)(c->NB < c->cap ? c->NB : c->cap);
+    CUDA_TRY(dalloc(&c->nbr16, (cap + nonempty + 2) * (size_t)(1 + LGPU_MG))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
     // a non-empty brick holds at least one particle, and there are at most NB bricks
-    CUDA_TRY(dalloc(&c->brick_work, (size_t)c->NB)); CUDA_TRY(dalloc(&c->brick_ctl, (size_t)(8 + LGPU_MAX_PASSES)));
-    CUDA_TRY(dalloc(&c->brick_desc, (size_t)(c->NB < c->cap ? c->NB : c->cap) + 1));
+    CUDA_TRY(dalloc(&c->brick_ctl, (size_t)(8 + LGPU_MAX_PASSES)));
+    c->rec_cap = (int)nonempty + 1;
+    CUDA_TRY(dalloc(&c->brick_rec, (size_t)c->rec_cap));
     CUDA_TRY(cudaMemsetAsync(c->brick_ctl, 0, sizeof(int) * (8 + LGPU_MAX_PASSES), c->stream));
     CUDA_TRY(dalloc(&c->lambda, cap)); CUDA_TRY(dalloc(&c->density, cap));
     CUDA_TRY(dalloc(&c->lambda_head, (size_t)LGPU_LAMBDA_HEAD));
@@ -174,7 +178,7 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_state);
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
-    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->brick_work); cudaFree(c->brick_ctl); cudaFree(c->brick_desc); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
+    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->brick_ctl); cudaFree(c->brick_rec); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
     lgpu_slab_free(c);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -199,7 +203,7 @@ View lgpu_make_view(lgpu_ctx* c) {
     v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
     v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt;
     v.nbY = c->nbY; v.nbX = c->nbX; v.nbZ = c->nbZ; v.NB = c->NB; v.stage_slots = c->stage_slots;
-    v.brick_work = c->brick_work; v.brick_ctl = c->brick_ctl; v.brick_desc = c->brick_desc;
+    v.brick_ctl = c->brick_ctl; v.brick_rec = c->brick_rec; v.rec_cap = c->rec_cap;
     v.lambda = c->lambda; v.density = c->density; v.lambda_head = c->lambda_head;
     v.counters = c->counters;
     return v;
@@ -375,7 +379,7 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
 extern "C" int lgpu_slab_step_begin(lgpu_ctx* c, const lgpu_step_params* p, int mode);
 extern "C" int lgpu_slab_step_end(lgpu_ctx* c);
 int lgpu_begin_passes(lgpu_ctx* c) {
-    // work-list counters and the work cursors of this substep's staged kernels
+    // work-list counters and the table allocator of this substep
     c->pass = 0;
     CUDA_TRY(cudaMemsetAsync(c->brick_ctl, 0, sizeof(int) * (8 + LGPU_MAX_PASSES), c->stream));
     return LGPU_OK;

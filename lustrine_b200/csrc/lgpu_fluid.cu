@@ -40,14 +40,14 @@ __device__ __forceinline__ void deltap_pair(const Geom& g, const FluidParams& fp
 
 // ---- density + lambda, iterations after the first ----
 template <int LM>
-__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_fluid_lambda(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
-                                                                        float4* cur, int* cursor) {
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_lambda(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
+                                                                        float4* cur) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int, int i, int slot) {
-        const int word = v.nbr_cnt[i];
-        if (word & LGPU_CNT_GHOST) return;
-        const float4 ci = info.mode == 0 ? lds128(slot_addr(smem_u32(stage), (uint32_t)slot)) : cur[i];
-        fluid_lambda_particle<LM>(v, fp, info, stage, cur, i, word, f3(ci));
+    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+        if (ck.word & LGPU_CNT_GHOST) return 0;
+        const float4 ci = ck.d->mode == 0 ? lds128(slot_addr(ck.stage_addr, (uint32_t)ck.slot)) : cur[ck.i];
+        fluid_lambda_particle<LM>(v, fp, ck, cur, ck.word, f3(ci));
+        return 0;
     });
 }
 
@@ -72,33 +72,34 @@ __device__ __noinline__ float3 deltap_walk(const View& v, const FluidParams& fp,
 // The staged neighbourhood holds (x*_j, lambda_j) per slot (the lambda pass stored lambda in the w lane; the w lane
 // of a solid is 0, which is the lambda the reference reads for it).
 template <int LM, bool LAST>
-__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_fluid_deltap(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
-                                                                        const float4* cur, float4* next, int* cursor) {
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_deltap(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
+                                                                        const float4* cur, float4* next) {
     typedef typename LambdaPolicy<LM>::P P;
     constexpr bool POLY6 = LambdaPolicy<LM>::poly6;
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int, int i, int slot) {
-        const int word = v.nbr_cnt[i];
+    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+        const int i = ck.i, word = ck.word, slot = ck.slot;
+        const int mode = ck.d->mode;
         if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
             if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
-            return;
+            return 0;
         }
         const Geom& g = v.g;
-        const uint32_t stage_addr = smem_u32(stage);
+        const uint32_t stage_addr = ck.stage_addr;
         const int cnt = word & LGPU_CNT_MASK;
-        const bool table = !(word & LGPU_CNT_WALK) && info.mode == 0;
+        const bool table = !(word & LGPU_CNT_WALK) && mode == 0;
+        float4 xo4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        int fl = 0, og = 0;
+        if (LAST) { xo4 = v.pos[i]; fl = v.flags[i]; og = v.orig[i]; }  // (issued before the gather: the latency hides behind it)
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         F3 xi;
         if (LM == LM_FAST) {
-            TableRow<8> row;
-            row.load_early<5>(v, i);
-            row.load_rest<5>(v, i, table ? cnt : 0);
-            const float4 ci = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
+            const float4 ci = mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
             xi = f3(ci);
             const float li = ci.w;
             if (table) {
                 uint32_t far = 0;
-                replay_row<true, 8>(row, stage_addr, cnt, [&](float4 pj, uint32_t, int k) {
+                replay_row<true>(ck, cnt, [&](float4 pj, uint32_t, int k) {
                     const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     const float len = sqrt_approx(r2);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_fluid_deltap(const __
                 while (far) {  // neighbours beyond q = 0.5: replace the inner-branch term by the true one
                     const int k = __ffs(far) - 1;
                     far &= far - 1;
-                    const float4 pj = lds128(slot_addr(stage_addr, row_code_reg(row, k)));
+                    const float4 pj = lds128(slot_addr(stage_addr, row_code(ck, k)));
                     const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     const float len = sqrt_approx(r2);
@@ -130,13 +131,13 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_fluid_deltap(const __
                 fx = f.x; fy = f.y; fz = f.z;
             }
         } else {
-            const float4 ci = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
+            const float4 ci = mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
             xi = f3(ci);
             const float li = ci.w;
             if (table) {
                 const bool literal = fp.literal_lambda_index != 0;
                 F3 f = f3(0.0f, 0.0f, 0.0f);
-                replay_table<false>(v, stage_addr, i, cnt, [&](float4 pj, uint32_t, int t) {
+                replay_row<false>(ck, cnt, [&](float4 pj, uint32_t, int t) {
                     // :97 — the reference indexes lambdas with the LOOP COUNTER
                     const float lj = literal ? (t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f) : pj.w;
                     deltap_pair<P, POLY6>(g, fp, xi, f3(pj), li, lj, f);
@@ -160,12 +161,12 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_fluid_deltap(const __
         p.z = resolve_collision(p.z, r, __fsub_rn((float)g.idomZ, r));
         next[i] = f4(p);
         if (LAST) {  // :110-111, always Exact (v and x feed the next step's keys); written to the step-boundary storage
-            const F3 xo = f3(v.pos[i]);
-            v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(p, xo), fp.dt));
+            v.vel_in[i] = f4(vdiv<Exact>(vsub<Exact>(p, f3(xo4)), fp.dt));
             v.pos_in[i] = f4(p);
-            v.flags_in[i] = v.flags[i];
-            v.orig_in[i] = v.orig[i];
+            v.flags_in[i] = fl;
+            v.orig_in[i] = og;
         }
+        return 0;
     });
 }
 
@@ -178,7 +179,7 @@ int lgpu_fluid_lambda_mode(const lgpu_ctx* c, const lgpu_step_params& p) {
 
 template <int LM>
 static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iterations) {
-    const int grid = 2 * c->num_sms;
+    const int grid = LGPU_CTAS_PER_SM * c->num_sms;
     const size_t smem = LGPU_BRICK_SMEM;
     float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
@@ -191,15 +192,15 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
         float4* next = bufs[it & 1];
         if (it > 0) {  // (the first density + lambda pass ran inside the table build)
             lgpu_mark(c, 6);
-            CUDA_TRY(launch_pdl(k_fluid_lambda<LM>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, cur, c->brick_ctl + 8 + c->pass));
+            CUDA_TRY(launch_pdl(k_fluid_lambda<LM>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, cur));
             c->pass++; c->launches++;
         }
         // slab mode: after each pass a small kernel copies the boundary particles' lambda (.w of cur) / corrected x*
         // (next) into the neighbours' ghost slots and waits for the neighbours' stores of the same pass
         if (slab && !fp.literal_lambda_index) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
-        if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap<LM, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));
-        else CUDA_TRY(launch_pdl(k_fluid_deltap<LM, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));
+        if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap<LM, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
+        else CUDA_TRY(launch_pdl(k_fluid_deltap<LM, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
         c->pass++; c->launches++;
         if (slab && it < iterations - 1) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;

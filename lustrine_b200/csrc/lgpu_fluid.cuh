@@ -157,25 +157,22 @@ __device__ __noinline__ float2 lambda_walk(const View& v, const FluidParams& fp,
 }
 
 // Density + lambda of ONE particle (src/Simulate.cpp:58-88) from its table row and the staged neighbourhood.
-// word = nbr_cnt[i]; xi = the particle's own x*.  Writes rho_i, lambda_i, and lambda_i into the w lane of the
+// word = list length | LGPU_CNT_*; xi = the particle's own x*.  Writes rho_i, lambda_i, and lambda_i into the w lane of the
 // particle's own x* so that the delta-p pass gets (x*_j, lambda_j) in one LDS.128.
 template <int LM>
-__device__ __forceinline__ void fluid_lambda_particle(const View& v, const FluidParams& fp, const BrickInfo& info, const float4* stage,
-                                                      float4* cur, int i, int word, F3 xi) {
+__device__ __forceinline__ void fluid_lambda_particle(const View& v, const FluidParams& fp, const Chunk& ck, float4* cur, int word, F3 xi) {
     typedef typename LambdaPolicy<LM>::P P;
     constexpr bool POLY6 = LambdaPolicy<LM>::poly6;
-    const uint32_t stage_addr = smem_u32(stage);
+    const uint32_t stage_addr = ck.stage_addr;
+    const int i = ck.i;
     const int cnt = word & LGPU_CNT_MASK;
-    const bool table = !(word & LGPU_CNT_WALK) && info.mode == 0;
+    const bool table = !(word & LGPU_CNT_WALK) && ck.d->mode == 0;
     float rho, lam;
     if (LM == LM_FAST) {
-        TableRow<8> row;
-        row.load_early<5>(v, i);
-        row.load_rest<5>(v, i, table ? cnt : 0);
         if (table) {
             float acc = 0.0f, sum = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
             uint32_t far = 0;
-            replay_row<true, 8>(row, stage_addr, cnt, [&](float4 pj, uint32_t, int k) {
+            replay_row<true>(ck, cnt, [&](float4 pj, uint32_t, int k) {
                 const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 const float len = sqrt_approx(r2);
@@ -188,7 +185,7 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
             while (far) {  // neighbours beyond q = 0.5: replace the inner-branch terms by the true ones
                 const int k = __ffs(far) - 1;
                 far &= far - 1;
-                const float4 pj = lds128(slot_addr(stage_addr, row_code_reg(row, k)));
+                const float4 pj = lds128(slot_addr(stage_addr, row_code(ck, k)));
                 const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 const float len = sqrt_approx(r2);
@@ -214,7 +211,7 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
             LambdaAcc<P, POLY6> acc;
             acc.init();
             const Geom& g = v.g;
-            replay_table<false>(v, stage_addr, i, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
+            replay_row<false>(ck, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
             lam = acc.finish(fp);
             rho = acc.rho;
         } else {

@@ -12,7 +12,7 @@
 #define LGPU_BLOCK 128
 #define LGPU_MAX_MARKS 96
 
-// ---- brick-staged neighbour table (lgpu_brick.cuh) ----
+// ---- brick-staged neighbour table (lgpu_neighbors.cuh) ----
 // The solver passes and the table build run over BRICKS of LGPU_BY x LGPU_BX cell columns x LGPU_BZ cells (z is the
 // fastest cell coordinate, so every column of a brick is ONE contiguous run of the cell-sorted storage).  A brick's
 // neighbourhood is the brick plus a one-cell shell: (BY+2)(BX+2) runs of BZ+2 cells, staged in shared memory with one
@@ -21,38 +21,63 @@
 #define LGPU_BY 4
 #define LGPU_BX 4
 #ifndef LGPU_BZ
-#define LGPU_BZ 8
+#define LGPU_BZ 7
 #endif
 #define LGPU_HX (LGPU_BX + 2)
 #define LGPU_HCOLS ((LGPU_BY + 2) * (LGPU_BX + 2))  // 36 halo columns
 #define LGPU_HB (LGPU_BZ + 3)                       // cell boundaries of a halo column (BZ + 2 cells)
 #define LGPU_OWN_COLS (LGPU_BY * LGPU_BX)           // 16
-#ifndef LGPU_NCW
-#define LGPU_NCW 15                                 // consumer warps of a block (+ 1 producer warp)
+#ifndef LGPU_BRICK_WARPS
+#define LGPU_BRICK_WARPS 8                          // warps of a block of the staged kernels (a brick of the unit lattice has 14-17 chunks of 32 particles at BZ = 7)
 #endif
-#define LGPU_BRICK_THREADS ((LGPU_NCW + 1) * 32)
-#ifndef LGPU_NSTAGE
-#define LGPU_NSTAGE 2                               // stage buffers of a block: the next brick is staged while this one is worked on
+#define LGPU_BRICK_THREADS (LGPU_BRICK_WARPS * 32)
+#ifndef LGPU_CTAS_PER_SM
+#define LGPU_CTAS_PER_SM 3                          // blocks of the staged kernels per SM: while one waits for its copies the others gather
 #endif
 #ifndef LGPU_STAGE_SLOTS
-#define LGPU_STAGE_SLOTS 3072    // float4 slots of ONE stage buffer (48 KB; two buffers per block, two blocks per SM)
+#define LGPU_STAGE_SLOTS 1600    // float4 slots of the staged neighbourhood of a block (unit lattice: <= 1408 at BZ = 7)
 #endif
+#ifndef LGPU_ROW_CAP
+#define LGPU_ROW_CAP 576         // own particles of a brick whose table block fits the block's shared memory (unit lattice: <= 539 at BZ = 7)
+#endif
+#define LGPU_MG 8                // table groups (of four 16-bit codes) per row: M = 32
 #define LGPU_DUMMY_SLOTS 8       // stage slots 0..7: far-away dummies (padding of sand rows)
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
 #define LGPU_CNT_GHOST (1 << 29)  // nbr_cnt flag: ghost particle of a neighbouring slab (not updated here)
 #define LGPU_CNT_MASK 0x0fffffff
+#define LGPU_CNT_SLOT_SHIFT 16    // meta word of a table block: list length (<= M) | stage slot << 16 | flags
+#define LGPU_CNT_SLOT_MASK 0x0fff0000
 #define LGPU_MAX_PASSES 40        // work cursors of one substep (table build + 2 K solver passes)
 
-// One non-empty brick of this substep (written by the table build's producer warps, read by every later pass).
-struct BrickDesc {
+// One non-empty brick of this substep: written by k_brick_desc (one warp per brick), fetched into shared memory by the
+// producer warps of the table build and of every solver pass with a bulk copy, two bricks ahead.
+// The brick's TABLE BLOCK lives at nbr16 + tab_off (8-byte words): n_pad meta words {sorted slot, list length | stage
+// slot << 16 | LGPU_CNT_*} — one per own particle, in the order of the brick's own runs — followed by LGPU_MG groups of
+// n_pad code words (four 16-bit stage-slot codes each, list order).  A solver pass brings in the first (1 + maxg) * n_pad
+// words with ONE bulk copy.
+struct alignas(16) BrickCol { int g0, s0, len, pad; };     // sorted slots [g0, g0 + len) sit in the stage slots from s0 (one LDS.128 per bulk copy)
+struct alignas(16) BrickDesc {
     int brick;                                // brick id = (by * nbX + bx) * nbZ + bz
-    int mode;                                 // 0 = staged; 2 = neighbourhood larger than the stage: its particles re-walk the stencil
+    int mode;                                 // 0 = staged; 2 = neighbourhood or table block larger than a ring slot: its particles re-walk the stencil
     int n_own;                                // particles of the brick itself
     int n_slots;                              // stage slots of the neighbourhood (dummies included)
-    int g0[LGPU_HCOLS], len[LGPU_HCOLS];      // halo column hc: sorted sand slots [g0, g0 + len)
-    int sg0[LGPU_HCOLS], slen[LGPU_HCOLS];    // ... sorted solid slots
-    int own_g0[LGPU_OWN_COLS], own_len[LGPU_OWN_COLS];  // the brick's own runs (inner columns, own cells)
+    int solid_base;                           // first stage slot that holds a solid (codes >= solid_base are solids)
+    int maxg;                                 // table groups (of four codes) of the brick's longest row
+    int n_pad;                                // n_own rounded up to an even number (16-byte rows of the table block)
+    int tab_off;                              // first 8-byte word of the brick's table block in nbr16
+    int cy0, cx0, cz0;                        // cell coordinates of the brick's first own cell
+    int work;                                 // index of the brick's record in brick_rec
+    int own_prefix[LGPU_OWN_COLS + 1];                 // particles of the own runs (inner columns, own cells) before run q
+    int own_g0[LGPU_OWN_COLS], own_s0[LGPU_OWN_COLS];  // first sorted slot / stage slot of own run q
+    BrickCol col[LGPU_HCOLS];                 // halo column hc, sand
+    BrickCol scol[LGPU_HCOLS];                // halo column hc, solids
+};
+// What k_brick_desc writes per non-empty brick: the descriptor, and for the table build the stage slot at every cell
+// boundary of every halo column.  The solver passes fetch only the descriptor.
+struct alignas(16) BrickRec {
+    BrickDesc d;
+    unsigned short cs[LGPU_HCOLS][LGPU_HB];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -121,9 +146,9 @@ struct View {
     // bricks (lgpu_brick.cuh)
     int nbY, nbX, nbZ, NB;    // brick grid
     int stage_slots;          // stage capacity in use (<= LGPU_STAGE_SLOTS; test hook lgpu_set_stage_slots)
-    int* brick_work;          // [NB] non-empty bricks: full ones from the front, sparse ones from the back
-    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [8 + pass] work cursor of each pass
-    BrickDesc* brick_desc;    // [work index]
+    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [2] table words allocated
+    BrickRec* brick_rec;      // non-empty bricks of this substep: full ones from the front, sparse ones from the back
+    int rec_cap;
     // unsorted (pre-reorder) buffers, indexed by the storage slot of the previous step
     float4 *pos_in, *vel_in, *pstar_in;
     int *flags_in, *orig_in;
@@ -136,11 +161,11 @@ struct View {
     // solids, sorted by cell once (src/neighbors/Neighbors.cpp:266-272)
     float4* solid_pos;
     int *solid_orig, *solid_cell_start;
-    // neighbour table: 16-bit codes in list order, four per uint2, group-major: codes 4g..4g+3 of
-    // particle i at nbr16[g * cap + i].  A code is the stage slot of the neighbour in the particle's brick
-    // (sand and solids alike; slots below LGPU_DUMMY_SLOTS are far-away dummies).
+    // neighbour table: one block per brick (see BrickDesc), 16-bit codes in list order, four per uint2.  A code is the
+    // stage slot of the neighbour in the particle's brick (sand and solids alike; slots below LGPU_DUMMY_SLOTS are
+    // far-away dummies).
     uint2* nbr16;
-    int* nbr_cnt;      // list length | LGPU_CNT_* flags
+    int* nbr_cnt;      // by sorted slot: list length | LGPU_CNT_* flags (dumps, re-walking bricks)
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;  // [0] key violations, [1] table overflows
 };
@@ -157,8 +182,9 @@ struct lgpu_ctx {
     int nbY, nbX, nbZ, NB;
     int num_sms;
     int pass;             // solver pass counter of the substep being enqueued (selects the work cursor)
-    int *brick_work, *brick_ctl;
-    BrickDesc* brick_desc;
+    int* brick_ctl;
+    BrickRec* brick_rec;
+    int rec_cap;
     bool generic_kernels; // test hook: run the fast-arithmetic fluid step with the generic kernels (lgpu_set_generic_kernels)
     bool grid_valid;      // cell_start/key describe the current storage
     bool solids_sorted;

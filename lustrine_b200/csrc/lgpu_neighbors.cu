@@ -8,72 +8,133 @@
 #include "lgpu_fluid.cuh"
 
 // ------------------------------------------------------------------------------------------
-// work list: the non-empty bricks of this substep (one thread per brick)
+// work list: the non-empty bricks of this substep and their descriptors (one warp per brick)
 // ------------------------------------------------------------------------------------------
-// Full bricks are appended from the front of brick_work and sparse ones (surface, spray) from the back, so that
-// the persistent blocks take the heavy bricks first and the light ones even out the tail.
-__global__ void __launch_bounds__(128) k_brick_list(View v) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= v.NB) return;
+// Full bricks are appended from the front of brick_rec and sparse ones (surface, spray) from the back, so that
+// the persistent blocks take the heavy bricks first and the light ones even out the tail.  The descriptor is put
+// together in shared memory and written out in one piece; it also reserves the brick's table block.
+#define LGPU_DESC_WARPS 8
+__global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __grid_constant__ View v) {
+    __shared__ BrickRec recs[LGPU_DESC_WARPS];
+    __shared__ int cs32[LGPU_DESC_WARPS][LGPU_HCOLS][LGPU_HB];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int brick = blockIdx.x * LGPU_DESC_WARPS + wib;
+    if (brick >= v.NB) return;
     const Geom& g = v.g;
-    const int by = b / (v.nbX * v.nbZ);
-    const int rem = b - by * (v.nbX * v.nbZ);
+    const int by = brick / (v.nbX * v.nbZ);
+    const int rem = brick - by * (v.nbX * v.nbZ);
     const int bx = rem / v.nbZ, bz = rem - bx * v.nbZ;
-    const int z0 = bz * LGPU_BZ, z1 = min(z0 + LGPU_BZ, g.gZ);
-    int n = 0;
-#pragma unroll
-    for (int q = 0; q < LGPU_OWN_COLS; q++) {
-        const int cy = by * LGPU_BY + q / LGPU_BX, cx = bx * LGPU_BX + q % LGPU_BX;
+    const int cy0 = by * LGPU_BY, cx0 = bx * LGPU_BX, cz0 = bz * LGPU_BZ;
+    // own particles: the inner columns, cells cz0 .. cz0 + BZ - 1
+    int own_len = 0, own_a = 0;
+    if (lane < LGPU_OWN_COLS) {
+        const int cy = cy0 + lane / LGPU_BX, cx = cx0 + lane % LGPU_BX;
         if (cy < g.gY && cx < g.gX) {
             const int base = cy * g.gXZ + cx * g.gZ;
-            n += v.cell_start[base + z1] - v.cell_start[base + z0];
+            own_a = v.cell_start[base + min(cz0, g.gZ)];
+            own_len = v.cell_start[base + min(cz0 + LGPU_BZ, g.gZ)] - own_a;
         }
     }
-    if (n == 0) return;
-    // (warp-aggregated by the compiler; the order inside the two lists does not affect any result)
-    if (n >= 256) v.brick_work[atomicAdd(&v.brick_ctl[0], 1)] = b;
-    else v.brick_work[v.NB - 1 - atomicAdd(&v.brick_ctl[1], 1)] = b;
+    const int oinc = warp_incl_scan_i(own_len, lane);
+    const int n_own = __shfl_sync(0xffffffffu, oinc, LGPU_OWN_COLS - 1);
+    if (n_own == 0) return;
+    BrickRec& rec = recs[wib];
+    BrickDesc& d = rec.d;
+    int (*cs)[LGPU_HB] = cs32[wib];
+    // sorted slot at every cell boundary of every halo column (cells cz0-1 .. cz0+BZ, clipped to the grid; the
+    // cell offsets are linear in the cell id with z fastest, so boundary gZ of a column is the next column's start)
+    for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
+        const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
+        const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
+        int val = 0;
+        if (cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
+        cs[hc][t] = val;
+    }
+    for (int idx = lane; idx < 2 * LGPU_HCOLS; idx += 32) {
+        const int hc = idx >> 1, t = (idx & 1) * (LGPU_HB - 1);
+        const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
+        int val = 0;
+        if (v.n_solid && cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.solid_cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
+        if (idx & 1) d.scol[hc].len = val; else d.scol[hc].g0 = val;  // (len = range END for the moment)
+    }
+    __syncwarp();
+    // lane: halo column `lane`; lanes 0..3 also column 32 + lane
+    const int hi = 32 + lane;
+    const bool two = lane < LGPU_HCOLS - 32;
+    const int len0 = cs[lane][LGPU_HB - 1] - cs[lane][0];
+    const int len1 = two ? cs[hi][LGPU_HB - 1] - cs[hi][0] : 0;
+    const int slen0 = d.scol[lane].len - d.scol[lane].g0;
+    const int slen1 = two ? d.scol[hi].len - d.scol[hi].g0 : 0;
+    // stage slots: dummies, sand columns 0..35, solid columns 0..35
+    const int inc0 = warp_incl_scan_i(len0, lane), tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    const int inc1 = warp_incl_scan_i(len1, lane), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+    const int sinc0 = warp_incl_scan_i(slen0, lane), stot0 = __shfl_sync(0xffffffffu, sinc0, 31);
+    const int sinc1 = warp_incl_scan_i(slen1, lane), stot1 = __shfl_sync(0xffffffffu, sinc1, 31);
+    const int solid_base = LGPU_DUMMY_SLOTS + tot0 + tot1;
+    const int n_slots = solid_base + stot0 + stot1;
+    d.col[lane].g0 = cs[lane][0]; d.col[lane].len = len0; d.col[lane].s0 = LGPU_DUMMY_SLOTS + inc0 - len0; d.col[lane].pad = 0;
+    d.scol[lane].len = slen0; d.scol[lane].s0 = solid_base + sinc0 - slen0; d.scol[lane].pad = 0;
+    if (two) {
+        d.col[hi].g0 = cs[hi][0]; d.col[hi].len = len1; d.col[hi].s0 = LGPU_DUMMY_SLOTS + tot0 + inc1 - len1; d.col[hi].pad = 0;
+        d.scol[hi].len = slen1; d.scol[hi].s0 = solid_base + stot0 + sinc1 - slen1; d.scol[hi].pad = 0;
+    }
+    __syncwarp();
+    const int n_pad = (n_own + 1) & ~1;
+    const int mode = (n_slots > v.stage_slots || n_pad > LGPU_ROW_CAP) ? 2 : 0;
+    // boundaries -> stage slots (16 bits; a brick whose neighbourhood does not fit a ring slot never looks at them)
+    for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
+        const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
+        rec.cs[hc][t] = (unsigned short)min(d.col[hc].s0 + (cs[hc][t] - d.col[hc].g0), 65535);
+    }
+    // own runs: cells 1 .. BZ of the inner halo columns
+    if (lane < LGPU_OWN_COLS) {
+        const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
+        d.own_g0[lane] = own_a;
+        d.own_s0[lane] = d.col[hc].s0 + (own_a - d.col[hc].g0);
+        d.own_prefix[lane + 1] = oinc;
+    }
+    int w = 0;
+    if (lane == 0) {
+        const bool full = n_own >= 256;
+        const int k = atomicAdd(&v.brick_ctl[full ? 0 : 1], 1);
+        w = full ? k : v.rec_cap - 1 - k;   // record index; the work index of a sparse brick is n_full + k (see rec_of_work)
+        d.own_prefix[0] = 0;
+        d.brick = brick; d.mode = mode; d.n_own = n_own; d.n_slots = n_slots;
+        d.solid_base = solid_base; d.maxg = 0; d.n_pad = n_pad;
+        d.tab_off = mode == 0 ? atomicAdd(&v.brick_ctl[2], n_pad * (1 + LGPU_MG)) : 0;
+        d.cy0 = cy0; d.cx0 = cx0; d.cz0 = cz0;
+        d.work = w;  // (= the record index)
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    __syncwarp();
+    int4* gd = reinterpret_cast<int4*>(&v.brick_rec[w]);
+    const int4* sd = reinterpret_cast<const int4*>(&rec);
+    for (int t = lane; t < (int)(sizeof(BrickRec) / 16); t += 32) gd[t] = sd[t];
 }
 
 // ------------------------------------------------------------------------------------------
 // table build
 // ------------------------------------------------------------------------------------------
-// Appends 16-bit codes to a table row.  Four consecutive codes share one 8-byte group and the groups
-// are strided by the capacity (nbr16 layout in lgpu_internal.cuh): the codes are packed in a 64-bit
-// shift register and every fourth emit stores one group.
+// Collects the 16-bit codes of a table row in the lane's row of the slot's table block (shared memory, [group][own
+// particle]); the finished block goes to global memory with one bulk copy, and the row is still at hand for the first
+// density + lambda pass.
 struct RowWriter {
-    uint2* col;       // next group of this particle's row
-    size_t stride;    // capacity
-    uint32_t lo, hi;  // shift register: after four emits lo = c0 | c1 << 16, hi = c2 | c3 << 16
+    uint32_t base, stride;    // shared address of the lane's first group; bytes between groups
     int M, cnt;
-    bool bad;
-    __device__ __forceinline__ void init(const View& v, int i) {
-        col = v.nbr16 + i;
-        stride = (size_t)v.cap;
-        lo = hi = 0;
-        M = v.M; cnt = 0; bad = false;
+    __device__ __forceinline__ void init(const View& v, const Chunk& ck) {
+        base = ck.row_addr; stride = ck.row_stride;
+        M = v.M; cnt = 0;
     }
-    __device__ __forceinline__ void shift_in(uint32_t code) {
-        lo = __byte_perm(lo, hi, 0x5432);    // (lo >> 16) | (hi << 16)
-        hi = __byte_perm(hi, code, 0x5432);  // (hi >> 16) | (code << 16)
+    __device__ __forceinline__ void put(int k, uint32_t code) {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)(k >> 2) * stride + (uint32_t)(k & 3) * 2u), "h"((unsigned short)code) : "memory");
     }
     __device__ __forceinline__ void emit(uint32_t code) {
-        if (cnt < M) {
-            shift_in(code);
-            if ((cnt & 3) == 3) { *col = make_uint2(lo, hi); col += stride; }
-        }
+        if (cnt < M) put(cnt, code);
         cnt++;
     }
-    __device__ __forceinline__ void emit_unchecked(uint32_t code) {  // the caller has checked cnt + (codes to come) <= M
-        shift_in(code);
-        if ((cnt & 3) == 3) { *col = make_uint2(lo, hi); col += stride; }
-        cnt++;
-    }
+    __device__ __forceinline__ void emit_unchecked(uint32_t code) { put(cnt, code); cnt++; }  // the caller has checked cnt + (codes to come) <= M
     __device__ __forceinline__ void finish(uint32_t pad) {  // completes the last group with the padding code
-        if (cnt < M && (cnt & 3)) {
-            for (int k = cnt & 3; k < 4; k++) shift_in(pad);
-            *col = make_uint2(lo, hi);
-        }
+        if (cnt < M) for (int k = cnt; k & 3; k++) put(k, pad);
     }
 };
 
@@ -81,32 +142,34 @@ struct RowWriter {
 // stencil over the global storage in the reference's nested order (per cell: sand then solids in the fluid lists,
 // solids then sand in the sand lists) and translate what they find into stage slots of their brick.
 template <bool SAND>
-__device__ __noinline__ int2 build_row_walk(const View& v, const BrickInfo& info, int i, F3 xi, int ly, int lx, uint32_t pad) {
+__device__ __noinline__ int build_row_walk(const View& v, const BrickDesc& d, const Chunk& ck, F3 xi, int ly, int lx, uint32_t pad) {
     RowWriter w;
-    w.init(v, i);
-    walk<SAND>(v, i, xi, [&](int j, int r) {
+    w.init(v, ck);
+    walk<SAND>(v, ck.i, xi, [&](int j, int r) {
         const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;  // halo column of stencil column r = 3 (dy + 1) + (dx + 1)
-        if (j >= 0) w.emit((uint32_t)(info.col_s0[hc] + (j - info.col_g0[hc])));
-        else w.emit((uint32_t)(info.scol_s0[hc] + (~j - info.scol_g0[hc])));
+        if (j >= 0) w.emit((uint32_t)(d.col[hc].s0 + (j - d.col[hc].g0)));
+        else w.emit((uint32_t)(d.scol[hc].s0 + (~j - d.scol[hc].g0)));
     });
     w.finish(pad);
-    return make_int2(w.cnt, w.bad ? 1 : 0);
+    return w.cnt;
 }
 
 template <bool SAND, int LM>
-__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, int* cursor) {
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_table(const __grid_constant__ View v, const __grid_constant__ FluidParams fp) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<true>(v, v.x0, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int q, int i, int slot) {
+    brick_loop<true>(v, v.x0, smem_raw, [&](const Chunk& ck) -> int {
         const Geom& g = v.g;
-        const uint32_t stage_addr = smem_u32(stage);
-        const float4 x0i = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : v.x0[i];
+        const BrickDesc& d = *ck.d;
+        const int i = ck.i, slot = ck.slot, q = ck.q;
+        const uint32_t stage_addr = ck.stage_addr;
+        const float4 x0i = d.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : v.x0[i];
         const F3 xi = f3(x0i);
-        int word;
+        int word, ng = 0;
         const int flags = g.slab ? v.flags[i] : 0;
         if (flags & LGPU_FLAG_GHOST) {  // ghost of a neighbouring slab: read by others, never updated here
             word = LGPU_CNT_GHOST;
-        } else if (info.mode != 0) {
-            // neighbourhood larger than the stage: count only, the solver passes re-walk the stencil
+        } else if (d.mode != 0) {
+            // neighbourhood larger than a ring slot: count only, the solver passes re-walk the stencil
             int cnt = 0;
             walk<SAND>(v, i, f3(v.x0[i]), [&](int, int) { cnt++; });
             word = cnt | LGPU_CNT_WALK;
@@ -117,7 +180,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __g
             // the particle's cell along its own run: boundary index tz with cs[hown][tz] <= slot < cs[hown][tz + 1]
             int tz = 1;
 #pragma unroll
-            for (int t = 2; t <= LGPU_BZ; t++) tz += slot >= info.cs[hown][t] ? 1 : 0;
+            for (int t = 2; t <= LGPU_BZ; t++) tz += slot >= ck.cs[hown][t] ? 1 : 0;
             // per stencil column: the candidates are the stage slots [cb, ce) — the three cells z-1..z+1 of a column are
             // contiguous in the sorted storage and therefore in the stage
             int cb[9], ce[9];
@@ -125,29 +188,20 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __g
 #pragma unroll
             for (int r = 0; r < 9; r++) {
                 const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;
-                cb[r] = info.cs[hc][tz - 1]; ce[r] = info.cs[hc][tz + 2];
+                cb[r] = ck.cs[hc][tz - 1]; ce[r] = ck.cs[hc][tz + 2];
                 if (ce[r] - cb[r] > 32) slow = true;
-            }
-            if (v.n_solid) {
-                // (one compare per column: the solid range of a halo column spans the brick's z extent)
-#pragma unroll
-                for (int r = 0; r < 9; r++) {
-                    const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;
-                    if (info.scol_len[hc] > 0) slow = true;
-                }
+                if (d.scol[hc].len > 0) slow = true;  // (the solid range of a halo column spans the brick's z extent)
             }
             const uint32_t self_code = (uint32_t)slot;
             // padding: sand = a far-away dummy (no contact); fluid = the particle itself (zero separation: every term of
             // the branch-free fluid bodies vanishes)
             const uint32_t pad = SAND ? 0u : self_code;
             int cnt;
-            bool bad;
             if (slow) {
-                const int2 r = build_row_walk<SAND>(v, info, i, xi, ly, lx, pad);
-                cnt = r.x; bad = r.y != 0;
+                cnt = build_row_walk<SAND>(v, d, ck, xi, ly, lx, pad);
             } else {
                 RowWriter w;
-                w.init(v, i);
+                w.init(v, ck);
                 // No solid near: the reference order is simply ascending sorted slot over the 9 columns (fluid: self
                 // included; sand: self skipped — SURVEY F7).  Per column: test the candidates with the Exact predicate
                 // into a hit mask, then emit the hits.
@@ -172,7 +226,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __g
                     const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
                     if (SAND && r == 4) m &= ~(1u << (top - self_code));
                     const int hits = __popc(m);
-                    if (w.cnt + hits > w.M) { w.cnt += hits; w.bad = true; continue; }  // row too long: the solver passes re-walk
+                    if (w.cnt + hits > w.M) { w.cnt += hits; continue; }  // row too long: the solver passes re-walk
                     while (m) {  // ascending candidate = descending bit
                         const uint32_t k = 31u - (uint32_t)__clz(m);
                         m ^= 1u << k;
@@ -180,24 +234,28 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_build_table(const __g
                     }
                 }
                 w.finish(pad);
-                cnt = w.cnt; bad = w.bad;
+                cnt = w.cnt;
             }
             word = cnt;
-            if (cnt > v.M || bad) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
+            if (cnt > v.M) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
+            else ng = (cnt + 3) >> 2;
         }
         v.nbr_cnt[i] = word;
+        const int mword = (word & LGPU_CNT_WALK) ? (word & ~LGPU_CNT_MASK) : word;  // (a re-walked row's length is not needed)
+        if (d.mode == 0) *ck.meta = make_uint2((uint32_t)i, (uint32_t)(mword | (slot << LGPU_CNT_SLOT_SHIFT)));
         if (!SAND && LM != LM_NONE) {
-            // first density + lambda pass on the list just written (the thread re-reads its own row)
-            if (!(word & LGPU_CNT_GHOST)) fluid_lambda_particle<LM>(v, fp, info, stage, v.x0, i, word, xi);
+            // first density + lambda pass on the list just collected
+            if (!(word & LGPU_CNT_GHOST)) fluid_lambda_particle<LM>(v, fp, ck, v.x0, mword, xi);
         }
+        return ng;
     });
 }
 
-static int brick_grid(const lgpu_ctx* c) { return 2 * c->num_sms; }
+static int brick_grid(const lgpu_ctx* c) { return LGPU_CTAS_PER_SM * c->num_sms; }
 
 template <bool SAND, int LM>
 static int launch_build(lgpu_ctx* c, const View& v, const FluidParams& fp, bool pdl) {
-    CUDA_TRY(launch_pdl(k_build_table<SAND, LM>, brick_grid(c), LGPU_BRICK_THREADS, LGPU_BRICK_SMEM, c->stream, pdl, v, fp, c->brick_ctl + 8 + c->pass));
+    CUDA_TRY(launch_pdl(k_build_table<SAND, LM>, brick_grid(c), LGPU_BRICK_THREADS, LGPU_BRICK_SMEM_BUILD, c->stream, pdl, v, fp));
     return LGPU_OK;
 }
 
@@ -206,7 +264,7 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order, const lgpu_step_params
     if (c->n == 0) return LGPU_OK;  // (slab mode: the solver drivers still run the refresh protocol)
     View v = lgpu_make_view(c);
     FluidParams fp = lgpu_make_fluid_params(c->g, p);
-    k_brick_list<<<(c->NB + 127) / 128, 128, 0, c->stream>>>(v);
+    k_brick_desc<<<(c->NB + LGPU_DESC_WARPS - 1) / LGPU_DESC_WARPS, LGPU_DESC_WARPS * 32, 0, c->stream>>>(v);
     static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
     const bool pdl = pdl_env && !c->phase_timing && !c->use_graph;
     int st;
@@ -229,30 +287,24 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order, const lgpu_step_params
 // translated back to sorted slots through the brick's descriptor, rows the table does not hold are re-walked.
 template <bool SAND>
 __global__ void __launch_bounds__(128) k_dump_nbr(View v, const long* __restrict__ offsets, int* __restrict__ flat) {
-    __shared__ BrickInfo info;
     const int n_full = v.brick_ctl[0], n_work = n_full + v.brick_ctl[1];
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        __syncthreads();
-        const BrickDesc& d = v.brick_desc[w];
-        if (threadIdx.x == 0) {
-            int s = LGPU_DUMMY_SLOTS;
-            for (int hc = 0; hc < LGPU_HCOLS; hc++) { info.col_g0[hc] = d.g0[hc]; info.col_s0[hc] = s; info.col_len[hc] = d.len[hc]; s += d.len[hc]; }
-            for (int hc = 0; hc < LGPU_HCOLS; hc++) { info.scol_g0[hc] = d.sg0[hc]; info.scol_s0[hc] = s; info.scol_len[hc] = d.slen[hc]; s += d.slen[hc]; }
-        }
-        __syncthreads();
+        const BrickDesc& d = v.brick_rec[rec_of_work(v, w, n_full)].d;
+        const uint2* tab = v.nbr16 + d.tab_off;
         for (int q = 0; q < LGPU_OWN_COLS; q++) {
-            for (int t = threadIdx.x; t < d.own_len[q]; t += blockDim.x) {
-                const int i = d.own_g0[q] + t;
+            const int len = d.own_prefix[q + 1] - d.own_prefix[q];
+            for (int t = threadIdx.x; t < len; t += blockDim.x) {
+                const int i = d.own_g0[q] + t, p = d.own_prefix[q] + t;
                 if (v.g.slab ? (v.flags[i] & LGPU_FLAG_GHOST) != 0 : false) continue;
                 long o = offsets[i];
                 const int word = v.nbr_cnt[i];
-                if (!(word & LGPU_CNT_WALK)) {
+                if (!(word & LGPU_CNT_WALK) && d.mode == 0) {
                     const int cnt = word & LGPU_CNT_MASK;
                     for (int k = 0; k < cnt; k++) {
-                        const uint2 g4 = v.nbr16[(size_t)(k >> 2) * v.cap + i];
+                        const uint2 g4 = tab[(size_t)(1 + (k >> 2)) * d.n_pad + p];
                         const uint32_t pair = (k & 2) ? g4.y : g4.x;
                         const int code = (int)((k & 1) ? pair >> 16 : pair & 0xffffu);
-                        const int j = decode_code(info, code);
+                        const int j = decode_code(d, code);
                         flat[o++] = j >= 0 ? j : v.n + v.solid_orig[~j];
                     }
                 } else {
@@ -272,7 +324,7 @@ int lgpu_launch_dump_nbr(lgpu_ctx* c, bool sand, const long* d_off, int* d_flat)
 
 #define LGPU_PRELOAD(f) do { cudaFuncAttributes a; CUDA_TRY(cudaFuncGetAttributes(&a, f)); } while (0)
 template <bool SAND, int LM> static int preload_build() {
-    CUDA_TRY(cudaFuncSetAttribute(k_build_table<SAND, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LGPU_BRICK_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_build_table<SAND, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LGPU_BRICK_SMEM_BUILD));
     return LGPU_OK;
 }
 // Loads every kernel of this file on the CURRENT device and opts the staged ones into their dynamic
@@ -280,6 +332,6 @@ template <bool SAND, int LM> static int preload_build() {
 int lgpu_preload_neighbors() {
     int st = preload_build<true, LM_NONE>() | preload_build<false, LM_NONE>() | preload_build<false, LM_FAST>() |
              preload_build<false, LM_EXACT>() | preload_build<false, LM_POLY6>() | preload_build<false, LM_GENERIC>();
-    LGPU_PRELOAD(k_brick_list); LGPU_PRELOAD(k_dump_nbr<true>); LGPU_PRELOAD(k_dump_nbr<false>);
+    LGPU_PRELOAD(k_brick_desc); LGPU_PRELOAD(k_dump_nbr<true>); LGPU_PRELOAD(k_dump_nbr<false>);
     return st ? LGPU_ERR_CUDA : LGPU_OK;
 }

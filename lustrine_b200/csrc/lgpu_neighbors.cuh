@@ -4,20 +4,28 @@
 // The reference materialises std::vector<int> lists (src/neighbors/Neighbors.cpp:306-361 for
 // sand "v1", :386-448 for fluid "v0") once per step and every solver loop accumulates over them
 // in list order.  Here the same lists, in the same order, are produced once per substep by
-// k_build_table (lgpu_neighbors.cu) and stored as 16-bit codes.  All staged kernels (the build and
-// every solver pass) are PERSISTENT: two blocks per SM, each a producer warp plus LGPU_NCW consumer
-// warps, working through the substep's list of non-empty bricks (LGPU_BY x LGPU_BX x LGPU_BZ cells):
-//   producer   takes the next brick from a device-side cursor, writes its descriptor to shared
-//              memory and issues one 1-D bulk copy (cp.async.bulk, the TMA engine) per halo column
-//              into the free stage buffer — the storage is cell-sorted with z fastest, so a column
-//              of BZ + 2 cells is ONE contiguous range — completing on that buffer's "full" mbarrier;
-//   consumers  wait for "full", take 32-particle chunks of the brick from a shared counter, replay
-//              each particle's list (one coalesced 8-byte load per four neighbours, one LDS.128 per
-//              neighbour) and arrive on the buffer's "empty" mbarrier when the brick is done.
-// With two stage buffers the copies of brick n+1 overlap the gather of brick n.
-// Lists that do not fit (more than M entries, a neighbourhood larger than the stage) fall back to a
+// k_build_table (lgpu_neighbors.cu) and stored as 16-bit codes, one contiguous TABLE BLOCK per brick.
+// All staged kernels (the build and every solver pass) run LGPU_CTAS_PER_SM blocks of LGPU_BRICK_THREADS threads per
+// SM; block b works through the bricks b, b + gridDim.x, ... of the substep's list of non-empty bricks
+// (LGPU_BY x LGPU_BX x LGPU_BZ cells).  Per brick:
+//   1. the brick's descriptor arrives in shared memory (one bulk copy, cp.async.bulk = the TMA engine, issued while the
+//      block was still working on its previous brick);
+//   2. every warp issues the bulk copies of a few halo columns of positions — the storage is cell-sorted with z
+//      fastest, so a column of BZ + 2 cells is ONE contiguous range; a warp issues one bulk copy per ~57 cycles
+//      whichever lane does it, but the warps of a block issue concurrently (tools/micro/stage_rate.cu) — and, in the
+//      solver passes, one warp the copy of the brick's TABLE BLOCK (per own particle: sorted slot, list length, codes);
+//      all of them complete on one mbarrier;
+//   3. each warp replays the lists of its 32-particle chunks: one conflict-free LDS.64 per four codes, one LDS.128 per
+//      neighbour.  The threads read NOTHING from global memory; their only global traffic is the stores of their
+//      results.  (Table build: the rows are collected in shared memory and the finished block leaves with one bulk store.)
+// While one block of an SM waits for its copies the other blocks of the SM gather: the hardware interleaves the
+// blocks' pipelines, no hand-made ring is needed (a persistent producer/consumer ring with 3 slots per SM was built
+// and measured slower: a slot is held until its LAST chunk is done, which halves the chunks in flight).
+// Lists that do not fit (more than M entries, a neighbourhood larger than a slot) fall back to a
 // stencil re-walk with the frozen build-time predicate — always correct, only slower.
 #pragma once
+#include <stdlib.h>
+
 #include "lgpu_internal.cuh"
 
 struct CellCoord { int y, x, z; };
@@ -141,14 +149,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
     uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
-
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    for (;;) {
+        // (the hardware suspends the warp for up to the time hint; a waiting warp takes no issue slots)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (ok) break;
+    }
+}
 // Programmatic dependent launch between consecutive kernels of the substep: a kernel lets its successor start
 // launching as soon as all of its own blocks are resident (pdl_trigger at the top); the successor's blocks
 // become resident as this kernel's blocks retire and its producer warps wait for this kernel's memory
@@ -168,6 +184,32 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int blo
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// shared -> global bulk copy (TMA store) of a finished table block, tracked by the issuing thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // the source may be reused
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // the writes are done
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    unsigned short r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+    return (uint32_t)r;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -183,28 +225,26 @@ __device__ __forceinline__ uint32_t slot_addr(uint32_t stage_addr, uint32_t code
 // ------------------------------------------------------------------------------------------
 // Brick pipeline
 // ------------------------------------------------------------------------------------------
-// Descriptor of the brick held by one stage buffer (shared memory; written by the producer warp before it
-// arrives on the buffer's "full" barrier).
-struct BrickInfo {
-    int work;                       // work index of the brick; -1 = no more work (the consumers leave)
-    int mode;                       // BrickDesc::mode
-    int n_own;
-    int solid_base;                 // first stage slot that holds a solid (codes >= solid_base are solids)
-    int cy0, cx0, cz0;              // cell coordinates of the brick's first own cell
-    int next_chunk;                 // 32-particle chunks handed out so far
-    int own_prefix[LGPU_OWN_COLS + 1];                 // particles of the own runs before run q
-    int own_g0[LGPU_OWN_COLS], own_s0[LGPU_OWN_COLS];  // first sorted slot / stage slot of own run q
-    int col_g0[LGPU_HCOLS], col_s0[LGPU_HCOLS];        // halo column hc: sorted sand slot j sits in stage slot col_s0 + (j - col_g0)
-    int scol_g0[LGPU_HCOLS], scol_s0[LGPU_HCOLS];      // ... sorted solid slot k
-    int col_len[LGPU_HCOLS], scol_len[LGPU_HCOLS];     // particles / solids of halo column hc
-    int cs[LGPU_HCOLS][LGPU_HB];    // table build only: stage slot at every cell boundary of every halo column
+// One ring slot: the staged neighbourhood and the brick's table block (layout of the block: see BrickDesc).
+struct BrickSlot {
+    float4 pos[LGPU_STAGE_SLOTS];
+    uint2 tab[LGPU_ROW_CAP * (1 + LGPU_MG)];
 };
 
+// Shared control block of a block: its brick's descriptor (double-buffered: the next brick's descriptor is fetched
+// while this one is worked on; the table build fetches whole records = descriptor + cell boundaries) and barriers.
+template <bool BUILD> struct BrickRingEntry { BrickDesc d; };
+template <> struct BrickRingEntry<true> { BrickDesc d; unsigned short cs[LGPU_HCOLS][LGPU_HB]; };
+template <bool BUILD>
 struct BrickShared {
-    uint64_t full[LGPU_NSTAGE], empty[LGPU_NSTAGE];
-    BrickInfo info[LGPU_NSTAGE];
+    uint64_t full, dfull[2];
+    alignas(16) BrickRingEntry<BUILD> ring[2];
+    int maxg;                       // table build: groups of the longest row collected so far
 };
-#define LGPU_BRICK_SMEM (sizeof(float4) * LGPU_STAGE_SLOTS * LGPU_NSTAGE + sizeof(BrickShared) + 128)
+#define LGPU_BRICK_SMEM_OF(BUILD) (sizeof(BrickSlot) + sizeof(BrickShared<BUILD>) + 128)
+#define LGPU_BRICK_SMEM LGPU_BRICK_SMEM_OF(false)
+#define LGPU_BRICK_SMEM_BUILD LGPU_BRICK_SMEM_OF(true)
+static_assert(LGPU_CTAS_PER_SM * (LGPU_BRICK_SMEM_BUILD + 1024) <= 233472, "the blocks of an SM exceed its 228 KB of shared memory");
 
 __device__ __forceinline__ int warp_incl_scan_i(int x, int lane) {
 #pragma unroll
@@ -215,310 +255,206 @@ __device__ __forceinline__ int warp_incl_scan_i(int x, int lane) {
     return x;
 }
 
-// work index -> brick id: full bricks were appended from the front of brick_work, sparse ones from the back
-__device__ __forceinline__ int brick_of_work(const View& v, int w, int n_full) {
-    return w < n_full ? v.brick_work[w] : v.brick_work[v.NB - 1 - (w - n_full)];
+// work index -> record: full bricks were appended from the front of brick_rec, sparse ones from the back
+__device__ __forceinline__ int rec_of_work(const View& v, int w, int n_full) {
+    return w < n_full ? w : v.rec_cap - 1 - (w - n_full);
 }
 
-// Producer warp, one brick: fills `info`, (BUILD) derives the descriptor from the cell offsets and publishes it to
-// v.brick_desc[w] for the later passes, or (!BUILD) reads it from there; then starts the bulk copies of `src` (sand
-// columns) and of the sorted solids into `stage`, completing on `full`.  All 32 lanes call it.
+// Starts the bulk copies of warp `pw`'s share of the brick described by d — `src` (sand columns), the sorted solids
+// and, in the solver passes (TABLE), the brick's table block — completing on `full` (whose transaction count thread 0
+// sets, brick_stage_bytes).  Called by lane 0 of every warp.
+__device__ __forceinline__ uint32_t brick_table_bytes(const BrickDesc& d) { return 8u * (uint32_t)d.n_pad * (uint32_t)(1 + d.maxg); }
+template <bool TABLE>
+__device__ __forceinline__ uint32_t brick_stage_bytes(const BrickDesc& d) {
+    return d.mode == 0 ? 16u * (uint32_t)(d.n_slots - LGPU_DUMMY_SLOTS) + (TABLE ? brick_table_bytes(d) : 0u) : 0u;
+}
+template <bool TABLE>
+__device__ __forceinline__ void brick_stage(const View& v, const BrickDesc& d, BrickSlot& slot, uint64_t* full, const float4* __restrict__ src, int pw) {
+    if (d.mode != 0) return;
+    if (TABLE && pw == LGPU_BRICK_WARPS - 1) bulk_g2s(slot.tab, v.nbr16 + d.tab_off, brick_table_bytes(d), full);
+    for (int hc = pw; hc < LGPU_HCOLS; hc += LGPU_BRICK_WARPS) {
+        const int4 c = *reinterpret_cast<const int4*>(&d.col[hc]);
+        if (c.z > 0) bulk_g2s(slot.pos + c.y, src + c.x, 16u * (uint32_t)c.z, full);
+    }
+    if (v.n_solid)
+        for (int hc = pw; hc < LGPU_HCOLS; hc += LGPU_BRICK_WARPS) {
+            const int4 c = *reinterpret_cast<const int4*>(&d.scol[hc]);
+            if (c.z > 0) bulk_g2s(slot.pos + c.y, v.solid_pos + c.x, 16u * (uint32_t)c.z, full);
+        }
+}
+
+// Carves the dynamic shared memory of a brick kernel: the slot (128-byte aligned), then barriers + descriptors.
 template <bool BUILD>
-__device__ __forceinline__ void brick_produce(const View& v, int w, int n_full, BrickInfo& info, float4* stage, uint64_t* full,
-                                              const float4* __restrict__ src) {
-    const int lane = threadIdx.x & 31;
-    const Geom& g = v.g;
-    const int brick = brick_of_work(v, w, n_full);
-    const int by = brick / (v.nbX * v.nbZ);
-    const int rem = brick - by * (v.nbX * v.nbZ);
-    const int bx = rem / v.nbZ, bz = rem - bx * v.nbZ;
-    const int cy0 = by * LGPU_BY, cx0 = bx * LGPU_BX, cz0 = bz * LGPU_BZ;
-    int len0, len1 = 0, slen0 = 0, slen1 = 0;  // lane: halo column `lane`; lanes 0..3 also column 32 + lane
-    int mode = 0, n_slots = 0;
-    if (BUILD) {
-        // sorted slot at every cell boundary of every halo column (cells cz0-1 .. cz0+BZ, clipped to the grid; the
-        // cell offsets are linear in the cell id with z fastest, so boundary gZ of a column is the next column's start)
-        for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
-            const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
-            const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
-            int val = 0;
-            if (cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
-            info.cs[hc][t] = val;
-        }
-        if (v.n_solid) {
-            for (int idx = lane; idx < 2 * LGPU_HCOLS; idx += 32) {
-                const int hc = idx >> 1, t = (idx & 1) * (LGPU_HB - 1);
-                const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
-                int val = 0;
-                if (cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.solid_cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
-                if (idx & 1) info.scol_s0[hc] = val; else info.scol_g0[hc] = val;  // (scol_s0 = range end, for the moment)
-            }
-        }
-        __syncwarp();
-        len0 = info.cs[lane][LGPU_HB - 1] - info.cs[lane][0];
-        info.col_g0[lane] = info.cs[lane][0];
-        if (lane < LGPU_HCOLS - 32) { len1 = info.cs[32 + lane][LGPU_HB - 1] - info.cs[32 + lane][0]; info.col_g0[32 + lane] = info.cs[32 + lane][0]; }
-        if (v.n_solid) {
-            slen0 = info.scol_s0[lane] - info.scol_g0[lane];
-            if (lane < LGPU_HCOLS - 32) slen1 = info.scol_s0[32 + lane] - info.scol_g0[32 + lane];
-        } else {
-            info.scol_g0[lane] = 0;
-            if (lane < LGPU_HCOLS - 32) info.scol_g0[32 + lane] = 0;
-        }
-    } else {
-        const BrickDesc& d = v.brick_desc[w];
-        len0 = d.len[lane]; info.col_g0[lane] = d.g0[lane];
-        slen0 = d.slen[lane]; info.scol_g0[lane] = d.sg0[lane];
-        if (lane < LGPU_HCOLS - 32) {
-            len1 = d.len[32 + lane]; info.col_g0[32 + lane] = d.g0[32 + lane];
-            slen1 = d.slen[32 + lane]; info.scol_g0[32 + lane] = d.sg0[32 + lane];
-        }
-        mode = d.mode;
-    }
-    // stage slots: dummies, sand columns 0..35, solid columns 0..35
-    const int inc0 = warp_incl_scan_i(len0, lane);
-    const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-    const int inc1 = warp_incl_scan_i(len1, lane);
-    const int tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-    const int sinc0 = warp_incl_scan_i(slen0, lane);
-    const int stot0 = __shfl_sync(0xffffffffu, sinc0, 31);
-    const int sinc1 = warp_incl_scan_i(slen1, lane);
-    const int stot1 = __shfl_sync(0xffffffffu, sinc1, 31);
-    const int s0 = LGPU_DUMMY_SLOTS + inc0 - len0;
-    const int s1 = LGPU_DUMMY_SLOTS + tot0 + inc1 - len1;
-    const int solid_base = LGPU_DUMMY_SLOTS + tot0 + tot1;
-    const int ss0 = solid_base + sinc0 - slen0;
-    const int ss1 = solid_base + stot0 + sinc1 - slen1;
-    n_slots = solid_base + stot0 + stot1;
-    info.col_s0[lane] = s0; info.col_len[lane] = len0;
-    info.scol_s0[lane] = ss0; info.scol_len[lane] = slen0;
-    if (lane < LGPU_HCOLS - 32) {
-        info.col_s0[32 + lane] = s1; info.col_len[32 + lane] = len1;
-        info.scol_s0[32 + lane] = ss1; info.scol_len[32 + lane] = slen1;
-    }
-    __syncwarp();
-    // own runs
-    int own_len = 0;
-    if (BUILD) {
-        if (n_slots > v.stage_slots) mode = 2;
-        // boundaries -> stage slots
-        for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
-            const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
-            info.cs[hc][t] = info.col_s0[hc] + (info.cs[hc][t] - info.col_g0[hc]);
-        }
-        __syncwarp();
-        if (lane < LGPU_OWN_COLS) {
-            const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
-            const int a = info.cs[hc][1], e = info.cs[hc][LGPU_HB - 2];
-            own_len = e - a;
-            info.own_s0[lane] = a;
-            info.own_g0[lane] = info.col_g0[hc] + (a - info.col_s0[hc]);
-        }
-    } else {
-        if (lane < LGPU_OWN_COLS) {
-            const BrickDesc& d = v.brick_desc[w];
-            const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
-            own_len = d.own_len[lane];
-            const int a = d.own_g0[lane];
-            info.own_g0[lane] = a;
-            info.own_s0[lane] = info.col_s0[hc] + (a - info.col_g0[hc]);
-        }
-    }
-    const int oinc = warp_incl_scan_i(own_len, lane);
-    if (lane < LGPU_OWN_COLS) info.own_prefix[lane + 1] = oinc;
-    const int n_own = __shfl_sync(0xffffffffu, oinc, LGPU_OWN_COLS - 1);
-    if (lane == 0) {
-        info.own_prefix[0] = 0;
-        info.work = w; info.mode = mode; info.n_own = n_own; info.solid_base = solid_base;
-        info.cy0 = cy0; info.cx0 = cx0; info.cz0 = cz0;
-        info.next_chunk = 0;
-    }
-    if (BUILD) {
-        BrickDesc& d = v.brick_desc[w];
-        d.g0[lane] = info.col_g0[lane]; d.len[lane] = len0; d.sg0[lane] = info.scol_g0[lane]; d.slen[lane] = slen0;
-        if (lane < LGPU_HCOLS - 32) {
-            d.g0[32 + lane] = info.col_g0[32 + lane]; d.len[32 + lane] = len1;
-            d.sg0[32 + lane] = info.scol_g0[32 + lane]; d.slen[32 + lane] = slen1;
-        }
-        if (lane < LGPU_OWN_COLS) { d.own_g0[lane] = info.own_g0[lane]; d.own_len[lane] = own_len; }
-        if (lane == 0) { d.brick = brick; d.mode = mode; d.n_own = n_own; d.n_slots = n_slots; }
-    }
-    __syncwarp();  // the descriptor stores of all lanes are ordered before lane 0's arrive (release)
-    const bool copy = mode == 0;
-    if (lane == 0) mbar_expect_tx(full, copy ? 16u * (uint32_t)(n_slots - LGPU_DUMMY_SLOTS) : 0u);
-    __syncwarp();
-    if (copy) {
-        if (len0 > 0) bulk_g2s(stage + s0, src + info.col_g0[lane], 16u * (uint32_t)len0, full);
-        if (len1 > 0) bulk_g2s(stage + s1, src + info.col_g0[32 + lane], 16u * (uint32_t)len1, full);
-        if (slen0 > 0) bulk_g2s(stage + ss0, v.solid_pos + info.scol_g0[lane], 16u * (uint32_t)slen0, full);
-        if (slen1 > 0) bulk_g2s(stage + ss1, v.solid_pos + info.scol_g0[32 + lane], 16u * (uint32_t)slen1, full);
-    }
-}
-
-// Carves the dynamic shared memory of a brick kernel: stage buffers (16-byte aligned), then barriers + descriptors.
 struct BrickSmem {
-    float4* stage;     // LGPU_NSTAGE buffers of LGPU_STAGE_SLOTS slots
-    BrickShared* sh;
+    BrickSlot* slot;
+    BrickShared<BUILD>* sh;
 };
-__device__ __forceinline__ BrickSmem brick_smem(unsigned char* raw) {
-    BrickSmem m;
+template <bool BUILD>
+__device__ __forceinline__ BrickSmem<BUILD> brick_smem(unsigned char* raw) {
+    BrickSmem<BUILD> m;
     uintptr_t a = ((uintptr_t)raw + 127) & ~(uintptr_t)127;
-    m.stage = (float4*)a;
-    m.sh = (BrickShared*)(a + sizeof(float4) * LGPU_STAGE_SLOTS * LGPU_NSTAGE);
+    m.slot = (BrickSlot*)a;
+    m.sh = (BrickShared<BUILD>*)(a + sizeof(BrickSlot));
     return m;
 }
 
-// The whole persistent loop of a brick kernel.  chunk(info, stage_of_buffer, q, i, slot): called by the lanes of a
-// consumer warp that hold a particle of the current 32-particle chunk (no warp collectives inside): sorted slot i,
-// own run q, stage slot `slot`.  `cursor` = this pass's work counter (zero at launch).
-template <bool BUILD, class Chunk>
-__device__ __forceinline__ void brick_loop(const View& v, const float4* __restrict__ src, int* cursor, unsigned char* smem_raw, Chunk&& chunk) {
-    const BrickSmem m = brick_smem(smem_raw);
-    BrickShared& sh = *m.sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int b = 0; b < LGPU_NSTAGE; b++) { mbar_init(&sh.full[b], 1); mbar_init(&sh.empty[b], LGPU_NCW); }
-        mbar_fence_init();
-    }
-    if (tid < LGPU_NSTAGE * LGPU_DUMMY_SLOTS)  // far-away dummies: farther than any support radius
-        m.stage[(tid / LGPU_DUMMY_SLOTS) * LGPU_STAGE_SLOTS + (tid % LGPU_DUMMY_SLOTS)] = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.0f);
-    __syncthreads();
-    pdl_trigger();
-    if (warp == LGPU_NCW) {
-        // ---- producer ----
-        pdl_wait();  // everything this kernel reads was written by its predecessors on the stream
-        const int n_full = v.brick_ctl[0], n_work = n_full + v.brick_ctl[1];
-        for (int it = 0;; it++) {
-            const int b = it % LGPU_NSTAGE;
-            if (it >= LGPU_NSTAGE) mbar_wait(&sh.empty[b], ((it / LGPU_NSTAGE) - 1) & 1);
-            int w = 0;
-            if (lane == 0) w = atomicAdd(cursor, 1);
-            w = __shfl_sync(0xffffffffu, w, 0);
-            if (w >= n_work) {
-                if (lane == 0) { sh.info[b].work = -1; mbar_expect_tx(&sh.full[b], 0u); }
-                break;
-            }
-            brick_produce<BUILD>(v, w, n_full, sh.info[b], m.stage + (size_t)b * LGPU_STAGE_SLOTS, &sh.full[b], src);
-        }
-    } else {
-        // ---- consumers ----
-        for (int it = 0;; it++) {
-            const int b = it % LGPU_NSTAGE;
-            mbar_wait(&sh.full[b], (it / LGPU_NSTAGE) & 1);
-            BrickInfo& info = sh.info[b];
-            if (info.work < 0) break;
-            const int n_own = info.n_own;
-            const float4* stage = m.stage + (size_t)b * LGPU_STAGE_SLOTS;
-            for (;;) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&info.next_chunk, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                const int p0 = c * 32;
-                if (p0 >= n_own) break;
-                int q = 0;  // own run of the chunk's first particle (the same for all lanes), then of the lane's
+// own particle number p of a brick -> own run q
+__device__ __forceinline__ int brick_run_of(const BrickDesc& d, int p) {
+    int q = 0;
 #pragma unroll
-                for (int s = LGPU_OWN_COLS / 2; s > 0; s >>= 1) if (info.own_prefix[q + s] <= p0) q += s;
-                const int p = p0 + lane;
-                if (p < n_own) {
-                    while (info.own_prefix[q + 1] <= p) q++;
-                    const int off = p - info.own_prefix[q];
-                    chunk(info, stage, q, info.own_g0[q] + off, info.own_s0[q] + off);
-                }
-                __syncwarp();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty[b]);
-        }
-    }
+    for (int s = LGPU_OWN_COLS / 2; s > 0; s >>= 1) if (d.own_prefix[q + s] <= p) q += s;
+    return q;
 }
 
-// ------------------------------------------------------------------------------------------
-// Table rows
-// ------------------------------------------------------------------------------------------
-// The whole row (MG groups of four codes) is loaded up front so that the table traffic is in flight before the
-// first neighbour is gathered.  PAD: the row is processed in whole groups of four.  The padding codes of a SAND
-// table are 0 = a far-away dummy (no contact); those of a FLUID table are the particle's own slot, whose zero
-// separation makes every term of the branch-free fluid bodies vanish (lgpu_fluid.cu).
-template <int MG>
-struct TableRow {
-    uint2 w[MG];
-    // groups [0, EARLY) unconditionally (stale codes beyond the list are never replayed), the rest once cnt is known
-    template <int EARLY> __device__ __forceinline__ void load_early(const View& v, int i) {
-        const uint2* col = v.nbr16 + i;
-#pragma unroll
-        for (int g = 0; g < EARLY; g++) w[g] = col[(size_t)g * v.cap];
-    }
-    template <int EARLY> __device__ __forceinline__ void load_rest(const View& v, int i, int cnt) {
-        const uint2* col = v.nbr16 + i;
-        const int ng = (cnt + 3) >> 2;
-#pragma unroll
-        for (int g = EARLY; g < MG; g++) {
-            w[g] = make_uint2(0u, 0u);
-            if (g < ng) w[g] = col[(size_t)g * v.cap];
-        }
-    }
+// What a consumer lane knows about its particle while it works on a chunk.
+struct Chunk {
+    const BrickDesc* d;
+    const unsigned short (*cs)[LGPU_HB];   // table build: stage slot at every cell boundary of every halo column
+    uint32_t stage_addr;   // shared address of the slot's staged positions
+    const float4* stage;
+    uint32_t row_addr;     // shared address of the lane's first table group (groups are `row_stride` bytes apart)
+    uint32_t row_stride;
+    uint2* meta;           // the lane's meta word pair in the slot's table block (table build: to be written)
+    int p;                 // own particle number in the brick
+    int q;                 // own run of the particle (table build and re-walking bricks; -1 otherwise)
+    int i;                 // sorted slot
+    int slot;              // stage slot
+    int word;              // list length | LGPU_CNT_* (solver passes)
 };
 
-// code number k of a row held in registers (k is not a constant; a switch keeps the row in registers,
-// an indexed or select-chain formulation makes the compiler move it to local memory)
-__device__ __forceinline__ uint32_t row_code_reg(const TableRow<8>& row, int k) {
-    uint32_t pair;
-    switch (k >> 1) {
-        case 0: pair = row.w[0].x; break;  case 1: pair = row.w[0].y; break;
-        case 2: pair = row.w[1].x; break;  case 3: pair = row.w[1].y; break;
-        case 4: pair = row.w[2].x; break;  case 5: pair = row.w[2].y; break;
-        case 6: pair = row.w[3].x; break;  case 7: pair = row.w[3].y; break;
-        case 8: pair = row.w[4].x; break;  case 9: pair = row.w[4].y; break;
-        case 10: pair = row.w[5].x; break; case 11: pair = row.w[5].y; break;
-        case 12: pair = row.w[6].x; break; case 13: pair = row.w[6].y; break;
-        case 14: pair = row.w[7].x; break; default: pair = row.w[7].y; break;
-    }
-    return (k & 1) ? pair >> 16 : pair & 0xffffu;
+__device__ __forceinline__ void atom_max_shared(int* p, int v) {
+    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-// replays a register-resident row: body(pj, code, k), pj = stage[code]
-template <bool PAD, int MG, class Body>
-__device__ __forceinline__ void replay_row(const TableRow<MG>& row, uint32_t stage_addr, int cnt, Body&& body) {
-    const int ng = (cnt + 3) >> 2;
-#pragma unroll
-    for (int g = 0; g < MG; g++) {
-        if (g < ng) {
-            const uint32_t code[4] = {row.w[g].x & 0xffffu, row.w[g].x >> 16, row.w[g].y & 0xffffu, row.w[g].y >> 16};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int k = 4 * g + q;
-                if (!PAD && k >= cnt) break;
-                body(lds128(slot_addr(stage_addr, code[q])), code[q], k);
+// The brick loop of a staged kernel (see the top of this file).
+//   BUILD  = table build: chunk(ck) fills the lane's row in the slot's table block, and the block stores the finished
+//            table block to global memory with one bulk copy.
+//   !BUILD = solver pass: the table block is copied in with the positions.
+// chunk is called by the lanes that hold a particle (no warp collectives inside) and returns the number of table
+// groups of the row it has written (table build; 0 otherwise).
+// Work item w of the substep's brick list goes to block w % gridDim.x (bricks of one kind cost the same; the list
+// holds the full bricks first and the sparse ones last, so the blocks' shares are even).
+template <bool BUILD, class ChunkFn>
+__device__ __forceinline__ void brick_loop(const View& v, const float4* __restrict__ src, unsigned char* smem_raw, ChunkFn&& chunk) {
+    const BrickSmem<BUILD> m = brick_smem<BUILD>(smem_raw);
+    BrickShared<BUILD>& sh = *m.sh;
+    BrickSlot& slot = *m.slot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t kRecBytes = (uint32_t)sizeof(BrickRingEntry<BUILD>);
+    static_assert(sizeof(BrickRingEntry<true>) == sizeof(BrickRec), "record layout");
+    if (tid == 0) {
+        mbar_init(&sh.full, 1); mbar_init(&sh.dfull[0], 1); mbar_init(&sh.dfull[1], 1);
+        sh.maxg = 0;
+        mbar_fence_init();
+    }
+    if (tid < LGPU_DUMMY_SLOTS) slot.pos[tid] = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.0f);  // far-away dummies: farther than any support radius
+    __syncthreads();
+    pdl_trigger();
+    pdl_wait();  // everything this kernel reads was written by its predecessors on the stream
+    const int n_full = v.brick_ctl[0], n_work = n_full + v.brick_ctl[1];
+    const int G = gridDim.x;
+    auto fetch_desc = [&](int wj, int e) {  // (thread 0)
+        if (wj < n_work) {
+            mbar_expect_tx(&sh.dfull[e], kRecBytes);
+            bulk_g2s(&sh.ring[e], &v.brick_rec[rec_of_work(v, wj, n_full)], kRecBytes, &sh.dfull[e]);
+        }
+    };
+    if (tid == 0) fetch_desc(blockIdx.x, 0);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += G, it++) {
+        const int e = it & 1;
+        mbar_wait(&sh.dfull[e], (uint32_t)(it >> 1) & 1u);
+        const BrickDesc& d = sh.ring[e].d;
+        if (tid == 0) {
+            fetch_desc(w + G, e ^ 1);  // (its previous user, brick it - 1, is done: everybody passed the barrier below)
+            mbar_expect_tx(&sh.full, brick_stage_bytes<!BUILD>(d));
+        }
+        if (lane == 0) brick_stage<!BUILD>(v, d, slot, &sh.full, src, warp);
+        const int n_own = d.n_own;
+        Chunk ck;
+        ck.d = &d; ck.stage = slot.pos; ck.stage_addr = smem_u32(slot.pos);
+        if constexpr (BUILD) ck.cs = sh.ring[e].cs; else ck.cs = nullptr;
+        ck.row_stride = 8u * (uint32_t)d.n_pad;
+        const bool from_meta = !BUILD && d.mode == 0;
+        mbar_wait(&sh.full, (uint32_t)it & 1u);
+        int mg = 0;
+        for (int p = tid; p < n_own; p += LGPU_BRICK_THREADS) {  // chunks of 32 own particles: warp, warp + LGPU_BRICK_WARPS, ...
+            ck.p = p; ck.meta = slot.tab + p; ck.row_addr = smem_u32(slot.tab + d.n_pad + p);
+            if (from_meta) {
+                const uint2 mw = lds64(smem_u32(slot.tab + p));
+                ck.i = (int)mw.x; ck.word = (int)mw.y & ~LGPU_CNT_SLOT_MASK; ck.slot = ((int)mw.y & LGPU_CNT_SLOT_MASK) >> LGPU_CNT_SLOT_SHIFT; ck.q = -1;
+            } else {
+                const int q = brick_run_of(d, p);
+                const int off = p - d.own_prefix[q];
+                ck.q = q; ck.i = d.own_g0[q] + off; ck.slot = d.own_s0[q] + off;
+                ck.word = BUILD ? 0 : v.nbr_cnt[ck.i];
             }
+            mg = max(mg, chunk(ck));
+        }
+        if (BUILD && d.mode == 0) {
+            mg = __reduce_max_sync(0xffffffffu, mg);
+            if (lane == 0 && mg > 0) atom_max_shared(&sh.maxg, mg);
+            fence_proxy_async();  // this thread's rows are visible to the bulk store of the block
+        }
+        __syncthreads();  // the brick is done: slot and descriptor may be reused
+        if (BUILD && d.mode == 0) {
+            if (tid == 0) {
+                const int g = sh.maxg;
+                v.brick_rec[d.work].d.maxg = g;
+                bulk_s2g(v.nbr16 + d.tab_off, slot.tab, 8u * (uint32_t)d.n_pad * (uint32_t)(1 + g));
+                bulk_commit();
+                bulk_wait_read();
+                sh.maxg = 0;
+            }
+            __syncthreads();  // (the store has read the block)
         }
     }
+    if (BUILD && tid == 0) bulk_wait_all();
 }
 
-// any table width: groups are loaded one ahead
+// Replays the lane's table row from the slot's table block: body(pj, code, k), pj = stage[code].  PAD: the row is
+// processed in whole groups of four.  The padding codes of a SAND table are 0 = a far-away dummy (no contact); those of
+// a FLUID table are the particle's own slot, whose zero separation makes every term of the branch-free fluid bodies
+// vanish (lgpu_fluid.cu).  One LDS.64 per group (the next group's codes are loaded one ahead), one LDS.128 per code.
 template <bool PAD, class Body>
-__device__ __forceinline__ void replay_table(const View& v, uint32_t stage_addr, int i, int cnt, Body&& body) {
-    const uint2* col = v.nbr16 + i;
+__device__ __forceinline__ void replay_row(const Chunk& ck, int cnt, Body&& body) {
     const int ng = (cnt + 3) >> 2;
-    uint2 w = ng > 0 ? col[0] : make_uint2(0u, 0u);
+    if (ng == 0) return;
+#ifdef LGPU_ROT
+    // Lanes start at different groups of their rows (the order of the terms is free within the stated tolerance):
+    // neighbouring lanes have similar lists, and staggering them spreads a step's LDS.128s over the bank groups.
+    int gi = (int)(threadIdx.x & LGPU_ROT);
+    while (gi >= ng) gi -= ng;
+#else
+    int gi = 0;
+#endif
+    uint2 w = lds64(ck.row_addr + (uint32_t)gi * ck.row_stride);
     for (int g = 0; g < ng; g++) {
-        uint2 wn = make_uint2(0u, 0u);
-        if (g + 1 < ng) wn = col[(size_t)(g + 1) * v.cap];
+        const int gc = gi;
+        gi = gi + 1 == ng ? 0 : gi + 1;
+        uint2 wn = w;
+        if (g + 1 < ng) wn = lds64(ck.row_addr + (uint32_t)gi * ck.row_stride);
         const uint32_t code[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int k = 4 * g + q;
+            const int k = 4 * gc + q;
             if (!PAD && k >= cnt) break;
-            body(lds128(slot_addr(stage_addr, code[q])), code[q], k);
+            body(lds128(slot_addr(ck.stage_addr, code[q])), code[q], k);
         }
         w = wn;
     }
 }
 
+// code number k of the lane's row
+__device__ __forceinline__ uint32_t row_code(const Chunk& ck, int k) {
+    return lds16(ck.row_addr + (uint32_t)(k >> 2) * ck.row_stride + (uint32_t)(k & 3) * 2u);
+}
+
 // sorted sand slot (>= 0) or ~(sorted solid slot) (< 0) of a table code of a brick (tests: lgpu_dump)
-__device__ __forceinline__ int decode_code(const BrickInfo& info, int code) {
+__device__ __forceinline__ int decode_code(const BrickDesc& d, int code) {
     for (int hc = 0; hc < LGPU_HCOLS; hc++) {
-        if (code >= info.col_s0[hc] && code < info.col_s0[hc] + info.col_len[hc]) return info.col_g0[hc] + (code - info.col_s0[hc]);
-        if (code >= info.scol_s0[hc] && code < info.scol_s0[hc] + info.scol_len[hc]) return ~(info.scol_g0[hc] + (code - info.scol_s0[hc]));
+        if (code >= d.col[hc].s0 && code < d.col[hc].s0 + d.col[hc].len) return d.col[hc].g0 + (code - d.col[hc].s0);
+        if (code >= d.scol[hc].s0 && code < d.scol[hc].s0 + d.scol[hc].len) return ~(d.scol[hc].g0 + (code - d.scol[hc].s0));
     }
     return 0;
 }

@@ -92,29 +92,30 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
 }
 
 template <class P, bool LAST>
-__global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_sand_iteration(const __grid_constant__ View v, const __grid_constant__ SandParams sp,
-                                                                          const float4* cur, float4* next, int* cursor) {
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_iteration(const __grid_constant__ View v, const __grid_constant__ SandParams sp,
+                                                                          const float4* cur, float4* next) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, cursor, smem_raw, [&](const BrickInfo& info, const float4* stage, int, int i, int slot) {
-        const int word = v.nbr_cnt[i];
+    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+        const int i = ck.i, word = ck.word;
+        const int mode = ck.d->mode;
         if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
             if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
-            return;
+            return 0;
         }
         const Geom& g = v.g;
-        const uint32_t stage_addr = smem_u32(stage);
-        const float4 ci = info.mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)slot)) : cur[i];
+        const uint32_t stage_addr = ck.stage_addr;
+        const float4 ci = mode == 0 ? lds128(slot_addr(stage_addr, (uint32_t)ck.slot)) : cur[i];
         const F3 pi = f3(ci);
         const F3 xi_old = f3(v.pos[i]);
         F3 deltap = f3(0.0f, 0.0f, 0.0f);
         bool touched = false;
-        if (!(word & LGPU_CNT_WALK) && info.mode == 0) {
+        if (!(word & LGPU_CNT_WALK) && mode == 0) {
             // Looped replay (one group of four per iteration, the next group's codes loaded one ahead): the
             // contact body is long, and unrolling it over the whole row made the kernel ~300 KB of code that
             // missed the instruction cache a quarter of the time.  The old position of a sand neighbour in
             // contact is read from the sorted storage at the slot its staged x* carries in the w lane.
-            const uint32_t solid_base = (uint32_t)info.solid_base;
-            replay_table<true>(v, stage_addr, i, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+            const uint32_t solid_base = (uint32_t)ck.d->solid_base;
+            replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
                 const bool is_sand = code < solid_base;
                 sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
             });
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, 2) k_sand_iteration(const 
             v.flags_in[i] = v.flags[i];
             v.orig_in[i] = v.orig[i];
         }
+        return 0;
     });
 }
 
@@ -165,7 +167,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     sp.credits = p.credits;
     int K = p.iterations < 1 ? 1 : p.iterations;
     if (1 + K > LGPU_MAX_PASSES) K = LGPU_MAX_PASSES - 1;
-    const int grid = 2 * c->num_sms;
+    const int grid = LGPU_CTAS_PER_SM * c->num_sms;
     const size_t smem = LGPU_BRICK_SMEM;
     const float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
@@ -174,14 +176,13 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;
-        int* cursor = c->brick_ctl + 8 + c->pass;
         lgpu_mark(c, 7);
         if (p.exact_math) {
-            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Exact, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
-            else CUDA_TRY(launch_pdl(k_sand_iteration<Exact, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Exact, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Exact, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
         } else {
-            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Fast, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
-            else CUDA_TRY(launch_pdl(k_sand_iteration<Fast, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, cursor));
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Fast, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Fast, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
         }
         c->pass++; c->launches++;
         if (!last && lgpu_slab_active(c)) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
