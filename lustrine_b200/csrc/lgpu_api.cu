@@ -141,8 +141,12 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
     // table blocks: a meta word and LGPU_MG code words per own particle, rows padded to an even count per brick
-    const size_t nonempty = (size_t)(c->NB < c->cap ? c->NB : c->cap);
+    // (a non-empty brick part holds at least one particle; a brick has at most LGPU_BZ parts)
+    const size_t nonempty = (size_t)((size_t)c->NB * LGPU_BZ < (size_t)c->cap ? (size_t)c->NB * LGPU_BZ : (size_t)c->cap);
     CUDA_TRY(dalloc(&c->nbr16, (cap + nonempty + 2) * (size_t)(1 + LGPU_MG))); CUDA_TRY(dalloc(&c->nbr_cnt, cap));
+    // spill chunks for the tails of lists longer than the table width: one per four particles (or at least 1024)
+    c->spill_cap = (int)(cap / 4 > 1024 ? cap / 4 : 1024);
+    CUDA_TRY(dalloc(&c->nbr_spill, (size_t)c->spill_cap * (LGPU_SPILL / 4))); CUDA_TRY(dalloc(&c->nbr_ovf, cap));
     // a non-empty brick holds at least one particle, and there are at most NB bricks
     CUDA_TRY(dalloc(&c->brick_ctl, (size_t)(8 + LGPU_MAX_PASSES)));
     c->rec_cap = (int)nonempty + 1;
@@ -178,7 +182,7 @@ extern "C" void lgpu_destroy(lgpu_ctx* c) {
     cudaFree(c->key_in); cudaFree(c->rank_in); cudaFree(c->tmp_id); cudaFree(c->key);
     cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->scan_state);
     cudaFree(c->solid_pos); cudaFree(c->solid_pos_unsorted); cudaFree(c->solid_orig); cudaFree(c->solid_cell_start);
-    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->brick_ctl); cudaFree(c->brick_rec); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
+    cudaFree(c->nbr16); cudaFree(c->nbr_cnt); cudaFree(c->nbr_spill); cudaFree(c->nbr_ovf); cudaFree(c->brick_ctl); cudaFree(c->brick_rec); cudaFree(c->lambda); cudaFree(c->density); cudaFree(c->lambda_head);
     cudaFree(c->counters); cudaFree(c->d_stage);
     lgpu_slab_free(c);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -201,7 +205,7 @@ View lgpu_make_view(lgpu_ctx* c) {
     v.key_in = c->key_in; v.rank_in = c->rank_in; v.tmp_id = c->tmp_id; v.key = c->key;
     v.cell_count = c->cell_count; v.cell_start = c->cell_start;
     v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
-    v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt;
+    v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt; v.nbr_spill = c->nbr_spill; v.nbr_ovf = c->nbr_ovf; v.spill_cap = c->spill_cap;
     v.nbY = c->nbY; v.nbX = c->nbX; v.nbZ = c->nbZ; v.NB = c->NB; v.stage_slots = c->stage_slots;
     v.brick_ctl = c->brick_ctl; v.brick_rec = c->brick_rec; v.rec_cap = c->rec_cap;
     v.lambda = c->lambda; v.density = c->density; v.lambda_head = c->lambda_head;

@@ -68,6 +68,19 @@ __device__ __noinline__ float3 deltap_walk(const View& v, const FluidParams& fp,
     return make_float3(f.x, f.y, f.z);
 }
 
+// entries 32 .. cnt-1 of a list longer than the table width (spill chunk)
+template <class P, bool POLY6>
+__device__ __noinline__ float3 deltap_spill(const View& v, const FluidParams& fp, const Chunk& ck, int cnt, F3 xi, float li, float3 f0) {
+    const Geom& g = v.g;
+    const bool literal = fp.literal_lambda_index != 0;
+    F3 f = f3(f0.x, f0.y, f0.z);
+    replay_spill<false>(v, ck, cnt, [&](float4 pj, uint32_t, int t) {
+        const float lj = literal ? (t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f) : pj.w;
+        deltap_pair<P, POLY6>(g, fp, xi, f3(pj), li, lj, f);
+    });
+    return make_float3(f.x, f.y, f.z);
+}
+
 // ---- delta-p + box collision (+ commit on the last iteration) ----
 // The staged neighbourhood holds (x*_j, lambda_j) per slot (the lambda pass stored lambda in the w lane; the w lane
 // of a solid is 0, which is the lambda the reference reads for it).
@@ -126,6 +139,10 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
                     const float dw = fmaf(-fp.s_corr_k, xt2 * xt2, li + pj.w) * cf - wf;
                     fx = fmaf(dw, dx, fx); fy = fmaf(dw, dy, fy); fz = fmaf(dw, dz, fz);
                 }
+                if (cnt > 4 * LGPU_MG) {
+                    const float3 f = deltap_spill<Fast, false>(v, fp, ck, cnt, xi, li, make_float3(fx, fy, fz));
+                    fx = f.x; fy = f.y; fz = f.z;
+                }
             } else {
                 const float3 f = deltap_walk<Fast, false>(v, fp, cur, i, xi, li);
                 fx = f.x; fy = f.y; fz = f.z;
@@ -143,6 +160,10 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
                     deltap_pair<P, POLY6>(g, fp, xi, f3(pj), li, lj, f);
                 });
                 fx = f.x; fy = f.y; fz = f.z;
+                if (cnt > 4 * LGPU_MG) {
+                    const float3 f2 = deltap_spill<P, POLY6>(v, fp, ck, cnt, xi, li, make_float3(fx, fy, fz));
+                    fx = f2.x; fy = f2.y; fz = f2.z;
+                }
             } else {
                 const float3 f = deltap_walk<P, POLY6>(v, fp, cur, i, xi, li);
                 fx = f.x; fy = f.y; fz = f.z;

@@ -156,6 +156,14 @@ __device__ __noinline__ float2 lambda_walk(const View& v, const FluidParams& fp,
     return make_float2(a.rho, lam);
 }
 
+// entries 32 .. cnt-1 of a list longer than the table width (spill chunk): the accumulator goes in and comes back by value
+template <class P, bool POLY6>
+__device__ __noinline__ LambdaAcc<P, POLY6> lambda_spill(const View& v, const FluidParams& fp, const Chunk& ck, int cnt, F3 xi, LambdaAcc<P, POLY6> acc) {
+    const Geom& g = v.g;
+    replay_spill<false>(v, ck, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
+    return acc;
+}
+
 // Density + lambda of ONE particle (src/Simulate.cpp:58-88) from its table row and the staged neighbourhood.
 // word = list length | LGPU_CNT_*; xi = the particle's own x*.  Writes rho_i, lambda_i, and lambda_i into the w lane of the
 // particle's own x* so that the delta-p pass gets (x*_j, lambda_j) in one LDS.128.
@@ -198,6 +206,13 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
                 const float dg = gt - gf;
                 gx = fmaf(-dg, dx, gx); gy = fmaf(-dg, dy, gy); gz = fmaf(-dg, dz, gz);
             }
+            if (cnt > 4 * LGPU_MG) {  // the tail of a long list, with the branches of the spline (LambdaAcc accumulates W/cubic_k)
+                LambdaAcc<Fast, false> t;
+                t.init();
+                t = lambda_spill<Fast, false>(v, fp, ck, cnt, xi, t);
+                acc += t.rho - (float)(cnt - 4 * LGPU_MG);
+                sum += t.sum; gx += t.gi.x; gy += t.gi.y; gz += t.gi.z;
+            }
             rho = fmaf(acc + (float)cnt, fp.mk, fp.mass * fp.W_zero);
             const float Ci = rho * fp.inv_rho0 - 1.0f;
             sum += gx * gx + gy * gy + gz * gz;
@@ -212,6 +227,7 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
             acc.init();
             const Geom& g = v.g;
             replay_row<false>(ck, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
+            if (cnt > 4 * LGPU_MG) acc = lambda_spill<P, POLY6>(v, fp, ck, cnt, xi, acc);
             lam = acc.finish(fp);
             rho = acc.rho;
         } else {

@@ -41,6 +41,7 @@
 #define LGPU_ROW_CAP 576         // own particles of a brick whose table block fits the block's shared memory (unit lattice: <= 539 at BZ = 7)
 #endif
 #define LGPU_MG 8                // table groups (of four 16-bit codes) per row: M = 32
+#define LGPU_SPILL 32            // codes of a spill chunk: a list of 33 .. 64 entries keeps its tail in one (global memory)
 #define LGPU_DUMMY_SLOTS 8       // stage slots 0..7: far-away dummies (padding of sand rows)
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
@@ -146,7 +147,7 @@ struct View {
     // bricks (lgpu_brick.cuh)
     int nbY, nbX, nbZ, NB;    // brick grid
     int stage_slots;          // stage capacity in use (<= LGPU_STAGE_SLOTS; test hook lgpu_set_stage_slots)
-    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [2] table words allocated
+    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [2] table words allocated, [3] spill chunks allocated
     BrickRec* brick_rec;      // non-empty bricks of this substep: full ones from the front, sparse ones from the back
     int rec_cap;
     // unsorted (pre-reorder) buffers, indexed by the storage slot of the previous step
@@ -166,6 +167,9 @@ struct View {
     // far-away dummies).
     uint2* nbr16;
     int* nbr_cnt;      // by sorted slot: list length | LGPU_CNT_* flags (dumps, re-walking bricks)
+    uint2* nbr_spill;  // spill chunks (LGPU_SPILL codes each): entries 32 .. 63 of the lists longer than the table width
+    int* nbr_ovf;      // by sorted slot: spill chunk of the particle (meaningful where the list is longer than M)
+    int spill_cap;     // spill chunks available
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;  // [0] key violations, [1] table overflows
 };
@@ -199,6 +203,9 @@ struct lgpu_ctx {
     int *solid_orig, *solid_cell_start;
     uint2* nbr16;
     int* nbr_cnt;
+    uint2* nbr_spill;
+    int* nbr_ovf;
+    int spill_cap;
     float *lambda, *density, *lambda_head;
     unsigned long long* counters;
     float4* pstar_final;  // where the last step left x* (for dumps)

@@ -16,7 +16,8 @@
 #define LGPU_DESC_WARPS 8
 __global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __grid_constant__ View v) {
     __shared__ BrickRec recs[LGPU_DESC_WARPS];
-    __shared__ int cs32[LGPU_DESC_WARPS][LGPU_HCOLS][LGPU_HB];
+    __shared__ int cs32[LGPU_DESC_WARPS][LGPU_HCOLS][LGPU_HB];   // sorted sand slot at every cell boundary of every halo column
+    __shared__ int ss32[LGPU_DESC_WARPS][LGPU_HCOLS][LGPU_HB];   // ... sorted solid slot
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int brick = blockIdx.x * LGPU_DESC_WARPS + wib;
     if (brick >= v.NB) return;
@@ -25,91 +26,123 @@ __global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __gri
     const int rem = brick - by * (v.nbX * v.nbZ);
     const int bx = rem / v.nbZ, bz = rem - bx * v.nbZ;
     const int cy0 = by * LGPU_BY, cx0 = bx * LGPU_BX, cz0 = bz * LGPU_BZ;
-    // own particles: the inner columns, cells cz0 .. cz0 + BZ - 1
-    int own_len = 0, own_a = 0;
+    // own particles of the whole brick: the inner columns, cells cz0 .. cz0 + BZ - 1
+    int own_all = 0;
     if (lane < LGPU_OWN_COLS) {
         const int cy = cy0 + lane / LGPU_BX, cx = cx0 + lane % LGPU_BX;
         if (cy < g.gY && cx < g.gX) {
             const int base = cy * g.gXZ + cx * g.gZ;
-            own_a = v.cell_start[base + min(cz0, g.gZ)];
-            own_len = v.cell_start[base + min(cz0 + LGPU_BZ, g.gZ)] - own_a;
+            own_all = v.cell_start[base + min(cz0 + LGPU_BZ, g.gZ)] - v.cell_start[base + min(cz0, g.gZ)];
         }
     }
-    const int oinc = warp_incl_scan_i(own_len, lane);
-    const int n_own = __shfl_sync(0xffffffffu, oinc, LGPU_OWN_COLS - 1);
-    if (n_own == 0) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) own_all += __shfl_xor_sync(0xffffffffu, own_all, o);
+    if (own_all == 0) return;
     BrickRec& rec = recs[wib];
     BrickDesc& d = rec.d;
     int (*cs)[LGPU_HB] = cs32[wib];
-    // sorted slot at every cell boundary of every halo column (cells cz0-1 .. cz0+BZ, clipped to the grid; the
-    // cell offsets are linear in the cell id with z fastest, so boundary gZ of a column is the next column's start)
+    int (*ss)[LGPU_HB] = ss32[wib];
+    // boundaries of the cells cz0-1 .. cz0+BZ of every halo column, clipped to the grid (the cell offsets are linear
+    // in the cell id with z fastest, so boundary gZ of a column is the next column's start)
     for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
         const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
         const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
-        int val = 0;
-        if (cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
-        cs[hc][t] = val;
-    }
-    for (int idx = lane; idx < 2 * LGPU_HCOLS; idx += 32) {
-        const int hc = idx >> 1, t = (idx & 1) * (LGPU_HB - 1);
-        const int cy = cy0 - 1 + hc / LGPU_HX, cx = cx0 - 1 + hc % LGPU_HX;
-        int val = 0;
-        if (v.n_solid && cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) val = v.solid_cell_start[cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ)];
-        if (idx & 1) d.scol[hc].len = val; else d.scol[hc].g0 = val;  // (len = range END for the moment)
+        int val = 0, sval = 0;
+        if (cy >= 0 && cy < g.gY && cx >= 0 && cx < g.gX) {
+            const int cell = cy * g.gXZ + cx * g.gZ + min(max(cz0 - 1 + t, 0), g.gZ);
+            val = v.cell_start[cell];
+            if (v.n_solid) sval = v.solid_cell_start[cell];
+        }
+        cs[hc][t] = val; ss[hc][t] = sval;
     }
     __syncwarp();
-    // lane: halo column `lane`; lanes 0..3 also column 32 + lane
+    // A brick whose neighbourhood or table block does not fit a block's shared memory is cut along z into 2, 4, ... parts
+    // (dense packings, pile-ups); only a part that still does not fit re-walks the stencil (mode 2).
     const int hi = 32 + lane;
     const bool two = lane < LGPU_HCOLS - 32;
-    const int len0 = cs[lane][LGPU_HB - 1] - cs[lane][0];
-    const int len1 = two ? cs[hi][LGPU_HB - 1] - cs[hi][0] : 0;
-    const int slen0 = d.scol[lane].len - d.scol[lane].g0;
-    const int slen1 = two ? d.scol[hi].len - d.scol[hi].g0 : 0;
-    // stage slots: dummies, sand columns 0..35, solid columns 0..35
-    const int inc0 = warp_incl_scan_i(len0, lane), tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-    const int inc1 = warp_incl_scan_i(len1, lane), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-    const int sinc0 = warp_incl_scan_i(slen0, lane), stot0 = __shfl_sync(0xffffffffu, sinc0, 31);
-    const int sinc1 = warp_incl_scan_i(slen1, lane), stot1 = __shfl_sync(0xffffffffu, sinc1, 31);
-    const int solid_base = LGPU_DUMMY_SLOTS + tot0 + tot1;
-    const int n_slots = solid_base + stot0 + stot1;
-    d.col[lane].g0 = cs[lane][0]; d.col[lane].len = len0; d.col[lane].s0 = LGPU_DUMMY_SLOTS + inc0 - len0; d.col[lane].pad = 0;
-    d.scol[lane].len = slen0; d.scol[lane].s0 = solid_base + sinc0 - slen0; d.scol[lane].pad = 0;
-    if (two) {
-        d.col[hi].g0 = cs[hi][0]; d.col[hi].len = len1; d.col[hi].s0 = LGPU_DUMMY_SLOTS + tot0 + inc1 - len1; d.col[hi].pad = 0;
-        d.scol[hi].len = slen1; d.scol[hi].s0 = solid_base + stot0 + sinc1 - slen1; d.scol[hi].pad = 0;
+    int parts = 1, nz = LGPU_BZ;
+    for (;;) {
+        bool fits = true;
+        for (int za = 0; za < LGPU_BZ; za += nz) {
+            const int zb = min(za + nz, LGPU_BZ);   // part = own cells za .. zb-1 of the brick, halo cells za-1 .. zb
+            int slots = cs[lane][zb + 2] - cs[lane][za] + ss[lane][zb + 2] - ss[lane][za];
+            if (two) slots += cs[hi][zb + 2] - cs[hi][za] + ss[hi][zb + 2] - ss[hi][za];
+            int own = 0;
+            if (lane < LGPU_OWN_COLS) {
+                const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
+                own = cs[hc][zb + 1] - cs[hc][za + 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { slots += __shfl_xor_sync(0xffffffffu, slots, o); own += __shfl_xor_sync(0xffffffffu, own, o); }
+            if (slots + LGPU_DUMMY_SLOTS > v.stage_slots || ((own + 1) & ~1) > LGPU_ROW_CAP) fits = false;
+        }
+        if (fits || nz == 1) break;
+        nz = (nz + 1) >> 1; parts++;
     }
-    __syncwarp();
-    const int n_pad = (n_own + 1) & ~1;
-    const int mode = (n_slots > v.stage_slots || n_pad > LGPU_ROW_CAP) ? 2 : 0;
-    // boundaries -> stage slots (16 bits; a brick whose neighbourhood does not fit a ring slot never looks at them)
-    for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
-        const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
-        rec.cs[hc][t] = (unsigned short)min(d.col[hc].s0 + (cs[hc][t] - d.col[hc].g0), 65535);
+    for (int za = 0; za < LGPU_BZ; za += nz) {
+        const int zb = min(za + nz, LGPU_BZ);
+        // own runs of the part
+        int own_len = 0, own_a = 0;
+        if (lane < LGPU_OWN_COLS) {
+            const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
+            own_a = cs[hc][za + 1];
+            own_len = cs[hc][zb + 1] - own_a;
+        }
+        const int oinc = warp_incl_scan_i(own_len, lane);
+        const int n_own = __shfl_sync(0xffffffffu, oinc, LGPU_OWN_COLS - 1);
+        if (n_own == 0) continue;
+        // lane: halo column `lane`; lanes 0..3 also column 32 + lane.  Stage slots: dummies, sand columns 0..35, solid columns 0..35
+        const int len0 = cs[lane][zb + 2] - cs[lane][za];
+        const int len1 = two ? cs[hi][zb + 2] - cs[hi][za] : 0;
+        const int slen0 = ss[lane][zb + 2] - ss[lane][za];
+        const int slen1 = two ? ss[hi][zb + 2] - ss[hi][za] : 0;
+        const int inc0 = warp_incl_scan_i(len0, lane), tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+        const int inc1 = warp_incl_scan_i(len1, lane), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+        const int sinc0 = warp_incl_scan_i(slen0, lane), stot0 = __shfl_sync(0xffffffffu, sinc0, 31);
+        const int sinc1 = warp_incl_scan_i(slen1, lane), stot1 = __shfl_sync(0xffffffffu, sinc1, 31);
+        const int solid_base = LGPU_DUMMY_SLOTS + tot0 + tot1;
+        const int n_slots = solid_base + stot0 + stot1;
+        __syncwarp();  // (the previous part's record has been written out)
+        d.col[lane].g0 = cs[lane][za]; d.col[lane].len = len0; d.col[lane].s0 = LGPU_DUMMY_SLOTS + inc0 - len0; d.col[lane].pad = 0;
+        d.scol[lane].g0 = ss[lane][za]; d.scol[lane].len = slen0; d.scol[lane].s0 = solid_base + sinc0 - slen0; d.scol[lane].pad = 0;
+        if (two) {
+            d.col[hi].g0 = cs[hi][za]; d.col[hi].len = len1; d.col[hi].s0 = LGPU_DUMMY_SLOTS + tot0 + inc1 - len1; d.col[hi].pad = 0;
+            d.scol[hi].g0 = ss[hi][za]; d.scol[hi].len = slen1; d.scol[hi].s0 = solid_base + stot0 + sinc1 - slen1; d.scol[hi].pad = 0;
+        }
+        __syncwarp();
+        const int n_pad = (n_own + 1) & ~1;
+        const int mode = (n_slots > v.stage_slots || n_pad > LGPU_ROW_CAP) ? 2 : 0;
+        // boundaries -> stage slots (16 bits; a part whose neighbourhood does not fit never looks at them); the boundaries
+        // past the part's last halo cell repeat its end, so that the build's cell search never runs past the part
+        for (int idx = lane; idx < LGPU_HCOLS * LGPU_HB; idx += 32) {
+            const int hc = idx / LGPU_HB, t = idx - hc * LGPU_HB;
+            const int tt = min(za + t, zb + 2);
+            rec.cs[hc][t] = (unsigned short)min(d.col[hc].s0 + (cs[hc][tt] - d.col[hc].g0), 65535);
+        }
+        if (lane < LGPU_OWN_COLS) {
+            const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
+            d.own_g0[lane] = own_a;
+            d.own_s0[lane] = d.col[hc].s0 + (own_a - d.col[hc].g0);
+            d.own_prefix[lane + 1] = oinc;
+        }
+        int w = 0;
+        if (lane == 0) {
+            const bool full = n_own >= 256;
+            const int k = atomicAdd(&v.brick_ctl[full ? 0 : 1], 1);
+            w = full ? k : v.rec_cap - 1 - k;   // record index; the work index of a sparse brick is n_full + k (see rec_of_work)
+            d.own_prefix[0] = 0;
+            d.brick = brick; d.mode = mode; d.n_own = n_own; d.n_slots = n_slots;
+            d.solid_base = solid_base; d.maxg = 0; d.n_pad = n_pad;
+            d.tab_off = mode == 0 ? atomicAdd(&v.brick_ctl[2], n_pad * (1 + LGPU_MG)) : 0;
+            d.cy0 = cy0; d.cx0 = cx0; d.cz0 = cz0 + za;
+            d.work = w;  // (= the record index)
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
+        __syncwarp();
+        int4* gd = reinterpret_cast<int4*>(&v.brick_rec[w]);
+        const int4* sd = reinterpret_cast<const int4*>(&rec);
+        for (int t = lane; t < (int)(sizeof(BrickRec) / 16); t += 32) gd[t] = sd[t];
     }
-    // own runs: cells 1 .. BZ of the inner halo columns
-    if (lane < LGPU_OWN_COLS) {
-        const int hc = (lane / LGPU_BX + 1) * LGPU_HX + (lane % LGPU_BX) + 1;
-        d.own_g0[lane] = own_a;
-        d.own_s0[lane] = d.col[hc].s0 + (own_a - d.col[hc].g0);
-        d.own_prefix[lane + 1] = oinc;
-    }
-    int w = 0;
-    if (lane == 0) {
-        const bool full = n_own >= 256;
-        const int k = atomicAdd(&v.brick_ctl[full ? 0 : 1], 1);
-        w = full ? k : v.rec_cap - 1 - k;   // record index; the work index of a sparse brick is n_full + k (see rec_of_work)
-        d.own_prefix[0] = 0;
-        d.brick = brick; d.mode = mode; d.n_own = n_own; d.n_slots = n_slots;
-        d.solid_base = solid_base; d.maxg = 0; d.n_pad = n_pad;
-        d.tab_off = mode == 0 ? atomicAdd(&v.brick_ctl[2], n_pad * (1 + LGPU_MG)) : 0;
-        d.cy0 = cy0; d.cx0 = cx0; d.cz0 = cz0;
-        d.work = w;  // (= the record index)
-    }
-    w = __shfl_sync(0xffffffffu, w, 0);
-    __syncwarp();
-    int4* gd = reinterpret_cast<int4*>(&v.brick_rec[w]);
-    const int4* sd = reinterpret_cast<const int4*>(&rec);
-    for (int t = lane; t < (int)(sizeof(BrickRec) / 16); t += 32) gd[t] = sd[t];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -120,21 +153,36 @@ __global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __gri
 // density + lambda pass.
 struct RowWriter {
     uint32_t base, stride;    // shared address of the lane's first group; bytes between groups
-    int M, cnt;
-    __device__ __forceinline__ void init(const View& v, const Chunk& ck) {
+    int cnt;
+    unsigned short* spill;    // the list's spill chunk (entries M .. M + LGPU_SPILL - 1), once it has one
+    bool lost;                // no spill chunk left, or more than M + LGPU_SPILL entries: the solver passes re-walk
+    __device__ __forceinline__ void init(const Chunk& ck) {
         base = ck.row_addr; stride = ck.row_stride;
-        M = v.M; cnt = 0;
+        cnt = 0; spill = nullptr; lost = false;
     }
     __device__ __forceinline__ void put(int k, uint32_t code) {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)(k >> 2) * stride + (uint32_t)(k & 3) * 2u), "h"((unsigned short)code) : "memory");
     }
-    __device__ __forceinline__ void emit(uint32_t code) {
-        if (cnt < M) put(cnt, code);
+    // entry number cnt >= M: into the spill chunk (rare)
+    __device__ __noinline__ void put_spill(const View& v, int i, uint32_t code) {
+        const int k = cnt - 4 * LGPU_MG;
+        if (k == 0) {
+            const int chunk = atomicAdd(&v.brick_ctl[3], 1);
+            if (chunk < v.spill_cap) { spill = reinterpret_cast<unsigned short*>(v.nbr_spill + (size_t)chunk * (LGPU_SPILL / 4)); v.nbr_ovf[i] = chunk; }
+            else lost = true;
+        }
+        if (k >= LGPU_SPILL) lost = true;
+        if (!lost) spill[k] = (unsigned short)code;
+    }
+    __device__ __forceinline__ void emit(const View& v, int i, uint32_t code) {
+        if (cnt < 4 * LGPU_MG) put(cnt, code);
+        else put_spill(v, i, code);
         cnt++;
     }
     __device__ __forceinline__ void emit_unchecked(uint32_t code) { put(cnt, code); cnt++; }  // the caller has checked cnt + (codes to come) <= M
     __device__ __forceinline__ void finish(uint32_t pad) {  // completes the last group with the padding code
-        if (cnt < M) for (int k = cnt; k & 3; k++) put(k, pad);
+        if (cnt <= 4 * LGPU_MG) { for (int k = cnt; k & 3; k++) put(k, pad); }
+        else if (!lost) { for (int k = cnt - 4 * LGPU_MG; k & 3; k++) spill[k] = (unsigned short)pad; }
     }
 };
 
@@ -144,14 +192,14 @@ struct RowWriter {
 template <bool SAND>
 __device__ __noinline__ int build_row_walk(const View& v, const BrickDesc& d, const Chunk& ck, F3 xi, int ly, int lx, uint32_t pad) {
     RowWriter w;
-    w.init(v, ck);
+    w.init(ck);
     walk<SAND>(v, ck.i, xi, [&](int j, int r) {
         const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;  // halo column of stencil column r = 3 (dy + 1) + (dx + 1)
-        if (j >= 0) w.emit((uint32_t)(d.col[hc].s0 + (j - d.col[hc].g0)));
-        else w.emit((uint32_t)(d.scol[hc].s0 + (~j - d.scol[hc].g0)));
+        if (j >= 0) w.emit(v, ck.i, (uint32_t)(d.col[hc].s0 + (j - d.col[hc].g0)));
+        else w.emit(v, ck.i, (uint32_t)(d.scol[hc].s0 + (~j - d.scol[hc].g0)));
     });
     w.finish(pad);
-    return w.cnt;
+    return w.lost ? -w.cnt : w.cnt;
 }
 
 template <bool SAND, int LM>
@@ -184,12 +232,11 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
             // per stencil column: the candidates are the stage slots [cb, ce) — the three cells z-1..z+1 of a column are
             // contiguous in the sorted storage and therefore in the stage
             int cb[9], ce[9];
-            bool slow = false;  // solids in the neighbouring columns, or a column with more than 32 candidates
+            bool slow = false;  // solids in the neighbouring columns
 #pragma unroll
             for (int r = 0; r < 9; r++) {
                 const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;
                 cb[r] = ck.cs[hc][tz - 1]; ce[r] = ck.cs[hc][tz + 2];
-                if (ce[r] - cb[r] > 32) slow = true;
                 if (d.scol[hc].len > 0) slow = true;  // (the solid range of a halo column spans the brick's z extent)
             }
             const uint32_t self_code = (uint32_t)slot;
@@ -201,44 +248,52 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
                 cnt = build_row_walk<SAND>(v, d, ck, xi, ly, lx, pad);
             } else {
                 RowWriter w;
-                w.init(v, ck);
+                w.init(ck);
                 // No solid near: the reference order is simply ascending sorted slot over the 9 columns (fluid: self
-                // included; sand: self skipped — SURVEY F7).  Per column: test the candidates with the Exact predicate
-                // into a hit mask, then emit the hits.
+                // included; sand: self skipped — SURVEY F7).  Per column, 32 candidates at a time (one round unless the
+                // cells are crowded): test them with the Exact predicate into a hit mask, then emit the hits.
 #pragma unroll
                 for (int r = 0; r < 9; r++) {
-                    const int n = ce[r] - cb[r];
-                    if (n == 0) continue;
-                    const uint32_t first = (uint32_t)cb[r];
-                    // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at bit n-1-t.
-                    // The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has the exact sign and is
-                    // +0 on equality), so a test costs the 8 separately rounded operations of the reference's
-                    // predicate (src/neighbors/Neighbors.cpp:433-435) plus one FADD and one funnel shift.
-                    uint32_t out = 0;
-                    const uint32_t a = slot_addr(stage_addr, first);
+                    for (int c0 = cb[r]; c0 < ce[r]; c0 += 32) {
+                        const int n = min(ce[r] - c0, 32);
+                        const uint32_t first = (uint32_t)c0;
+                        // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at bit n-1-t.
+                        // The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has the exact sign and is
+                        // +0 on equality), so a test costs the 8 separately rounded operations of the reference's
+                        // predicate (src/neighbors/Neighbors.cpp:433-435) plus one FADD and one funnel shift.
+                        uint32_t out = 0;
+                        const uint32_t a = slot_addr(stage_addr, first);
 #pragma unroll 4
-                    for (int t = 0; t < n; t++) {
-                        const float4 pj = lds128(a + 16u * (uint32_t)t);
-                        const F3 dd = vsub<Exact>(xi, f3(pj));
-                        out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
-                    }
-                    uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
-                    const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
-                    if (SAND && r == 4) m &= ~(1u << (top - self_code));
-                    const int hits = __popc(m);
-                    if (w.cnt + hits > w.M) { w.cnt += hits; continue; }  // row too long: the solver passes re-walk
-                    while (m) {  // ascending candidate = descending bit
-                        const uint32_t k = 31u - (uint32_t)__clz(m);
-                        m ^= 1u << k;
-                        w.emit_unchecked(top - k);
+                        for (int t = 0; t < n; t++) {
+                            const float4 pj = lds128(a + 16u * (uint32_t)t);
+                            const F3 dd = vsub<Exact>(xi, f3(pj));
+                            out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
+                        }
+                        uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
+                        const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k
+                        if (SAND && r == 4 && self_code >= first && self_code <= top) m &= ~(1u << (top - self_code));
+                        if (w.cnt + __popc(m) <= 4 * LGPU_MG) {
+                            while (m) {  // ascending candidate = descending bit
+                                const uint32_t k = 31u - (uint32_t)__clz(m);
+                                m ^= 1u << k;
+                                w.emit_unchecked(top - k);
+                            }
+                        } else {
+                            while (m) {
+                                const uint32_t k = 31u - (uint32_t)__clz(m);
+                                m ^= 1u << k;
+                                w.emit(v, i, top - k);
+                            }
+                        }
                     }
                 }
                 w.finish(pad);
-                cnt = w.cnt;
+                cnt = w.lost ? -w.cnt : w.cnt;
             }
-            word = cnt;
-            if (cnt > v.M) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
-            else ng = (cnt + 3) >> 2;
+            // (cnt < 0: the list did not fit the table row plus a spill chunk)
+            word = cnt < 0 ? -cnt : cnt;
+            if (cnt < 0 || (v.M < 4 * LGPU_MG && cnt > v.M)) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
+            else ng = (min(cnt, 4 * LGPU_MG) + 3) >> 2;
         }
         v.nbr_cnt[i] = word;
         const int mword = (word & LGPU_CNT_WALK) ? (word & ~LGPU_CNT_MASK) : word;  // (a re-walked row's length is not needed)
@@ -301,7 +356,8 @@ __global__ void __launch_bounds__(128) k_dump_nbr(View v, const long* __restrict
                 if (!(word & LGPU_CNT_WALK) && d.mode == 0) {
                     const int cnt = word & LGPU_CNT_MASK;
                     for (int k = 0; k < cnt; k++) {
-                        const uint2 g4 = tab[(size_t)(1 + (k >> 2)) * d.n_pad + p];
+                        const uint2 g4 = k < 4 * LGPU_MG ? tab[(size_t)(1 + (k >> 2)) * d.n_pad + p]
+                                                         : v.nbr_spill[(size_t)v.nbr_ovf[i] * (LGPU_SPILL / 4) + ((k - 4 * LGPU_MG) >> 2)];
                         const uint32_t pair = (k & 2) ? g4.y : g4.x;
                         const int code = (int)((k & 1) ? pair >> 16 : pair & 0xffffu);
                         const int j = decode_code(d, code);

@@ -412,36 +412,48 @@ __device__ __forceinline__ void brick_loop(const View& v, const float4* __restri
     if (BUILD && tid == 0) bulk_wait_all();
 }
 
-// Replays the lane's table row from the slot's table block: body(pj, code, k), pj = stage[code].  PAD: the row is
-// processed in whole groups of four.  The padding codes of a SAND table are 0 = a far-away dummy (no contact); those of
-// a FLUID table are the particle's own slot, whose zero separation makes every term of the branch-free fluid bodies
-// vanish (lgpu_fluid.cu).  One LDS.64 per group (the next group's codes are loaded one ahead), one LDS.128 per code.
+// Replays the lane's table row from the slot's table block: body(pj, code, k), pj = stage[code], for the first
+// min(cnt, M) entries of the list.  PAD: the row is processed in whole groups of four.  The padding codes of a SAND table
+// are 0 = a far-away dummy (no contact); those of a FLUID table are the particle's own slot, whose zero separation
+// makes every term of the branch-free fluid bodies vanish (lgpu_fluid.cu).  One LDS.64 per group (the next group's
+// codes are loaded one ahead), one LDS.128 per code.
 template <bool PAD, class Body>
 __device__ __forceinline__ void replay_row(const Chunk& ck, int cnt, Body&& body) {
+    cnt = min(cnt, 4 * LGPU_MG);
     const int ng = (cnt + 3) >> 2;
     if (ng == 0) return;
-#ifdef LGPU_ROT
-    // Lanes start at different groups of their rows (the order of the terms is free within the stated tolerance):
-    // neighbouring lanes have similar lists, and staggering them spreads a step's LDS.128s over the bank groups.
-    int gi = (int)(threadIdx.x & LGPU_ROT);
-    while (gi >= ng) gi -= ng;
-#else
-    int gi = 0;
-#endif
-    uint2 w = lds64(ck.row_addr + (uint32_t)gi * ck.row_stride);
+    uint32_t a = ck.row_addr;
+    uint2 w = lds64(a);
     for (int g = 0; g < ng; g++) {
-        const int gc = gi;
-        gi = gi + 1 == ng ? 0 : gi + 1;
+        a += ck.row_stride;
         uint2 wn = w;
-        if (g + 1 < ng) wn = lds64(ck.row_addr + (uint32_t)gi * ck.row_stride);
+        if (g + 1 < ng) wn = lds64(a);
         const uint32_t code[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int k = 4 * gc + q;
+            const int k = 4 * g + q;
             if (!PAD && k >= cnt) break;
             body(lds128(slot_addr(ck.stage_addr, code[q])), code[q], k);
         }
         w = wn;
+    }
+}
+
+// ... and the tail of a list longer than the table width from its spill chunk (global memory; a few particles per
+// thousand in a collapsing dam break): entries M .. cnt-1.  Called from out-of-line functions only (the hot loops stay small).
+template <bool PAD, class Body>
+__device__ __forceinline__ void replay_spill(const View& v, const Chunk& ck, int cnt, Body&& body) {
+    const uint2* sp = v.nbr_spill + (size_t)v.nbr_ovf[ck.i] * (LGPU_SPILL / 4);
+    const int ng = (cnt - 4 * LGPU_MG + 3) >> 2;
+    for (int g = 0; g < ng; g++) {
+        const uint2 w = sp[g];
+        const uint32_t code[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = 4 * (LGPU_MG + g) + q;
+            if (!PAD && k >= cnt) break;
+            body(lds128(slot_addr(ck.stage_addr, code[q])), code[q], k);
+        }
     }
 }
 

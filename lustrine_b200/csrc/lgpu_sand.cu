@@ -91,6 +91,17 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
     }
 }
 
+// entries 32 .. cnt-1 of a list longer than the table width (spill chunk): returns the displacement, w != 0 if touched
+template <class P>
+__device__ __noinline__ float4 sand_spill(const View& v, const SandParams& sp, const Chunk& ck, int cnt, F3 pi, F3 xi_old, F3 deltap, bool touched) {
+    const uint32_t solid_base = (uint32_t)ck.d->solid_base;
+    replay_spill<true>(v, ck, cnt, [&](float4 pj, uint32_t code, int) {
+        const bool is_sand = code < solid_base;
+        sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
+    });
+    return make_float4(deltap.x, deltap.y, deltap.z, touched ? 1.0f : 0.0f);
+}
+
 template <class P, bool LAST>
 __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_iteration(const __grid_constant__ View v, const __grid_constant__ SandParams sp,
                                                                           const float4* cur, float4* next) {
@@ -119,6 +130,10 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
                 const bool is_sand = code < solid_base;
                 sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
             });
+            if ((word & LGPU_CNT_MASK) > 4 * LGPU_MG) {
+                const float4 r = sand_spill<P>(v, sp, ck, word & LGPU_CNT_MASK, pi, xi_old, deltap, touched);
+                deltap = f3(r.x, r.y, r.z); touched = r.w != 0.0f;
+            }
         } else {
             walk<true>(v, i, f3(v.x0[i]), [&](int j, int) {
                 const bool is_sand = j >= 0;

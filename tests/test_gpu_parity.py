@@ -229,6 +229,33 @@ def test_fluid_table_overflow_falls_back_to_walk():
     G.close(); P.close()
 
 
+@pytest.mark.parametrize("spacing", [0.74, 0.6])
+def test_dense_scenes_spill_chunks_and_split_bricks(spacing):
+    """Packings denser than the rest lattice: lists longer than the 32-entry table row continue in a spill chunk
+    (33..64 entries; beyond that the particle re-walks), columns with more than 32 candidates are tested in rounds,
+    and bricks whose neighbourhood exceeds a block's shared memory are cut along z.  Same parity contract."""
+    n = 20
+    sand = scenes.lattice(n, n, n, origin=(1.5, 1.5, 1.5), spacing=spacing, jitter=0.03, seed=4242)
+    domain = (24, 24, 24)
+    P, G = make_pair(domain, sand)
+    for step in range(2):
+        compare_fluid_substep(P, G, 2, False, False)
+        if step == 0:
+            cnt = G.dump(lgpu.DUMP_NBR_COUNT)
+            print("spacing %.2f: list length mean %.1f max %d, longer than 32: %.0f%%, longer than 64: %.0f%%, re-walked rows %d"
+                  % (spacing, cnt.mean(), cnt.max(), 100.0 * (cnt > 32).mean(), 100.0 * (cnt > 64).mean(), G.dump(lgpu.DUMP_COUNTERS)[1]))
+            assert (cnt > 32).mean() > 0.3, "the scene must exercise the spill chunks"
+        compare_fluid_substep(P, G, 1, True, True)
+    G.close(); P.close()
+    if spacing < 0.7:
+        return  # (sand grains of diameter 1 at this spacing overlap by 40 %: the push-out is an explosion, not a parity scene)
+    solids = scenes.floor_plate(24, 24)
+    P, G = make_pair(domain, sand, solids)
+    for step in range(2):
+        compare_sand_substep(P, G, 4, step % 2 == 0)
+    G.close(); P.close()
+
+
 @pytest.mark.parametrize("slots", [600, 40])
 def test_small_stage_uses_virtual_slots_or_walk(slots):
     # a stage too small for the neighbourhoods: blocks switch to virtual slots (same codes, neighbours
