@@ -17,6 +17,8 @@ synthetic scene named in config.workload.  Prints ONE JSON line (rank 0).
             this box's host cores on a bounded sample (rank 0, N=1 only).
 """
 import argparse
+import contextlib
+import ctypes as C
 import json
 import os
 import sys
@@ -573,6 +575,113 @@ def wrapper_e2e(workload, steps, sync_mode):
                        else "SYNC_LAZY (state resident on the device, positions copied out every step)")}
 
 
+@contextlib.contextmanager
+def quiet_stdout():
+    """The reference (and the kept API, like it) prints banners on stdout; main() has already sent fd 1 to stderr, this
+    drops them altogether for the chatty set-up calls."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+
+
+def fluid_demo_config1(calls, with_cpu):
+    """BASELINE configs[0]: the reference's own fluid experiment (experiments/fluid/fluid.cpp:46-118: 40x40x80 domain,
+    level1_physical.vox solids, 27 sand particles, four sources, one sink), headless, `calls` frames of
+    Lustrine::simulate with simulate_fun = simulate_fluid, dt = 0.01.  The caller is tests/cpp/fluid_demo.cpp, ONE
+    C++ source compiled against the drop-in and against the reference; the scene holds a few thousand particles, so
+    the GPU side is bound by launch latency and the host<->device round trip of every frame (SYNC_FULL), not by bandwidth."""
+    from fluid_demo_driver import DEMO_B200, DEMO_REF, Demo
+    if not os.path.exists(DEMO_B200):
+        raise RuntimeError("tests/cpp/_build/libfluid_demo_b200.so is missing: run __graft_entry__.build()")
+    out = {"config": "experiments/fluid scene, %d calls of Lustrine::simulate, simulate_fluid, dt=0.01" % calls}
+    with quiet_stdout():
+        d = Demo(DEMO_B200, 2)
+        d.run(20)
+        counts, _, seconds = d.run(calls)
+        d.close()
+    out["b200"] = {"calls_per_s": calls / seconds, "value": float(counts.sum()) / seconds, "unit": "particle-substeps/s",
+                   "live_particles_last_frame": int(counts[-1]), "seconds": seconds}
+    if with_cpu and os.path.exists(DEMO_REF):
+        with quiet_stdout():
+            r = Demo(DEMO_REF, 2)
+            r.run(20)
+            rcounts, _, rseconds = r.run(calls)
+            r.close()
+        out["cpu_reference"] = {"calls_per_s": calls / rseconds, "value": float(rcounts.sum()) / rseconds, "unit": "particle-substeps/s",
+                                "live_particles_last_frame": int(rcounts[-1]), "seconds": rseconds, "cores": 1, "kind": "reference",
+                                "sample": "the same %d frames on the unmodified reference (-O2 -ffp-contract=off build, fluid loop double-buffered: SURVEY F5)" % calls}
+    return out
+
+
+def mixed_scene_config5(steps):
+    """BASELINE configs[4]: mixed scene through the LustrineWrapper C API (reference experiments/bullet/bullet.cpp:71-121
+    scaled up): 126^3 = 2 000 376 sand particles on voxel solids, a capsule player + boxes on the HOST rigid-body side,
+    init_simulation_extra_parameters(subdivision 1, kernel_radius_scale 3.1, no credits), simulate(dt = 0.016, attract,
+    blow) with attraction on steps 100..199 and blowing on 300..319, particle bounding boxes around the player enabled,
+    simulation_bind_positions_copy every step (timed separately).  The rigid bodies run on the host as in the
+    reference; in this repository they are integrated by host/HostBodies.cpp, a stand-in for Bullet."""
+    import torch
+    from wrapper_driver import Vec3, Wrapper
+    lib = os.path.join(ROOT, "lustrine_b200", "lib", "liblustrine_b200.so")
+    side = 126
+    domain = (3 * side, 2 * side, 3 * side)
+    os.environ.setdefault("LUSTRINE_B200_QUIET", "1")
+    os.environ["LUSTRINE_B200_MAX_SAND"] = str(side ** 3 + 65536)
+    W = Wrapper(lib)
+    L = W.L
+    L.add_capsule.argtypes = [Vec3, C.c_float, C.c_float]
+    L.add_box.argtypes = [Vec3, C.c_bool, Vec3]
+    L.set_player_box_scale.argtypes = [Vec3]
+    solids = [((3 * side, 2, 3 * side), (0.0, 0.0, 0.0), 2), ((40, 8, 40), (float(side) + 20.0, 2.0, float(side) + 20.0), 2),
+              ((30, 12, 30), (float(side) + 70.0, 2.0, float(side) + 60.0), 2)]
+    with quiet_stdout():
+        data = W.init(domain, 0.5, sand=[((side, side, side), (float(side), 3.0, float(side)))], solids=solids, subdivision=1, extra=(3.1, 0))
+        n = data.num_sand_particles
+        top = 3.0 + side
+        player = L.add_capsule(Vec3(1.5 * side, top + 6.0, 1.5 * side), 2.0, 3.0)
+        L.add_box(Vec3(1.5 * side + 1.0, top + 3.0, 1.5 * side + 1.0), True, Vec3(1.0, 1.0, 1.0))
+        L.add_box(Vec3(1.5 * side - 1.0, top + 3.0, 1.5 * side - 1.0), True, Vec3(1.0, 1.0, 1.0))
+        L.add_box(Vec3(1.5 * side - 5.0, top + 2.0, 1.5 * side - 5.0), True, Vec3(3.0, 1.0, 1.0))
+        L.add_box(Vec3(1.5 * side, -0.5, 1.5 * side), False, Vec3(1.5 * side, 1.0, 1.5 * side))
+        L.set_player_id(player)
+        L.set_player_box_scale(Vec3(2.0, 2.0, 2.0))
+        L.enable_particles_bounding_boxes()
+        L.set_attract_blow_parameters(12.0, 9.0, 1000.0, 500.0)
+        L.b200_set_solver_options(1, 0, 0)
+        L.b200_set_host_sync(2)  # the state stays on the device; positions are copied out on request (what the game does)
+    out = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    t_sim = t_copy = 0.0
+    for s in range(steps):
+        attract, blow = 100 <= s < 200, 300 <= s < 320
+        t0 = time.perf_counter()
+        L.simulate(0.016, attract, blow)
+        t1 = time.perf_counter()
+        L.simulation_bind_positions_copy(out.data_ptr())
+        t2 = time.perf_counter()
+        if s >= 5:
+            t_sim += t1 - t0; t_copy += t2 - t1
+    timed = steps - 5
+    checksum = float(out.double().sum())
+    with quiet_stdout():
+        L.cleanup_simulation()
+    return {"value": n * timed / t_sim, "unit": "particle-substeps/s", "particles": int(n), "solid_particles": int(data.num_solid_particles),
+            "steps": steps, "ms_per_step_simulate": 1e3 * t_sim / timed, "ms_per_step_positions_copy": 1e3 * t_copy / timed,
+            "attract_steps": [100, 200], "blow_steps": [300, 320], "position_checksum": checksum,
+            "d2h_bytes_per_step": int(n) * 12, "h2d_bytes_per_step": 0,
+            "path": "LustrineWrapper C API on liblustrine_b200.so (init_grid_box, init_simulation_extra_parameters, add_capsule, add_box, set_player_id, "
+                    "enable_particles_bounding_boxes, simulate, simulation_bind_positions_copy), SYNC_LAZY",
+            "note": "wall clock of the C calls on the host (the step is synchronous at return); the rigid bodies are stepped on the host by "
+                    "host/HostBodies.cpp, a stand-in for Bullet; no CPU reference at this size (the reference needs ~35 s per 2M-particle step, see secondary.sand_pile_4m.cpu_baseline)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -705,6 +814,9 @@ def main():
             cbs, _, _, _ = run_cpu_reference("sand", 160, 4, 0.016, steps=2, warmup=1, budget_s=args.cpu_budget)
             sec_line["cpu_baseline"] = cbs
         extras["secondary"] = {"sand_pile_4m": sec_line}
+        # BASELINE configs[0] and configs[4] through the kept API (C++ caller / C wrapper)
+        extras["secondary"]["fluid_demo"] = fluid_demo_config1(600, not args.no_cpu_baseline)
+        extras["secondary"]["mixed_2m"] = mixed_scene_config5(330)
 
     # ---------------- e2e through the plugin boundary with host buffers ----------------
     e2e = None

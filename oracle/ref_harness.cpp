@@ -253,6 +253,16 @@ void refh_set_player(void* hv, const float* pos, int attract, int blow, float at
     s.attract_coeff = attract_coeff; s.blow_coeff = blow_coeff;
 }
 
+// A Simulation owned by somebody else (tests/cpp/fluid_demo.cpp compiled against the reference): its simulate_fun
+// becomes the O-jac step with these options.
+void refh_use_jacobi(void* simulation, int iterations, int literal_lambda_index) {
+    static Handle external;  // (only its options and scratch are used; external.sim stays empty)
+    external.jacobi_iterations = iterations;
+    external.literal_lambda_index = literal_lambda_index != 0;
+    g_current = &external;
+    ((Lustrine::Simulation*)simulation)->simulate_fun = simulate_fluid_jacobi;
+}
+
 // Runs `steps` calls and returns the wall seconds spent inside them.
 double refh_step(void* hv, float dt, int steps, int through_simulate) {
     Handle* h = (Handle*)hv;
