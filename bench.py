@@ -501,8 +501,11 @@ def single_gpu_workload(workload, args, device, flush, hbm_gbs, peak_src, steps,
     params = lgpu.default_step_params(**step_kwargs(kind, K, dt, args.exact, args.literal))
     step = G.step_fluid if kind == "fluid" else G.step_sand
     reset = lambda: G.upload_sand(sand)
+    # the substep's launches are captured once and replayed as ONE CUDA graph per substep (lgpu_set_use_graph)
+    G.set_use_graph(0 if args.no_graph else 1)
     ms = timed_substeps(G, step, params, steps, warmup, flush, reset, args.reset_every)
     launches = timed_substeps.launches
+    G.set_use_graph(0)
     phase = phase_times(G, step, params, flush, reset)
     counters = G.dump(lgpu.DUMP_COUNTERS)
     roofline, roofline_step = rooflines(kind, K, n, G.num_cells, phase, ms, hbm_gbs, peak_src, workload)
@@ -522,7 +525,8 @@ def single_gpu_workload(workload, args, device, flush, hbm_gbs, peak_src, steps,
                            "ms_per_step_after": tail_ms, "table_overflows": int(c2[1]) - int(counters[1]),
                            "key_violations": int(c2[0]) - int(counters[0]),
                            "note": "reset-every 0: %d free-running substeps from the initial scene (SURVEY §8d config 2), then %d more "
-                                   "(ms_per_step_after); table_overflows = particle-substeps whose list exceeded 32 entries and re-walked"
+                                   "(ms_per_step_after); table_overflows = particle-substeps that re-walked the stencil (list longer than 64 entries, or a "
+                                   "brick part that does not fit a block's shared memory even when cut down to one cell layer)"
                                    % (free_run_steps, max(free_run_steps // 4, 1))}
     return out, G, (domain, sand, solids, params, step, kind, K, dt)
 
@@ -693,6 +697,7 @@ def main():
     ap.add_argument("--literal", type=int, default=0, help="fluid: 1 = lambdas[loop counter] as in the reference (single GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (with programmatic dependent launch) instead of one CUDA graph per substep")
     ap.add_argument("--no-extras", action="store_true", help="skip free_run / stock_pair / secondary workloads (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--free-run", type=int, default=200, help="free-running substeps of the free_run leg")
@@ -840,6 +845,7 @@ def main():
             "notes": {"arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",
                       "timing": "CUDA events on the launching stream around every substep, summed",
+                      "launch": "eager launches" if args.no_graph else "one CUDA graph replay per substep (captured once: lgpu_set_use_graph)",
                       "pipelined_ms_per_step_no_flush": pipelined_ms, "pipelined_ms_per_step_no_flush_cuda_graph": pipelined_graph_ms,
                       "table_overflows": main_res["table_overflows"], "key_violations": main_res["key_violations"]},
             "roofline": main_res["roofline"], "roofline_step": main_res["roofline_step"], "cpu_baseline": cpu_baseline, "e2e": e2e,

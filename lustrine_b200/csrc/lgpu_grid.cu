@@ -298,8 +298,18 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) 
     if (c == v.g.C) return;  // slab mode: dead slot (trash cell), dropped
     int b = v.cell_start[c], e = v.cell_start[c + 1];
     int mine = v.orig_in[i];
-    int r = 0;
-    for (int u = b; u < e; u++) r += (v.orig_in[v.tmp_id[u]] < mine) ? 1 : 0;
+    int r;
+    if (e - b <= LGPU_STABLE_MAX) {
+        // stable order inside the cell (ascending reference slot, src/neighbors/Sorting.cpp:26-33): rank among the cell's members
+        r = 0;
+        for (int u = b; u < e; u++) r += (v.orig_in[v.tmp_id[u]] < mine) ? 1 : 0;
+    } else {
+        // More members than any packing puts into one cell: particles whose coordinates left the grid and were clamped
+        // into a border cell (undefined behaviour in the reference).  The quadratic re-rank is skipped;
+        // the cell keeps the order in which its members arrived (a valid permutation, not the reference's), counted.
+        r = s - b;
+        if (s == b) atomicAdd(&v.counters[2], 1ULL);
+    }
     int dst = b + r;
     v.pos[dst] = v.pos_in[i];
     v.vel[dst] = v.vel_in[i];

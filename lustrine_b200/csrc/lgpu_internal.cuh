@@ -42,6 +42,7 @@
 #endif
 #define LGPU_MG 8                // table groups (of four 16-bit codes) per row: M = 32
 #define LGPU_SPILL 32            // codes of a spill chunk: a list of 33 .. 64 entries keeps its tail in one (global memory)
+#define LGPU_STABLE_MAX 256      // cells with more members keep arrival order instead of the stable re-rank (k_reorder)
 #define LGPU_DUMMY_SLOTS 8       // stage slots 0..7: far-away dummies (padding of sand rows)
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
@@ -171,7 +172,7 @@ struct View {
     int* nbr_ovf;      // by sorted slot: spill chunk of the particle (meaningful where the list is longer than M)
     int spill_cap;     // spill chunks available
     float *lambda, *density, *lambda_head;
-    unsigned long long* counters;  // [0] key violations, [1] table overflows
+    unsigned long long* counters;  // [0] key violations, [1] table overflows, [2] cells too crowded for the stable re-rank
 };
 
 struct lgpu_ctx {

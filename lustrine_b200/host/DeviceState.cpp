@@ -19,35 +19,58 @@ void die(const char* what, int status) {
 #define LGPU_MUST(call) do { int _s = (call); if (_s != LGPU_OK) die(#call, _s); } while (0)
 }  // namespace
 
-DeviceState* DeviceState::create(Simulation* s, float kernel_radius_scale) {
-    DeviceState* d = new DeviceState();
+// The device context is sized for the particles that exist, with head room, and GROWS when the particle sources outgrow
+// it — not for every slot of the reference's host arrays (total_allocated = X*Y*Z slots, src/Lustrine.cpp:237-239: 12 M
+// slots for the 1 M dam break, 192 M for the 16 M domain).  LUSTRINE_B200_MAX_SAND pins the capacity instead.
+void DeviceState::make_context(Simulation* s, int capacity_sand) {
     lgpu_config cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.domain[0] = s->parameters_copy.X; cfg.domain[1] = s->parameters_copy.Y; cfg.domain[2] = s->parameters_copy.Z;
     cfg.particle_radius = s->parameters_copy.particleRadius;
     cfg.particle_diameter = s->parameters_copy.particleDiameter;
     cfg.kernel_radius_scale = kernel_radius_scale;
-    // every slot below the solid tail can become sand through the particle sources (src/Lustrine.cpp:237-239)
-    cfg.capacity_sand = s->ptr_solid_ordered_end + 1 > 0 ? s->ptr_solid_ordered_end + 1 : 1;
-    const char* cap_env = std::getenv("LUSTRINE_B200_MAX_SAND");
-    if (cap_env) {
-        int cap = std::atoi(cap_env);
-        if (cap >= s->num_sand_particles && cap < cfg.capacity_sand) cfg.capacity_sand = cap;
-    }
+    cfg.capacity_sand = capacity_sand;
     cfg.capacity_solid = s->num_solid_particles;
     cfg.device = -1;
-    LGPU_MUST(lgpu_create(&cfg, &d->ctx));
+    LGPU_MUST(lgpu_create(&cfg, &ctx));
+    capacity = capacity_sand;
     lgpu_grid_info gi;
-    LGPU_MUST(lgpu_get_grid(d->ctx, &gi));
+    LGPU_MUST(lgpu_get_grid(ctx, &gi));
     if (gi.grid[0] != s->gridX || gi.grid[1] != s->gridY || gi.grid[2] != s->gridZ || gi.kernel_radius != s->kernelRadius ||
         gi.cubic_k != s->cubic_kernel_k || gi.cubic_l != s->cubic_kernel_l) {
         std::cerr << "lustrine_b200: device grid constants differ from the host's" << std::endl;
         std::abort();
     }
     if (s->num_solid_particles > 0)
-        LGPU_MUST(lgpu_upload_solids(d->ctx, s->num_solid_particles, reinterpret_cast<const float*>(s->positions + s->ptr_solid_start)));
+        LGPU_MUST(lgpu_upload_solids(ctx, s->num_solid_particles, reinterpret_cast<const float*>(s->positions + s->ptr_solid_start)));
+}
+
+DeviceState* DeviceState::create(Simulation* s, float kernel_radius_scale) {
+    DeviceState* d = new DeviceState();
+    d->kernel_radius_scale = kernel_radius_scale;
+    d->capacity_limit = s->ptr_solid_ordered_end + 1 > 0 ? s->ptr_solid_ordered_end + 1 : 1;
+    const int live = s->ptr_sand_end - s->ptr_sand_start;
+    int cap = live + live / 2 + 65536;  // head room for the sources; grows on demand
+    const char* cap_env = std::getenv("LUSTRINE_B200_MAX_SAND");
+    if (cap_env && std::atoi(cap_env) >= live) cap = std::atoi(cap_env);
+    if (cap > d->capacity_limit) cap = d->capacity_limit;
+    if (cap < live) cap = live;
+    d->make_context(s, cap > 0 ? cap : 1);
     d->upload(s);
     return d;
+}
+
+void DeviceState::ensure_capacity(Simulation* s, int needed) {
+    if (needed <= capacity) return;
+    // the device state is authoritative unless every step uploads it anyway: bring it home before the context goes
+    if (sync_mode != SYNC_FULL) download(s);
+    long grown = (long)needed + needed / 2 + 65536;
+    if (grown > capacity_limit) grown = capacity_limit;
+    if (grown < needed) grown = needed;
+    lgpu_destroy(ctx);
+    ctx = nullptr;
+    make_context(s, (int)grown);
+    device_sand = 0;
 }
 
 void DeviceState::destroy(DeviceState* d) {
@@ -58,6 +81,7 @@ void DeviceState::destroy(DeviceState* d) {
 
 void DeviceState::upload(Simulation* s) {
     const int n = s->ptr_sand_end - s->ptr_sand_start;
+    ensure_capacity(s, n);
     LGPU_MUST(lgpu_upload_sand(ctx, n, reinterpret_cast<const float*>(s->positions + s->ptr_sand_start),
                                reinterpret_cast<const float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
     device_sand = n;
@@ -74,6 +98,13 @@ void DeviceState::download_positions_into(float* dst) { LGPU_MUST(lgpu_download_
 
 void DeviceState::append_from_host(Simulation* s, int first, int count) {
     if (sync_mode == SYNC_FULL) return;  // the next step uploads everything anyway
+    if (device_sand + count > capacity) {
+        // the context is re-created larger; `first .. first + count` are already in the host arrays, so one upload brings
+        // everything (the old particles just downloaded, and the new ones)
+        ensure_capacity(s, device_sand + count);
+        upload(s);
+        return;
+    }
     LGPU_MUST(lgpu_append_sand(ctx, count, reinterpret_cast<const float*>(s->positions + first),
                                reinterpret_cast<const float*>(s->velocities + first), s->attracted + first));
     device_sand += count;

@@ -20,10 +20,15 @@ struct DeviceState {
     bool host_pinned = false;
     float last_ms = 0.0f;
     int device_sand = 0;               // particles resident on the device
+    int capacity = 0;                  // sand slots of the device context (grows on demand, see ensure_capacity)
+    int capacity_limit = 0;            // every slot below the solid tail can become sand through the particle sources
+    float kernel_radius_scale = 3.1f;
 
     static DeviceState* create(Simulation* s, float kernel_radius_scale);
     static void destroy(DeviceState* d);
 
+    void make_context(Simulation* s, int capacity_sand);          // (re)creates the lgpu context with that many sand slots
+    void ensure_capacity(Simulation* s, int needed);              // grows the context (x1.5) when the sources outgrow it
     void upload(Simulation* s);                                  // host arrays -> device (positions, velocities, attracted)
     void download(Simulation* s);                                // device -> host arrays
     void download_positions_into(float* dst);

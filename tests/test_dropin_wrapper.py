@@ -77,3 +77,22 @@ def test_wrapper_matches_reference(scenario, host_sync):
     assert worst <= 1e-5
     if scenario == "source_sink":
         assert ref["n"][-1] != ref["n0"][0], "sources/sinks must have changed the particle count"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_sync", [0, 1, 2])
+def test_device_capacity_grows_with_the_sources(host_sync, monkeypatch):
+    """The drop-in sizes its device context for the live particles (not for the X*Y*Z slots of the reference's host
+    arrays) and re-creates it larger when the particle sources outgrow it: with the capacity pinned to the initial
+    count, the first spawn forces a growth — results must not change."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    kw = dict(steps=24, flags=None, with_source_sink=True)
+    ref = run_scenario(Wrapper(O.REF_LIT_SO), **kw)
+    monkeypatch.setenv("LUSTRINE_B200_MAX_SAND", str(ref["n0"][0]))
+    got = run_scenario(Wrapper(OURS), host_sync=host_sync, **kw)
+    assert got["n"] == ref["n"] and max(ref["n"]) > ref["n0"][0], "the sources must have outgrown the initial capacity"
+    assert got["q"] == ref["q"]
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(got["pos"], ref["pos"]))
+    print("  growth under host_sync %d: max|dx| %.3e" % (host_sync, worst))
+    assert worst <= 1e-5
