@@ -41,9 +41,9 @@ __device__ __forceinline__ void deltap_pair(const Geom& g, const FluidParams& fp
 // ---- density + lambda, iterations after the first ----
 template <int LM>
 __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_lambda(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
-                                                                        float4* cur) {
+                                                                        float4* cur, int* cursor) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+    brick_loop<false>(v, cur, cursor, smem_raw, [&](const Chunk& ck) -> int {
         if (ck.word & LGPU_CNT_GHOST) return 0;
         const float4 ci = ck.d->mode == 0 ? lds128(slot_addr(ck.stage_addr, (uint32_t)ck.slot)) : cur[ck.i];
         fluid_lambda_particle<LM>(v, fp, ck, cur, ck.word, f3(ci));
@@ -86,11 +86,11 @@ __device__ __noinline__ float3 deltap_spill(const View& v, const FluidParams& fp
 // of a solid is 0, which is the lambda the reference reads for it).
 template <int LM, bool LAST>
 __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_deltap(const __grid_constant__ View v, const __grid_constant__ FluidParams fp,
-                                                                        const float4* cur, float4* next) {
+                                                                        const float4* cur, float4* next, int* cursor) {
     typedef typename LambdaPolicy<LM>::P P;
     constexpr bool POLY6 = LambdaPolicy<LM>::poly6;
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+    brick_loop<false>(v, cur, cursor, smem_raw, [&](const Chunk& ck) -> int {
         const int i = ck.i, word = ck.word, slot = ck.slot;
         const int mode = ck.d->mode;
         if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
@@ -213,15 +213,15 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
         float4* next = bufs[it & 1];
         if (it > 0) {  // (the first density + lambda pass ran inside the table build)
             lgpu_mark(c, 6);
-            CUDA_TRY(launch_pdl(k_fluid_lambda<LM>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, cur));
+            CUDA_TRY(launch_pdl(k_fluid_lambda<LM>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, cur, c->brick_ctl + 8 + c->pass));
             c->pass++; c->launches++;
         }
         // slab mode: after each pass a small kernel copies the boundary particles' lambda (.w of cur) / corrected x*
         // (next) into the neighbours' ghost slots and waits for the neighbours' stores of the same pass
         if (slab && !fp.literal_lambda_index) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
-        if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap<LM, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
-        else CUDA_TRY(launch_pdl(k_fluid_deltap<LM, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next));
+        if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap<LM, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));
+        else CUDA_TRY(launch_pdl(k_fluid_deltap<LM, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));
         c->pass++; c->launches++;
         if (slab && it < iterations - 1) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
         cur = next;

@@ -148,7 +148,7 @@ struct View {
     // bricks (lgpu_brick.cuh)
     int nbY, nbX, nbZ, NB;    // brick grid
     int stage_slots;          // stage capacity in use (<= LGPU_STAGE_SLOTS; test hook lgpu_set_stage_slots)
-    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [2] table words allocated, [3] spill chunks allocated
+    int* brick_ctl;           // [0] full bricks, [1] sparse bricks, [2] table words allocated, [3] spill chunks allocated, [8 + pass] work cursor of each staged kernel
     BrickRec* brick_rec;      // non-empty bricks of this substep: full ones from the front, sparse ones from the back
     int rec_cap;
     // unsorted (pre-reorder) buffers, indexed by the storage slot of the previous step

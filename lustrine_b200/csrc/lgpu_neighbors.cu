@@ -203,9 +203,9 @@ __device__ __noinline__ int build_row_walk(const View& v, const BrickDesc& d, co
 }
 
 template <bool SAND, int LM>
-__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_table(const __grid_constant__ View v, const __grid_constant__ FluidParams fp) {
+__global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_table(const __grid_constant__ View v, const __grid_constant__ FluidParams fp, int* cursor) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<true>(v, v.x0, smem_raw, [&](const Chunk& ck) -> int {
+    brick_loop<true>(v, v.x0, cursor, smem_raw, [&](const Chunk& ck) -> int {
         const Geom& g = v.g;
         const BrickDesc& d = *ck.d;
         const int i = ck.i, slot = ck.slot, q = ck.q;
@@ -310,7 +310,7 @@ static int brick_grid(const lgpu_ctx* c) { return LGPU_CTAS_PER_SM * c->num_sms;
 
 template <bool SAND, int LM>
 static int launch_build(lgpu_ctx* c, const View& v, const FluidParams& fp, bool pdl) {
-    CUDA_TRY(launch_pdl(k_build_table<SAND, LM>, brick_grid(c), LGPU_BRICK_THREADS, LGPU_BRICK_SMEM_BUILD, c->stream, pdl, v, fp));
+    CUDA_TRY(launch_pdl(k_build_table<SAND, LM>, brick_grid(c), LGPU_BRICK_THREADS, LGPU_BRICK_SMEM_BUILD, c->stream, pdl, v, fp, c->brick_ctl + 8 + c->pass));
     return LGPU_OK;
 }
 

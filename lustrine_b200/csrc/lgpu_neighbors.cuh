@@ -239,6 +239,7 @@ template <bool BUILD>
 struct BrickShared {
     uint64_t full, dfull[2];
     alignas(16) BrickRingEntry<BUILD> ring[2];
+    int work[2];                    // work index of the brick whose descriptor is in ring[e]; -1 = the list is exhausted
     int maxg;                       // table build: groups of the longest row collected so far
 };
 #define LGPU_BRICK_SMEM_OF(BUILD) (sizeof(BrickSlot) + sizeof(BrickShared<BUILD>) + 128)
@@ -332,10 +333,11 @@ __device__ __forceinline__ void atom_max_shared(int* p, int v) {
 //   !BUILD = solver pass: the table block is copied in with the positions.
 // chunk is called by the lanes that hold a particle (no warp collectives inside) and returns the number of table
 // groups of the row it has written (table build; 0 otherwise).
-// Work item w of the substep's brick list goes to block w % gridDim.x (bricks of one kind cost the same; the list
-// holds the full bricks first and the sparse ones last, so the blocks' shares are even).
+// The blocks draw their bricks from `cursor` (a device counter of this pass, zeroed with the work list): the list
+// holds the full bricks first and the sparse ones last, so the tail of a pass is made of small pieces.  One thread
+// draws the NEXT brick and starts the copy of its descriptor while the block works on the current one.
 template <bool BUILD, class ChunkFn>
-__device__ __forceinline__ void brick_loop(const View& v, const float4* __restrict__ src, unsigned char* smem_raw, ChunkFn&& chunk) {
+__device__ __forceinline__ void brick_loop(const View& v, const float4* __restrict__ src, int* cursor, unsigned char* smem_raw, ChunkFn&& chunk) {
     const BrickSmem<BUILD> m = brick_smem<BUILD>(smem_raw);
     BrickShared<BUILD>& sh = *m.sh;
     BrickSlot& slot = *m.slot;
@@ -352,24 +354,27 @@ __device__ __forceinline__ void brick_loop(const View& v, const float4* __restri
     pdl_trigger();
     pdl_wait();  // everything this kernel reads was written by its predecessors on the stream
     const int n_full = v.brick_ctl[0], n_work = n_full + v.brick_ctl[1];
-    const int G = gridDim.x;
-    auto fetch_desc = [&](int wj, int e) {  // (thread 0)
+    // thread 1 draws work and fetches descriptors (thread 0 and the other lanes 0 are busy issuing the brick's copies)
+    auto draw = [&](int e) {
+        const int wj = atomicAdd(cursor, 1);
         if (wj < n_work) {
+            sh.work[e] = wj;
             mbar_expect_tx(&sh.dfull[e], kRecBytes);
             bulk_g2s(&sh.ring[e], &v.brick_rec[rec_of_work(v, wj, n_full)], kRecBytes, &sh.dfull[e]);
+        } else {
+            sh.work[e] = -1;
         }
     };
-    if (tid == 0) fetch_desc(blockIdx.x, 0);
-    int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += G, it++) {
+    if (tid == 1) draw(0);
+    __syncthreads();
+    for (int it = 0;; it++) {
         const int e = it & 1;
+        if (sh.work[e] < 0) break;
         mbar_wait(&sh.dfull[e], (uint32_t)(it >> 1) & 1u);
         const BrickDesc& d = sh.ring[e].d;
-        if (tid == 0) {
-            fetch_desc(w + G, e ^ 1);  // (its previous user, brick it - 1, is done: everybody passed the barrier below)
-            mbar_expect_tx(&sh.full, brick_stage_bytes<!BUILD>(d));
-        }
+        if (tid == 0) mbar_expect_tx(&sh.full, brick_stage_bytes<!BUILD>(d));
         if (lane == 0) brick_stage<!BUILD>(v, d, slot, &sh.full, src, warp);
+        if (tid == 1) draw(e ^ 1);  // (ring[e ^ 1]'s previous user, brick it - 1, is done: everybody passed the barrier below)
         const int n_own = d.n_own;
         Chunk ck;
         ck.d = &d; ck.stage = slot.pos; ck.stage_addr = smem_u32(slot.pos);

@@ -104,9 +104,9 @@ __device__ __noinline__ float4 sand_spill(const View& v, const SandParams& sp, c
 
 template <class P, bool LAST>
 __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_iteration(const __grid_constant__ View v, const __grid_constant__ SandParams sp,
-                                                                          const float4* cur, float4* next) {
+                                                                          const float4* cur, float4* next, int* cursor) {
     extern __shared__ unsigned char smem_raw[];
-    brick_loop<false>(v, cur, smem_raw, [&](const Chunk& ck) -> int {
+    brick_loop<false>(v, cur, cursor, smem_raw, [&](const Chunk& ck) -> int {
         const int i = ck.i, word = ck.word;
         const int mode = ck.d->mode;
         if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
@@ -193,11 +193,11 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
         const bool last = it == K - 1;
         lgpu_mark(c, 7);
         if (p.exact_math) {
-            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Exact, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
-            else CUDA_TRY(launch_pdl(k_sand_iteration<Exact, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Exact, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, c->brick_ctl + 8 + c->pass));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Exact, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, c->brick_ctl + 8 + c->pass));
         } else {
-            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Fast, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
-            else CUDA_TRY(launch_pdl(k_sand_iteration<Fast, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next));
+            if (last) CUDA_TRY(launch_pdl(k_sand_iteration<Fast, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, c->brick_ctl + 8 + c->pass));
+            else CUDA_TRY(launch_pdl(k_sand_iteration<Fast, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, sp, cur, next, c->brick_ctl + 8 + c->pass));
         }
         c->pass++; c->launches++;
         if (!last && lgpu_slab_active(c)) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, next, false); if (st) return st; }
