@@ -82,6 +82,18 @@ def slab_capacity(pos, slabs, owned, cs, grid_x, factor=1.5):
     return int(need * factor) + 4096
 
 
+def imbalance(owned_counts):
+    """max / mean of the slabs' particle counts (1.0 = perfectly balanced)."""
+    c = np.asarray(owned_counts, np.float64)
+    return float(c.max() / max(c.mean(), 1.0))
+
+
+def needs_replan(owned_counts, live_counts, capacity, max_imbalance=1.25, fill=0.8):
+    """Re-plan when a slab holds `max_imbalance` times the mean, or when a slab's storage (owned + ghosts, counted
+    twice like slab_capacity does) approaches its capacity — whichever comes first."""
+    return imbalance(owned_counts) > max_imbalance or max(live_counts) > fill * capacity
+
+
 def merge_by_id(parts, n_total):
     """Reassembles (pos, vel, flags, ids) tuples of all slabs into arrays indexed by particle id."""
     pos = np.zeros((n_total, 3), np.float32)
@@ -130,12 +142,20 @@ class VirtualSlabs:
                  slabs=None, **ctx_kw):
         pos = np.ascontiguousarray(pos, np.float32)
         self.n_total = len(pos)
+        self.world = world
+        self._args = (domain, solids, device, capacity_factor, halo_capacity, ctx_kw)
+        self.grid = grid_dims(domain, cell_size())
+        self.ctx = []
+        self.replans = 0
+        self._build(pos, vel, flags, None, slabs)
+
+    def _build(self, pos, vel, flags, ids, slabs=None):
+        domain, solids, device, capacity_factor, halo_capacity, ctx_kw = self._args
         cs = cell_size()
-        self.grid = grid_dims(domain, cs)
-        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], world)
+        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
         owned = deal(pos, self.slabs, cs)
-        cap = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
-        self.ctx = [SlabContext(domain, s, cap, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
+        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
+        self.ctx = [SlabContext(domain, s, self.capacity, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
         exports = [c.G.slab_export() for c in self.ctx]
         for k, c in enumerate(self.ctx):
             if k > 0:
@@ -143,7 +163,7 @@ class VirtualSlabs:
             if k + 1 < len(self.ctx):
                 c.G.slab_connect(1, same_process_ptr=exports[k + 1][1])
         for c, idx in zip(self.ctx, owned):
-            c.G.slab_upload(pos[idx], idx, None if vel is None else vel[idx], None if flags is None else flags[idx])
+            c.G.slab_upload(pos[idx], idx if ids is None else ids[idx], None if vel is None else vel[idx], None if flags is None else flags[idx])
 
     def step(self, mode, params=None, **kw):
         p = params if params is not None else lgpu.default_step_params(**kw)
@@ -151,6 +171,24 @@ class VirtualSlabs:
             c.G.slab_step_begin(p, mode)
         for c in self.ctx:
             c.G.slab_step_end()
+
+    def counts(self):
+        info = [c.G.slab_info() for c in self.ctx]
+        return [i["owned"] for i in info], [i["owned"] + 2 * i["ghosts"] for i in info]
+
+    def replan_if_needed(self, max_imbalance=1.25, fill=0.8):
+        """Re-plans the slab boundaries from the current per-column histogram when the particles have gathered in a few
+        slabs: all particles are collected, dealt again and uploaded into new contexts.  A rare, slow step
+        (the boundaries are fixed between re-plans); returns True if it happened."""
+        owned, live = self.counts()
+        if not needs_replan(owned, live, self.capacity, max_imbalance, fill):
+            return False
+        pos, vel, flags = self.gather()
+        for c in self.ctx:
+            c.close()
+        self._build(pos, vel, flags, np.arange(self.n_total, dtype=np.int32))
+        self.replans += 1
+        return True
 
     def sync(self):
         for c in self.ctx:
@@ -174,31 +212,41 @@ class DistributedSlab:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         pos = np.ascontiguousarray(pos, np.float32)
         self.n_total = len(pos)
-        cs = cell_size()
-        self.grid = grid_dims(domain, cs)
+        self._args = (domain, solids, device, capacity_factor, halo_capacity, context_factory or SlabContext, ctx_kw)
+        self.grid = grid_dims(domain, cell_size())
+        self.ctx = None
+        self.replans = 0
         # every rank holds the same synthetic scene and derives the same plan: no broadcast needed
+        idx = self._build(pos, vel, flags, None)
+        self.initial = (pos[idx].copy(), idx.copy())
+        dist.barrier()
+
+    def _build(self, pos, vel, flags, ids):
+        """Plans the slabs from `pos` (the same array on every rank), creates this rank's context, wires the neighbours
+        through CUDA IPC handles and uploads this rank's particles.  Returns the indices this rank owns."""
+        domain, solids, device, capacity_factor, halo_capacity, factory, ctx_kw = self._args
+        cs = cell_size()
         self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
         owned = deal(pos, self.slabs, cs)
-        cap = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
-        self.ctx = (context_factory or SlabContext)(domain, self.slabs[self.rank], cap, solids, device, halo_capacity, **ctx_kw)
+        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
+        self.ctx = factory(domain, self.slabs[self.rank], self.capacity, solids, device, halo_capacity, **ctx_kw)
         handle, _, _ = self.ctx.G.slab_export()
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle)
+        self.dist.all_gather_object(handles, handle)
         if self.rank > 0:
             self.ctx.G.slab_connect(0, handle=handles[self.rank - 1])
         if self.rank + 1 < self.world:
             self.ctx.G.slab_connect(1, handle=handles[self.rank + 1])
         idx = owned[self.rank]
-        self.ctx.G.slab_upload(pos[idx], idx, None if vel is None else vel[idx], None if flags is None else flags[idx])
-        self.initial = (pos[idx].copy(), idx.copy())
-        dist.barrier()
+        self.ctx.G.slab_upload(pos[idx], idx if ids is None else ids[idx], None if vel is None else vel[idx], None if flags is None else flags[idx])
+        return idx
 
     @property
     def G(self):
         return self.ctx.G
 
     def reset(self):
-        """Puts the slab back to its initial particles (all ranks must call it together)."""
+        """Puts the slab back to its initial particles (all ranks must call it together; not after a re-plan)."""
         self.ctx.G.slab_upload(self.initial[0], self.initial[1])
 
     def step(self, mode, params):
@@ -206,6 +254,31 @@ class DistributedSlab:
             self.ctx.G.step_fluid(params)
         else:
             self.ctx.G.step_sand(params)
+
+    def counts(self):
+        """(owned, storage need) of every rank — one small all_gather, no device data."""
+        info = self.ctx.G.slab_info()
+        mine = (int(info["owned"]), int(info["owned"] + 2 * info["ghosts"]))
+        allc = [None] * self.world
+        self.dist.all_gather_object(allc, mine)
+        return [c[0] for c in allc], [c[1] for c in allc]
+
+    def replan_if_needed(self, max_imbalance=1.25, fill=0.8):
+        """Collective: re-plans the slab boundaries from the current particle columns when the load has drifted
+        (SURVEY §8e "rebalanced every R steps from the per-x-plane histogram").  Every rank contributes its particles
+        (all_gather over the process group), derives the same new plan, re-creates its context and re-wires its
+        neighbours.  Rare and slow by design: between re-plans the boundaries are fixed and the data path has no
+        collective.  Returns True if it happened."""
+        owned, live = self.counts()
+        if not needs_replan(owned, live, self.capacity, max_imbalance, fill):
+            return False
+        pos, vel, flags = self.gather()
+        self.dist.barrier()        # nobody re-maps a neighbour's arena while it is still being read
+        self.ctx.close()
+        self._build(pos, vel, flags, np.arange(self.n_total, dtype=np.int32))
+        self.replans += 1
+        self.dist.barrier()
+        return True
 
     def gather(self):
         """All particles in id order on every rank."""

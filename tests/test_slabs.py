@@ -83,6 +83,7 @@ class FakeG:
     def slab_download(self):
         pos, ids = self.state
         return pos, np.zeros_like(pos), np.zeros(len(ids), np.int32), ids
+    def slab_info(self): return {{"owned": len(self.state[1]), "ghosts": 0}}
     def close(self): pass
 
 class FakeCtx:
@@ -106,9 +107,24 @@ assert np.array_equal(got, pos)
 counts = [None] * world
 dist.all_gather_object(counts, len(S.initial[1]))
 assert sum(counts) == len(pos) and S.ctx.capacity >= max(counts)
+assert not S.replan_if_needed(), "a balanced deal must not be re-planned"
+# the particles drift to +x: after the migrations of many substeps the last slab owns most of them
+moved = pos + np.array([0.45 * domain[0], 0.0, 0.0], np.float32)
+mine = slabs.deal(moved, S.slabs, slabs.cell_size())[rank]
+S.G.state = (moved[mine].copy(), mine.copy())
+before = list(S.slabs)
+owned, live = S.counts()
+assert sum(owned) == len(pos) and slabs.imbalance(owned) > 1.25, owned
+assert S.replan_if_needed() and S.replans == 1
+assert S.slabs != before and S.slabs == slabs.plan_slabs(slabs.cell_x(moved, slabs.cell_size()), S.grid[0], world)
+assert S.G.connected == want, "neighbours re-wired after the re-plan"
+owned2, _ = S.counts()
+assert sum(owned2) == len(pos) and slabs.imbalance(owned2) < 1.1, owned2
+got2, _, _ = S.gather()
+assert np.array_equal(got2, moved)
 dist.barrier()
 dist.destroy_process_group()
-sys.stdout.write("slab-rank-%d-ok %s\n" % (rank, counts)); sys.stdout.flush()
+sys.stdout.write("slab-rank-%d-ok %s %s\n" % (rank, counts, owned2)); sys.stdout.flush()
 '''
 
 
@@ -246,3 +262,45 @@ def test_literal_lambda_index_is_refused_on_slabs():
     with pytest.raises(lgpu.LgpuError):
         V.step(1, dt=0.01, iterations=1, literal_lambda_index=1)
     V.close()
+
+
+@pytest.mark.gpu
+def test_free_running_slabs_replan_instead_of_overflowing():
+    """A free-running dam break drains the slabs on the left into the slab on the right.  With the boundaries planned
+    once the right slab outgrows its capacity (LGPU_ERR_CAPACITY); re-planning from the current per-column histogram
+     keeps the run going, and the particles stay those of the single-context run."""
+    domain, pos = scenes.dam_break(24)
+    kw = dict(dt=0.01, iterations=2, literal_lambda_index=0, exact_math=1)
+    steps, every = 240, 10
+    with lgpu.Context(domain, capacity_sand=len(pos)) as G:
+        G.upload_sand(pos)
+        fixed = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1)
+        V = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1)
+        overflowed = None
+        for step in range(steps):
+            G.step_fluid(**kw)
+            V.step(1, **kw)
+            if fixed is not None:
+                try:
+                    fixed.step(1, **kw)
+                    fixed.sync()
+                except lgpu.LgpuError as e:
+                    overflowed = (step, str(e))
+                    fixed = None
+            if (step + 1) % every == 0 and V.replan_if_needed():
+                print("step", step + 1, "re-planned:", V.slabs, V.counts()[0])
+        owned, _ = V.counts()
+        fixed_owned = fixed.counts()[0] if fixed is not None else None
+        print("re-plans", V.replans, "final owned", owned, "| fixed plan:", fixed_owned, "overflowed at", overflowed)
+        assert V.replans >= 1 and slabs.imbalance(owned) < 1.6
+        # the plan made once either ran out of capacity or ended far more lopsided than the re-planned one
+        if overflowed is not None:
+            assert "capacity" in overflowed[1].lower()
+        else:
+            assert slabs.imbalance(fixed_owned) > 1.5 * slabs.imbalance(owned), (fixed_owned, owned)
+            fixed.close()
+        rp, rv, _ = G.download()
+        sp, sv, _ = V.gather()
+        close(sp, rp, "position")
+        close(sv, rv, "velocity", atol=1e-3)
+        V.close()

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--side", type=int, default=40)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--kind", default="fluid", choices=["fluid"])
+    ap.add_argument("--replan-every", type=int, default=0, help="free run: check the load every R substeps and re-plan the slab boundaries when it has drifted")
+    ap.add_argument("--no-push", action="store_true", help="no initial sideways velocity: a plain free-running dam break")
+    ap.add_argument("--capacity-factor", type=float, default=1.5)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -41,7 +44,8 @@ def main():
 
     domain, pos = scenes.dam_break(args.side)
     vel0 = np.zeros_like(pos)
-    vel0[:, 0] = 12.0 * np.sin(pos[:, 2])  # pushes particles across the slab boundaries: migration every substep
+    if not args.no_push:
+        vel0[:, 0] = 12.0 * np.sin(pos[:, 2])  # pushes particles across the slab boundaries: migration every substep
     solids = scenes.floor_plate(domain[0], domain[2]) if args.kind == "sand" else None
     if args.kind == "fluid":
         kw = dict(dt=0.01, iterations=4, literal_lambda_index=0, exact_math=1)
@@ -51,10 +55,16 @@ def main():
         mode = 2
     params = lgpu.default_step_params(**kw)
 
-    S = slabs.DistributedSlab(domain, pos, solids=solids, vel=vel0, device=local_rank)
-    for _ in range(args.steps):
+    S = slabs.DistributedSlab(domain, pos, solids=solids, vel=vel0, device=local_rank, capacity_factor=args.capacity_factor)
+    worst_imbalance = 1.0
+    for k in range(args.steps):
         S.step(mode, params)
+        if args.replan_every and (k + 1) % args.replan_every == 0:
+            S.G.sync()
+            worst_imbalance = max(worst_imbalance, slabs.imbalance(S.counts()[0]))
+            S.replan_if_needed()
     S.G.sync()
+    final_owned = S.counts()[0]
     info = S.G.slab_info()
     sp, sv, _ = S.gather()
     ok = True
@@ -73,7 +83,8 @@ def main():
         ok = err <= tol
         line = {"check": "mp_slab", "kind": args.kind, "world": world, "particles": len(pos), "steps": args.steps,
                 "max_abs_dx_vs_single_context": err, "max_abs_dv": verr, "tolerance": tol, "ok": ok, "slabs": [list(s) for s in S.slabs],
-                "rank0_owned": info["owned"], "rank0_ghosts": info["ghosts"]}
+                "rank0_owned": info["owned"], "rank0_ghosts": info["ghosts"], "replans": S.replans, "owned_per_rank": final_owned,
+                "worst_imbalance_seen": worst_imbalance}
         print(json.dumps(line), flush=True)
         G.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
