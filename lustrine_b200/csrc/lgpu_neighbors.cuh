@@ -372,7 +372,12 @@ __device__ __forceinline__ void brick_loop(const View& v, const float4* __restri
         if (sh.work[e] < 0) break;
         mbar_wait(&sh.dfull[e], (uint32_t)(it >> 1) & 1u);
         const BrickDesc& d = sh.ring[e].d;
-        if (tid == 0) mbar_expect_tx(&sh.full, brick_stage_bytes<!BUILD>(d));
+        if (tid == 0) {
+            // (table build: the bulk store of the previous brick's table block must have read the block before anybody
+            // writes rows again — and nobody does before this barrier's phase completes, which needs this arrival)
+            if (BUILD && it > 0) bulk_wait_read();
+            mbar_expect_tx(&sh.full, brick_stage_bytes<!BUILD>(d));
+        }
         if (lane == 0) brick_stage<!BUILD>(v, d, slot, &sh.full, src, warp);
         if (tid == 1) draw(e ^ 1);  // (ring[e ^ 1]'s previous user, brick it - 1, is done: everybody passed the barrier below)
         const int n_own = d.n_own;
@@ -401,17 +406,13 @@ __device__ __forceinline__ void brick_loop(const View& v, const float4* __restri
             if (lane == 0 && mg > 0) atom_max_shared(&sh.maxg, mg);
             fence_proxy_async();  // this thread's rows are visible to the bulk store of the block
         }
-        __syncthreads();  // the brick is done: slot and descriptor may be reused
-        if (BUILD && d.mode == 0) {
-            if (tid == 0) {
-                const int g = sh.maxg;
-                v.brick_rec[d.work].d.maxg = g;
-                bulk_s2g(v.nbr16 + d.tab_off, slot.tab, 8u * (uint32_t)d.n_pad * (uint32_t)(1 + g));
-                bulk_commit();
-                bulk_wait_read();
-                sh.maxg = 0;
-            }
-            __syncthreads();  // (the store has read the block)
+        __syncthreads();  // the brick is done: the staged positions and the descriptor may be reused
+        if (BUILD && d.mode == 0 && tid == 0) {
+            const int g = sh.maxg;
+            v.brick_rec[d.work].d.maxg = g;
+            bulk_s2g(v.nbr16 + d.tab_off, slot.tab, 8u * (uint32_t)d.n_pad * (uint32_t)(1 + g));
+            bulk_commit();
+            sh.maxg = 0;
         }
     }
     if (BUILD && tid == 0) bulk_wait_all();

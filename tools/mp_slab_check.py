@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--replan-every", type=int, default=0, help="free run: check the load every R substeps and re-plan the slab boundaries when it has drifted")
     ap.add_argument("--no-push", action="store_true", help="no initial sideways velocity: a plain free-running dam break")
     ap.add_argument("--capacity-factor", type=float, default=1.5)
+    ap.add_argument("--wide", action="store_true", help="a domain the splash never leaves (8 x 3 x 6 sides): no predicted position outside the grid, "
+                    "where a slab bins per axis and the single context wraps like the reference (DESIGN.md §6)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -43,6 +45,9 @@ def main():
     world = dist.get_world_size()
 
     domain, pos = scenes.dam_break(args.side)
+    if args.wide:
+        domain = (8 * args.side, 3 * args.side, 6 * args.side)
+        pos = pos + np.array([0.0, 0.0, 2.0 * args.side], np.float32)
     vel0 = np.zeros_like(pos)
     if not args.no_push:
         vel0[:, 0] = 12.0 * np.sin(pos[:, 2])  # pushes particles across the slab boundaries: migration every substep
