@@ -123,6 +123,16 @@ LGPU_API int lgpu_append_sand(lgpu_ctx* ctx, int n, const float* pos, const floa
  * (src/neighbors/Neighbors.cpp:288-304); after a fluid step it is the unchanged upload order.
  * Any pointer may be NULL. */
 LGPU_API int lgpu_download_sand(lgpu_ctx* ctx, float* pos, float* vel, int* flags);
+/* The same, with the positions delivered to TWO host arrays by the copy engine (the reference leaves
+ * positions_star == positions after a step, src/Simulate.cpp:111,318: the drop-in fills both without a host
+ * memcpy).  pos2 may be NULL. */
+LGPU_API int lgpu_download_sand2(lgpu_ctx* ctx, float* pos, float* pos2, float* vel, int* flags);
+/* Page-locks caller-owned host memory (the host arrays of Lustrine::Simulation, src/Lustrine.cpp:129-141) so that
+ * uploads and downloads run at the PCIe rate instead of through the driver's bounce buffers.  Optional: every
+ * transfer also works with pageable memory.  lgpu_host_is_pinned: 1 if ptr lies in page-locked memory, else 0. */
+LGPU_API int lgpu_host_register(void* ptr, size_t bytes);
+LGPU_API int lgpu_host_unregister(void* ptr);
+LGPU_API int lgpu_host_is_pinned(const void* ptr);
 LGPU_API int lgpu_num_sand(const lgpu_ctx* ctx);
 LGPU_API int lgpu_num_solids(const lgpu_ctx* ctx);
 

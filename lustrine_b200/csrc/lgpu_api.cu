@@ -137,7 +137,11 @@ static int create_impl(const lgpu_config* cfg, lgpu_ctx* c, int device) {
     CUDA_TRY(dalloc(&c->perm, cap)); CUDA_TRY(dalloc(&c->key_in, cap + 4)); CUDA_TRY(dalloc(&c->rank_in, cap + 4));
     CUDA_TRY(dalloc(&c->tmp_id, cap + 4)); CUDA_TRY(dalloc(&c->key, cap));
     CUDA_TRY(dalloc(&c->cell_count, C1)); CUDA_TRY(dalloc(&c->cell_start, C1));
-    CUDA_TRY(dalloc(&c->scan_state, (C1 > cap + 4 ? C1 : cap + 4) / 4096 + 4));
+    {   // scan state: three counters and one status word per 16384-element tile, zeroed once (the scan re-arms it itself)
+        const size_t words = (C1 > cap + 4 ? C1 : cap + 4) / 4096 + 8;
+        CUDA_TRY(dalloc(&c->scan_state, words));
+        CUDA_TRY(cudaMemsetAsync(c->scan_state, 0, sizeof(unsigned long long) * words, c->stream));
+    }
     CUDA_TRY(dalloc(&c->solid_pos, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_pos_unsorted, (size_t)c->cap_solid));
     CUDA_TRY(dalloc(&c->solid_orig, (size_t)c->cap_solid)); CUDA_TRY(dalloc(&c->solid_cell_start, C1));
     // table blocks: a meta word and LGPU_MG code words per own particle, rows padded to an even count per brick
@@ -203,6 +207,7 @@ View lgpu_make_view(lgpu_ctx* c) {
     v.pos = c->pos[1]; v.vel = c->vel[1]; v.x0 = c->x0; v.pa = c->pa; v.pb = c->pb;
     v.flags = c->flags[1]; v.orig = c->orig[1]; v.perm = c->perm;
     v.key_in = c->key_in; v.rank_in = c->rank_in; v.tmp_id = c->tmp_id; v.key = c->key;
+    v.sort_rec = reinterpret_cast<int4*>(c->vel[1]);
     v.cell_count = c->cell_count; v.cell_start = c->cell_start;
     v.solid_pos = c->solid_pos; v.solid_orig = c->solid_orig; v.solid_cell_start = c->solid_cell_start;
     v.nbr16 = c->nbr16; v.nbr_cnt = c->nbr_cnt; v.nbr_spill = c->nbr_spill; v.nbr_ovf = c->nbr_ovf; v.spill_cap = c->spill_cap;
@@ -350,7 +355,7 @@ extern "C" int lgpu_upload_solids(lgpu_ctx* c, int n, const float* pos) {
     return lgpu_sort_solids(c);
 }
 
-extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flags) {
+extern "C" int lgpu_download_sand2(lgpu_ctx* c, float* pos, float* pos2, float* vel, int* flags) {
     if (!c) return LGPU_ERR_ARG;
     CUDA_TRY(cudaSetDevice(c->device));
     const int n = c->n_owned;
@@ -359,9 +364,9 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
     float* d_pos = c->d_stage;
     float* d_vel = d_pos + 3 * (size_t)n;
     int* d_flags = (int*)(d_vel + 3 * (size_t)n);
-    if (pos) {
+    if (pos || pos2) {
         k_pack3_by_orig<<<blocks, LGPU_BLOCK, 0, c->stream>>>(c->pos[0], c->orig[0], n, d_pos);
-        CUDA_TRY(cudaMemcpyAsync(pos, d_pos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        if (pos) CUDA_TRY(cudaMemcpyAsync(pos, d_pos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
     if (vel) {
@@ -374,9 +379,30 @@ extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flag
         CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
+    // (the second copy of the positions goes last: the caller's primary arrays are complete first)
+    if (pos2) CUDA_TRY(cudaMemcpyAsync(pos2, d_pos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LGPU_OK;
+}
+extern "C" int lgpu_download_sand(lgpu_ctx* c, float* pos, float* vel, int* flags) { return lgpu_download_sand2(c, pos, nullptr, vel, flags); }
+
+// ---------------- page-locked caller memory ----------------
+extern "C" int lgpu_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return LGPU_OK;
+}
+extern "C" int lgpu_host_unregister(void* ptr) {
+    if (!ptr) return LGPU_ERR_ARG;
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return LGPU_OK;
+}
+extern "C" int lgpu_host_is_pinned(const void* ptr) {
+    if (!ptr) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 // ---------------- step drivers ----------------

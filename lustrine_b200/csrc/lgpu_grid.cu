@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_fluid(View v, float dt, 
         // src/Simulate.cpp:49-50: v += gravity * mass * dt;  x* = x + v * dt
         vel = vadd<Exact>(vel, vscale<Exact>(gm, dt));
         F3 xs = vadd<Exact>(x, vscale<Exact>(vel, dt));
-        v.vel_in[i] = f4(vel);
+        // (the predicted velocity is not stored: the last solver pass rewrites v from the positions, src/Simulate.cpp:110)
         v.pstar_in[i] = f4(xs);
         if (v.g.slab && slab_classify(v, i, x, vel, xs, a)) v.flags_in[i] = a | LGPU_FLAG_GHOST;
         key = cell_id_checked(v.g, xs, v.counters);
@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_sand(View v, SandPredict
         xs.x = fminf(fmaxf(xs.x, r), P::sub(v.g.domainX, r));
         xs.y = fminf(fmaxf(xs.y, r), P::sub(v.g.domainY, r));
         xs.z = fminf(fmaxf(xs.z, r), P::sub(v.g.domainZ, r));
-        v.vel_in[i] = f4(vel);
-        v.flags_in[i] = a;
+        v.flags_in[i] = a;  // (the predicted velocity is not stored: the last contact pass rewrites v, src/Simulate.cpp:317)
         v.pstar_in[i] = f4(xs);
         if (v.g.slab && slab_classify(v, i, x, vel, xs, a)) v.flags_in[i] = a | LGPU_FLAG_GHOST;
         key = cell_id_checked(v.g, xs, v.counters);
@@ -159,12 +158,19 @@ int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p) {
 
 // ------------------------------------------------------------------------------------------
 // exclusive prefix sum over the cell histogram (inclusive scan of Sorting::counting_sort,
-// src/neighbors/Sorting.cpp:22-24, as cell offsets): ONE pass over the grid, decoupled look-back
-// between 4096-cell tiles.  Reads the histogram once (int4, coalesced), writes the offsets once and
-// zeroes the histogram for the next substep in the same pass: 12 bytes per cell.
+// src/neighbors/Sorting.cpp:22-24, as cell offsets): ONE pass over the grid.  Reads the histogram once
+// (int4, coalesced), writes the offsets once and zeroes the histogram for the next substep in the same
+// pass: 12 bytes per cell.
+// Tiles of 8192 cells, one 1024-thread block each, taken in ticket order.  A tile publishes its aggregate
+// and then looks back over its predecessors a WINDOW of 1024 tiles at a time, one status word per thread
+// (the usual warp-wide look-back walks 32 tiles per round trip to L2: 25 dependent rounds for the 400 tiles
+// of the 1 M dam break; here the whole history is one round): the nearest predecessor that already knows
+// its inclusive prefix ends the walk.
 // ------------------------------------------------------------------------------------------
-#define SCAN_THREADS 256
-#define SCAN_TILE 4096  // 4 sub-tiles of 256 threads x int4
+#define SCAN_THREADS 1024
+#define SCAN_WARPS (SCAN_THREADS / 32)
+#define SCAN_SUB 4                                // sub-tiles of 1024 threads x int4 per tile
+#define SCAN_TILE (SCAN_SUB * SCAN_THREADS * 4)   // 16384 cells: the 3.3 M cells of the 1 M dam break are 200 blocks = one wave
 
 __device__ __forceinline__ int warp_incl_scan(int x) {
 #pragma unroll
@@ -175,26 +181,40 @@ __device__ __forceinline__ int warp_incl_scan(int x) {
     return x;
 }
 
-// tile status word: bits 62..63 = 0 not ready, 1 tile aggregate, 2 inclusive prefix; low 32 bits = value
-#define SCAN_AGG (1ULL << 62)
-#define SCAN_PFX (2ULL << 62)
+// Scan state (device memory, zeroed once when it is allocated): [0] ticket counter, [1] tiles finished, [2] epoch,
+// [3 + tile] status word of the tile: bits 62..63 = 1 tile aggregate / 2 inclusive prefix, bits 32..61 = epoch of the
+// launch that wrote it, low 32 bits = value.  A word of another epoch reads as "not ready", so nothing has to be
+// cleared between launches: the last tile to finish resets the counters and bumps the epoch (launches on the stream
+// are serialised, and the same captured graph node can be replayed).
+#define SCAN_AGG 1ULL
+#define SCAN_PFX 2ULL
+#define SCAN_EPOCH_MASK 0x3fffffffULL
+__device__ __forceinline__ unsigned long long scan_word(unsigned long long flag, unsigned long long epoch, int value) {
+    return (flag << 62) | (epoch << 32) | (unsigned int)value;
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ counts, int n, int* __restrict__ starts,
                                                              unsigned long long* __restrict__ state, int zero_counts) {
-    __shared__ int warp_sums[SCAN_THREADS / 32];
+    __shared__ int warp_sums[SCAN_SUB][SCAN_WARPS];
+    __shared__ int look_sum[SCAN_WARPS], look_end[SCAN_WARPS];
     __shared__ int s_tile, s_prefix;
+    __shared__ unsigned long long s_epoch;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nb = gridDim.x;
-    if (tid == 0) s_tile = (int)atomicAdd(&state[nb], 1ULL);  // ticket: tiles start in look-back order
+    volatile unsigned long long* vs = state + 3;
+    if (tid == 0) {
+        s_epoch = *(volatile unsigned long long*)(state + 2) & SCAN_EPOCH_MASK;
+        s_tile = (int)atomicAdd(&state[0], 1ULL);  // ticket: a tile only ever waits for tiles that started before it
+    }
     __syncthreads();
     const int tile = s_tile;
+    const unsigned long long epoch = s_epoch;
     const long base = (long)tile * SCAN_TILE;
-    int4 vals[4];
-    int tsum[4];
-    int total = 0;
+    int4 vals[SCAN_SUB];
+    int tsum[SCAN_SUB], inc[SCAN_SUB];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        long idx = base + (long)k * 1024 + tid * 4;
+    for (int k = 0; k < SCAN_SUB; k++) {
+        const long idx = base + (long)k * (SCAN_THREADS * 4) + tid * 4;
         int4 a = make_int4(0, 0, 0, 0);
         if (idx + 3 < n) a = *reinterpret_cast<const int4*>(counts + idx);
         else {
@@ -204,60 +224,68 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ c
         }
         vals[k] = a;
         tsum[k] = a.x + a.y + a.z + a.w;
-        total += tsum[k];
     }
-    // block aggregate
-    int wt = total;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-    if (lane == 0) warp_sums[w] = wt;
+    for (int k = 0; k < SCAN_SUB; k++) inc[k] = warp_incl_scan(tsum[k]);
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < SCAN_SUB; k++) warp_sums[k][w] = inc[k];
+    }
     __syncthreads();
-    if (w == 0) {
-        int agg = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+    // every warp scans the SCAN_SUB x 32 warp sums for itself: offsets of its own warp and the tile aggregate
+    int woff[SCAN_SUB];
+    int agg = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
-        volatile unsigned long long* vs = state;
-        if (tile == 0) {
-            if (lane == 0) { vs[0] = SCAN_PFX | (unsigned int)agg; s_prefix = 0; }
-        } else {
-            if (lane == 0) vs[tile] = SCAN_AGG | (unsigned int)agg;
-            int running = 0;
-            int look = tile - 1 - lane;
-            while (true) {
-                unsigned long long st = look >= 0 ? vs[look] : SCAN_PFX;
-                while (__any_sync(0xffffffffu, (st >> 62) == 0)) st = look >= 0 ? vs[look] : SCAN_PFX;
-                unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                int first = pm ? __ffs(pm) - 1 : 32;
-                int contrib = lane <= first ? (int)(unsigned int)st : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                running += contrib;
-                if (pm) break;
-                look -= 32;
+    for (int k = 0; k < SCAN_SUB; k++) {
+        const int ws = warp_sums[k][lane];
+        const int wi = warp_incl_scan(ws);
+        woff[k] = agg + __shfl_sync(0xffffffffu, wi - ws, w);
+        agg += __shfl_sync(0xffffffffu, wi, 31);
+    }
+    if (tile == 0) {
+        if (tid == 0) { vs[0] = scan_word(SCAN_PFX, epoch, agg); s_prefix = 0; }
+        __syncthreads();
+    } else {
+        if (tid == 0) vs[tile] = scan_word(SCAN_AGG, epoch, agg);
+        int running = 0;
+        for (int hi = tile - 1;; hi -= SCAN_THREADS) {  // window: tiles hi, hi - 1, ..., hi - 1023 (thread t looks at hi - t)
+            const int look = hi - tid;
+            unsigned long long st = scan_word(SCAN_PFX, epoch, 0);  // (before tile 0: prefix 0)
+            if (look >= 0) {
+                const long long t0 = clock64();
+                do {
+                    st = vs[look];
+                    // (a predecessor that never publishes would be a bug or a killed launch: give up after ~2 s instead of hanging the device)
+                    if (clock64() - t0 > 4000000000LL) { st = scan_word(SCAN_PFX, epoch, 0); break; }
+                } while ((st >> 62) == 0 || ((st >> 32) & SCAN_EPOCH_MASK) != epoch);
             }
-            if (lane == 0) { vs[tile] = SCAN_PFX | (unsigned int)(running + agg); s_prefix = running; }
+            const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == SCAN_PFX);
+            const int first = pm ? __ffs(pm) - 1 : 32;
+            int contrib = lane <= first ? (int)(unsigned int)st : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            if (lane == 0) { look_sum[w] = contrib; look_end[w] = pm ? 1 : 0; }
+            __syncthreads();
+            // warps in window order until the first one that met an inclusive prefix
+            const unsigned em = __ballot_sync(0xffffffffu, look_end[lane] != 0);
+            const int wfirst = em ? __ffs(em) - 1 : 32;
+            int part = lane <= wfirst ? look_sum[lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            running += part;
+            __syncthreads();  // (look_sum / look_end are rewritten by the next window)
+            if (em) break;
         }
+        if (tid == 0) { vs[tile] = scan_word(SCAN_PFX, epoch, running + agg); s_prefix = running; }
+        __syncthreads();
     }
-    __syncthreads();
-    int carry = s_prefix;
+    const int carry = s_prefix;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        // exclusive scan of the per-thread sums of this sub-tile
-        int inc = warp_incl_scan(tsum[k]);
-        __syncthreads();
-        if (lane == 31) warp_sums[w] = inc;
-        __syncthreads();
-        int woff = 0, sub_total = 0;
-#pragma unroll
-        for (int q = 0; q < SCAN_THREADS / 32; q++) {
-            int sv = warp_sums[q];
-            if (q < w) woff += sv;
-            sub_total += sv;
-        }
-        int ex = carry + woff + inc - tsum[k];
-        long idx = base + (long)k * 1024 + tid * 4;
-        int4 a = vals[k];
-        int4 o4 = make_int4(ex, ex + a.x, ex + a.x + a.y, ex + a.x + a.y + a.z);
+    for (int k = 0; k < SCAN_SUB; k++) {
+        const int ex = carry + woff[k] + inc[k] - tsum[k];
+        const long idx = base + (long)k * (SCAN_THREADS * 4) + tid * 4;
+        const int4 a = vals[k];
+        const int4 o4 = make_int4(ex, ex + a.x, ex + a.x + a.y, ex + a.x + a.y + a.z);
         if (idx + 3 < n) {
             *reinterpret_cast<int4*>(starts + idx) = o4;
             if (zero_counts) *reinterpret_cast<int4*>(counts + idx) = make_int4(0, 0, 0, 0);
@@ -268,13 +296,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ c
         }
         // starts[n] = grand total: written by the thread that owns element n-1
         if (n - 1 >= idx && n - 1 <= idx + 3) starts[n] = ex + tsum[k];
-        carry += sub_total;
+    }
+    // the last tile to get here (every tile has read all the status words it needs by now) re-arms the state
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&state[1], 1ULL) == (unsigned long long)(nb - 1)) {
+            state[0] = 0; state[1] = 0; state[2] = (epoch + 1) & SCAN_EPOCH_MASK;
+        }
     }
 }
 
 int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts) {
     int nb = (num_cells + SCAN_TILE - 1) / SCAN_TILE;
-    CUDA_TRY(cudaMemsetAsync(c->scan_state, 0, sizeof(unsigned long long) * ((size_t)nb + 1), c->stream));
     k_scan_cells<<<nb, SCAN_THREADS, 0, c->stream>>>(counts, num_cells, starts, c->scan_state, zero_counts ? 1 : 0);
     c->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -284,25 +317,32 @@ int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells,
 // ------------------------------------------------------------------------------------------
 // scatter + stable reorder
 // ------------------------------------------------------------------------------------------
+// The scattered record of a particle: {reference slot, unsorted index, cell key}.  k_reorder ranks a particle among
+// its cell mates from the records next to its own (one contiguous read) instead of chasing index -> reference slot
+// per mate, and needs no further look-up to find its cell.
 __global__ void __launch_bounds__(LGPU_BLOCK) k_scatter_ids(View v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.n_in) return;
-    v.tmp_id[v.cell_start[v.key_in[i]] + v.rank_in[i]] = i;
+    const int key = v.key_in[i];
+    v.sort_rec[v.cell_start[key] + v.rank_in[i]] = make_int4(v.orig_in[i], i, key, 0);
 }
 
 __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= v.n_in) return;
-    int i = v.tmp_id[s];
-    int c = v.key_in[i];
+    const int4 rec = v.sort_rec[s];
+    const int mine = rec.x, i = rec.y, c = rec.z;
     if (c == v.g.C) return;  // slab mode: dead slot (trash cell), dropped
-    int b = v.cell_start[c], e = v.cell_start[c + 1];
-    int mine = v.orig_in[i];
+    // (everything the particle brings along is requested before the rank loop: one round of memory latency)
+    const float4 x = v.pos_in[i];
+    float4 ps = v.pstar_in[i];
+    const int fl = v.flags_in[i];
+    const int b = v.cell_start[c], e = v.cell_start[c + 1];
     int r;
     if (e - b <= LGPU_STABLE_MAX) {
         // stable order inside the cell (ascending reference slot, src/neighbors/Sorting.cpp:26-33): rank among the cell's members
         r = 0;
-        for (int u = b; u < e; u++) r += (v.orig_in[v.tmp_id[u]] < mine) ? 1 : 0;
+        for (int u = b; u < e; u++) r += (v.sort_rec[u].x < mine) ? 1 : 0;
     } else {
         // More members than any packing puts into one cell: particles whose coordinates left the grid and were clamped
         // into a border cell (undefined behaviour in the reference).  The quadratic re-rank is skipped;
@@ -310,15 +350,15 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) 
         r = s - b;
         if (s == b) atomicAdd(&v.counters[2], 1ULL);
     }
-    int dst = b + r;
-    v.pos[dst] = v.pos_in[i];
-    v.vel[dst] = v.vel_in[i];
+    const int dst = b + r;
+    v.pos[dst] = x;
+    // (the sorted copy of the velocities is not kept: both solvers recompute v from the positions at the end of the
+    // step, src/Simulate.cpp:110,317)
     // the w lane of a predicted position carries the particle's own sorted slot: the sand solver gets the
     // storage slot of a staged neighbour from it (the fluid solver overwrites it with lambda)
-    float4 ps = v.pstar_in[i];
     ps.w = __int_as_float(dst);
     v.x0[dst] = ps;
-    v.flags[dst] = v.flags_in[i];
+    v.flags[dst] = fl;
     v.key[dst] = c;
     v.perm[dst] = mine;
     // the reference permutes its own storage in the sand path (src/neighbors/Neighbors.cpp:296-300):
@@ -435,7 +475,8 @@ int lgpu_counting_sort(const int* keys, int n, int num_cells, int* sorted, int d
     CUDA_TRY(cudaMalloc(&d_sorted, sizeof(int) * n));
     CUDA_TRY(cudaMalloc(&d_counts, sizeof(int) * ((size_t)num_cells + 1)));
     CUDA_TRY(cudaMalloc(&d_starts, sizeof(int) * ((size_t)num_cells + 1)));
-    CUDA_TRY(cudaMalloc(&tmpctx.scan_state, sizeof(unsigned long long) * ((size_t)nb + 2)));
+    CUDA_TRY(cudaMalloc(&tmpctx.scan_state, sizeof(unsigned long long) * ((size_t)nb + 4)));
+    CUDA_TRY(cudaMemsetAsync(tmpctx.scan_state, 0, sizeof(unsigned long long) * ((size_t)nb + 4), tmpctx.stream));
     CUDA_TRY(cudaMemcpyAsync(d_keys, keys, sizeof(int) * n, cudaMemcpyHostToDevice, tmpctx.stream));
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * ((size_t)num_cells + 1), tmpctx.stream));
     k_cs_hist<<<lgpu_blocks(n), LGPU_BLOCK, 0, tmpctx.stream>>>(d_keys, n, d_ranks, d_counts);

@@ -159,6 +159,7 @@ struct View {
     float4 *pa, *pb;         // ping-pong predicted positions of the solver iterations
     int *flags, *orig, *perm;
     int *key_in, *rank_in, *tmp_id, *key;
+    int4* sort_rec;  // scattered {reference slot, unsorted index, cell key} records of the sort (lives in the unused sorted-velocity buffer)
     int *cell_count, *cell_start;
     // solids, sorted by cell once (src/neighbors/Neighbors.cpp:266-272)
     float4* solid_pos;

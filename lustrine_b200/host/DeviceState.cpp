@@ -46,6 +46,30 @@ void DeviceState::make_context(Simulation* s, int capacity_sand) {
         LGPU_MUST(lgpu_upload_solids(ctx, s->num_solid_particles, reinterpret_cast<const float*>(s->positions + s->ptr_solid_start)));
 }
 
+// Page-locks the live part of the host arrays a SYNC_FULL / SYNC_RESIDENT step transfers (positions, positions_star,
+// velocities, attracted: the first `capacity` sand slots), so that the copies run at the PCIe rate; the arrays stay the
+// caller's (src/Lustrine.cpp:129-141 allocates them, clean_simulation frees them).  LUSTRINE_B200_PIN_HOST=0 keeps them
+// pageable; a failing registration is not an error (the transfers work either way).
+void DeviceState::pin_host(Simulation* s) {
+    unpin_host();
+    const char* env = std::getenv("LUSTRINE_B200_PIN_HOST");
+    if (env && std::atoi(env) == 0) return;
+    const size_t n = (size_t)capacity;
+    void* ptrs[4] = {s->positions + s->ptr_sand_start, s->positions_star + s->ptr_sand_start, s->velocities + s->ptr_sand_start,
+                     s->attracted + s->ptr_sand_start};
+    const size_t bytes[4] = {n * sizeof(glm::vec3), n * sizeof(glm::vec3), n * sizeof(glm::vec3), n * sizeof(int)};
+    for (int k = 0; k < 4; k++) {
+        if (!ptrs[k] || lgpu_host_register(ptrs[k], bytes[k]) != LGPU_OK) { unpin_host(); return; }
+        pinned[k] = ptrs[k];
+    }
+    host_pinned = true;
+}
+
+void DeviceState::unpin_host() {
+    for (int k = 0; k < 4; k++) { if (pinned[k]) lgpu_host_unregister(pinned[k]); pinned[k] = nullptr; }
+    host_pinned = false;
+}
+
 DeviceState* DeviceState::create(Simulation* s, float kernel_radius_scale) {
     DeviceState* d = new DeviceState();
     d->kernel_radius_scale = kernel_radius_scale;
@@ -57,6 +81,7 @@ DeviceState* DeviceState::create(Simulation* s, float kernel_radius_scale) {
     if (cap > d->capacity_limit) cap = d->capacity_limit;
     if (cap < live) cap = live;
     d->make_context(s, cap > 0 ? cap : 1);
+    d->pin_host(s);
     d->upload(s);
     return d;
 }
@@ -71,11 +96,13 @@ void DeviceState::ensure_capacity(Simulation* s, int needed) {
     lgpu_destroy(ctx);
     ctx = nullptr;
     make_context(s, (int)grown);
+    pin_host(s);
     device_sand = 0;
 }
 
 void DeviceState::destroy(DeviceState* d) {
     if (!d) return;
+    d->unpin_host();
     lgpu_destroy(d->ctx);
     delete d;
 }
@@ -89,16 +116,19 @@ void DeviceState::upload(Simulation* s) {
 }
 
 void DeviceState::download(Simulation* s) {
-    LGPU_MUST(lgpu_download_sand(ctx, reinterpret_cast<float*>(s->positions + s->ptr_sand_start),
-                                 reinterpret_cast<float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
-    // the reference leaves positions_star == positions after a step (src/Simulate.cpp:111,318)
-    std::memcpy(s->positions_star + s->ptr_sand_start, s->positions + s->ptr_sand_start, sizeof(glm::vec3) * (size_t)lgpu_num_sand(ctx));
+    // the reference leaves positions_star == positions after a step (src/Simulate.cpp:111,318): with page-locked host
+    // arrays the copy engine delivers the positions to both (12 B per particle over PCIe instead of a host memcpy)
+    float* star = reinterpret_cast<float*>(s->positions_star + s->ptr_sand_start);
+    LGPU_MUST(lgpu_download_sand2(ctx, reinterpret_cast<float*>(s->positions + s->ptr_sand_start), host_pinned ? star : nullptr,
+                                  reinterpret_cast<float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
+    if (!host_pinned) std::memcpy(star, s->positions + s->ptr_sand_start, sizeof(glm::vec3) * (size_t)lgpu_num_sand(ctx));
+    device_matches_host = true;
 }
 
 void DeviceState::download_positions_into(float* dst) { LGPU_MUST(lgpu_download_sand(ctx, dst, nullptr, nullptr)); }
 
 void DeviceState::append_from_host(Simulation* s, int first, int count) {
-    if (sync_mode == SYNC_FULL) return;  // the next step uploads everything anyway
+    if (sync_mode == SYNC_FULL) { device_matches_host = false; return; }  // the next step uploads everything anyway
     if (device_sand + count > capacity) {
         // the context is re-created larger; `first .. first + count` are already in the host arrays, so one upload brings
         // everything (the old particles just downloaded, and the new ones)
@@ -155,7 +185,7 @@ void DeviceState::step(Simulation* s, float dt, int mode) {
         s->first_iteration = false;
     }
     if (sync_mode != SYNC_LAZY) download(s);
-    else LGPU_MUST(lgpu_sync(ctx));
+    else { device_matches_host = false; LGPU_MUST(lgpu_sync(ctx)); }
     LGPU_MUST(lgpu_last_step_ms(ctx, 0, &last_ms));
     Profiling::record(2, last_ms * 1e-3);
 }

@@ -17,7 +17,9 @@ struct DeviceState {
     bool literal_lambda_index = true;  // reference behaviour
     bool exact_math = true;
     bool prev_attract_flag = false;    // the reference keeps this in a function-local static (src/Simulate.cpp:185)
-    bool host_pinned = false;
+    bool host_pinned = false;          // the live part of the host arrays is page-locked (pin_host)
+    void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool device_matches_host = false;  // the device positions equal the host arrays (set by download, cleared by host-side appends)
     float last_ms = 0.0f;
     int device_sand = 0;               // particles resident on the device
     int capacity = 0;                  // sand slots of the device context (grows on demand, see ensure_capacity)
@@ -29,6 +31,8 @@ struct DeviceState {
 
     void make_context(Simulation* s, int capacity_sand);          // (re)creates the lgpu context with that many sand slots
     void ensure_capacity(Simulation* s, int needed);              // grows the context (x1.5) when the sources outgrow it
+    void pin_host(Simulation* s);                                // page-locks the first `capacity` sand slots of the host arrays
+    void unpin_host();
     void upload(Simulation* s);                                  // host arrays -> device (positions, velocities, attracted)
     void download(Simulation* s);                                // device -> host arrays
     void download_positions_into(float* dst);

@@ -49,7 +49,8 @@ DUMP_KEYS, DUMP_PERM, DUMP_ORIG, DUMP_NBR_COUNT, DUMP_NBR, DUMP_DENSITY, DUMP_LA
 # every symbol include/lgpu.h declares
 SYMBOLS = [
     "lgpu_default_step_params", "lgpu_create", "lgpu_destroy", "lgpu_last_error", "lgpu_get_grid",
-    "lgpu_upload_sand", "lgpu_upload_solids", "lgpu_append_sand", "lgpu_download_sand", "lgpu_num_sand",
+    "lgpu_upload_sand", "lgpu_upload_solids", "lgpu_append_sand", "lgpu_download_sand", "lgpu_download_sand2",
+    "lgpu_host_register", "lgpu_host_unregister", "lgpu_host_is_pinned", "lgpu_num_sand",
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
     "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_graph_stats", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
@@ -79,6 +80,10 @@ def lib():
         L.lgpu_append_sand.argtypes = [vp, c_i, vp, vp, vp]
         L.lgpu_upload_solids.argtypes = [vp, c_i, vp]
         L.lgpu_download_sand.argtypes = [vp, vp, vp, vp]
+        L.lgpu_download_sand2.argtypes = [vp, vp, vp, vp, vp]
+        L.lgpu_host_register.argtypes = [vp, C.c_size_t]
+        L.lgpu_host_unregister.argtypes = [vp]
+        L.lgpu_host_is_pinned.argtypes = [vp]
         L.lgpu_num_sand.argtypes = [vp]
         L.lgpu_num_solids.argtypes = [vp]
         L.lgpu_step_fluid.argtypes = [vp, C.POINTER(StepParams)]

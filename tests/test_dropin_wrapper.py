@@ -31,7 +31,7 @@ def test_wrapper_symbols_exported():
         assert re.search(r"_ZN8Lustrine\d+%s" % cxx, out), "C++ API function %s not exported" % cxx
 
 
-def run_scenario(w, steps, flags=None, with_source_sink=False, host_sync=0):
+def run_scenario(w, steps, flags=None, with_source_sink=False, host_sync=0, pinned_out=False):
     data = w.init((30, 30, 30), 0.5, sand=[((10, 10, 10), (5.0, 8.0, 5.0))],
                   solids=[((24, 1, 24), (0.0, 0.0, 0.0), 2), ((4, 3, 4), (8.0, 1.0, 8.0), 2)], subdivision=1)
     if host_sync:
@@ -46,7 +46,7 @@ def run_scenario(w, steps, flags=None, with_source_sink=False, host_sync=0):
     for s in range(steps):
         att, blow = flags[s] if flags else (False, False)
         w.L.simulate(0.016, att, blow)
-        trace["pos"].append(w.positions())
+        trace["pos"].append(w.positions(pinned_out))
         trace["n"].append(w.L.get_num_sand_particles())
         trace["q"].append((w.query((4.0, 0.0, 4.0), (16.0, 12.0, 16.0), False), w.query((0.0, 0.0, 0.0), (30.0, 4.0, 30.0), True)))
     w.L.cleanup_simulation()
@@ -95,4 +95,23 @@ def test_device_capacity_grows_with_the_sources(host_sync, monkeypatch):
     assert got["q"] == ref["q"]
     worst = max(float(np.abs(a - b).max()) for a, b in zip(got["pos"], ref["pos"]))
     print("  growth under host_sync %d: max|dx| %.3e" % (host_sync, worst))
+    assert worst <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pin_host,pinned_out", [("0", False), ("1", True), ("0", True)])
+def test_host_arrays_pageable_or_page_locked(pin_host, pinned_out, monkeypatch):
+    """The drop-in page-locks the live part of the Simulation's host arrays (positions, positions_star, velocities,
+    attracted) and lets the copy engine fill positions_star and a page-locked simulation_bind_positions_copy
+    destination; LUSTRINE_B200_PIN_HOST=0 keeps everything pageable.  Same frames either way, sources growing the
+    registered range included."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    kw = dict(steps=24, flags=None, with_source_sink=True)
+    ref = run_scenario(Wrapper(O.REF_LIT_SO), **kw)
+    monkeypatch.setenv("LUSTRINE_B200_PIN_HOST", pin_host)
+    monkeypatch.setenv("LUSTRINE_B200_MAX_SAND", str(ref["n0"][0]))  # the first spawn re-creates the context and re-registers
+    got = run_scenario(Wrapper(OURS), pinned_out=pinned_out, **kw)
+    assert got["n"] == ref["n"] and got["q"] == ref["q"]
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(got["pos"], ref["pos"]))
     assert worst <= 1e-5

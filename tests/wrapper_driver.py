@@ -89,8 +89,14 @@ class Wrapper:
             self.L.init_simulation_extra_parameters(C.byref(p), C.byref(data), sg, len(sand), og, len(solids), subdivision, extra[0], extra[1])
         return data
 
-    def positions(self):
+    def positions(self, pinned=False):
         n = self.L.get_num_sand_particles()
+        if pinned:  # a page-locked caller buffer (the drop-in fills it with the copy engine)
+            import torch
+            buf = torch.zeros((max(n, 1), 3), dtype=torch.float32).pin_memory()
+            if n:
+                self.L.simulation_bind_positions_copy(buf.data_ptr())
+            return buf.numpy()[:n].copy()
         out = np.zeros((n, 3), np.float32)
         if n:
             self.L.simulation_bind_positions_copy(out.ctypes.data)
