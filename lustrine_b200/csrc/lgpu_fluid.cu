@@ -112,8 +112,10 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
             const float li = ci.w;
             if (table) {
                 uint32_t far = 0;
+                const unsigned long long xi_xy = pack2(xi.x, xi.y);
                 replay_row<true>(ck, cnt, [&](float4 pj, uint32_t, int k) {
-                    const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+                    const float2 dxy = unpack2(sub2_rn(xi_xy, pack2(pj.x, pj.y)));  // (one FADD2 for the x and y lanes)
+                    const float dx = dxy.x, dy = dxy.y, dz = xi.z - pj.z;
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     const float len = sqrt_approx(r2);
                     const float x = fmaf(r2, fmaf(len, fp.xA, -fp.xB), fp.kx);   // W / W(s_corr_dq)

@@ -180,8 +180,10 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
         if (table) {
             float acc = 0.0f, sum = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
             uint32_t far = 0;
+            const unsigned long long xi_xy = pack2(xi.x, xi.y);
             replay_row<true>(ck, cnt, [&](float4 pj, uint32_t, int k) {
-                const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
+                const float2 dxy = unpack2(sub2_rn(xi_xy, pack2(pj.x, pj.y)));  // (one FADD2 for the x and y lanes)
+                const float dx = dxy.x, dy = dxy.y, dz = xi.z - pj.z;
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 const float len = sqrt_approx(r2);
                 acc = fmaf(r2, fmaf(len, fp.fA, -fp.fB), acc);       // sum of W/cubic_k - 1

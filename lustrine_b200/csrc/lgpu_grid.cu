@@ -161,16 +161,16 @@ int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p) {
 // src/neighbors/Sorting.cpp:22-24, as cell offsets): ONE pass over the grid.  Reads the histogram once
 // (int4, coalesced), writes the offsets once and zeroes the histogram for the next substep in the same
 // pass: 12 bytes per cell.
-// Tiles of 8192 cells, one 1024-thread block each, taken in ticket order.  A tile publishes its aggregate
-// and then looks back over its predecessors a WINDOW of 1024 tiles at a time, one status word per thread
+// Tiles of 8192 cells, one 512-thread block each, taken in ticket order.  A tile publishes its aggregate
+// and then looks back over its predecessors a WINDOW of 512 tiles at a time, one status word per thread
 // (the usual warp-wide look-back walks 32 tiles per round trip to L2: 25 dependent rounds for the 400 tiles
 // of the 1 M dam break; here the whole history is one round): the nearest predecessor that already knows
 // its inclusive prefix ends the walk.
 // ------------------------------------------------------------------------------------------
-#define SCAN_THREADS 1024
+#define SCAN_THREADS 512
 #define SCAN_WARPS (SCAN_THREADS / 32)
-#define SCAN_SUB 4                                // sub-tiles of 1024 threads x int4 per tile
-#define SCAN_TILE (SCAN_SUB * SCAN_THREADS * 4)   // 16384 cells: the 3.3 M cells of the 1 M dam break are 200 blocks = one wave
+#define SCAN_SUB 4                                // sub-tiles of 512 threads x int4 per tile
+#define SCAN_TILE (SCAN_SUB * SCAN_THREADS * 4)   // 8192 cells: the 3.3 M cells of the 1 M dam break are 401 blocks, three per SM = one wave
 
 __device__ __forceinline__ int warp_incl_scan(int x) {
 #pragma unroll
@@ -193,7 +193,7 @@ __device__ __forceinline__ unsigned long long scan_word(unsigned long long flag,
     return (flag << 62) | (epoch << 32) | (unsigned int)value;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ counts, int n, int* __restrict__ starts,
+__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_cells(int* __restrict__ counts, int n, int* __restrict__ starts,
                                                              unsigned long long* __restrict__ state, int zero_counts) {
     __shared__ int warp_sums[SCAN_SUB][SCAN_WARPS];
     __shared__ int look_sum[SCAN_WARPS], look_end[SCAN_WARPS];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ c
     int agg = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_SUB; k++) {
-        const int ws = warp_sums[k][lane];
+        const int ws = lane < SCAN_WARPS ? warp_sums[k][lane] : 0;
         const int wi = warp_incl_scan(ws);
         woff[k] = agg + __shfl_sync(0xffffffffu, wi - ws, w);
         agg += __shfl_sync(0xffffffffu, wi, 31);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ c
     } else {
         if (tid == 0) vs[tile] = scan_word(SCAN_AGG, epoch, agg);
         int running = 0;
-        for (int hi = tile - 1;; hi -= SCAN_THREADS) {  // window: tiles hi, hi - 1, ..., hi - 1023 (thread t looks at hi - t)
+        for (int hi = tile - 1;; hi -= SCAN_THREADS) {  // window: tiles hi, hi - 1, ..., hi - 511 (thread t looks at hi - t)
             const int look = hi - tid;
             unsigned long long st = scan_word(SCAN_PFX, epoch, 0);  // (before tile 0: prefix 0)
             if (look >= 0) {
@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells(int* __restrict__ c
             if (lane == 0) { look_sum[w] = contrib; look_end[w] = pm ? 1 : 0; }
             __syncthreads();
             // warps in window order until the first one that met an inclusive prefix
-            const unsigned em = __ballot_sync(0xffffffffu, look_end[lane] != 0);
+            const unsigned em = __ballot_sync(0xffffffffu, lane < SCAN_WARPS && look_end[lane] != 0);
             const int wfirst = em ? __ffs(em) - 1 : 32;
-            int part = lane <= wfirst ? look_sum[lane] : 0;
+            int part = (lane <= wfirst && lane < SCAN_WARPS) ? look_sum[lane] : 0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             running += part;

@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
             } else {
                 RowWriter w;
                 w.init(ck);
+                const unsigned long long xi_xy = pack2(xi.x, xi.y);
                 // No solid near: the reference order is simply ascending sorted slot over the 9 columns (fluid: self
                 // included; sand: self skipped — SURVEY F7).  Per column, 32 candidates at a time (one round unless the
                 // cells are crowded): test them with the Exact predicate into a hit mask, then emit the hits.
@@ -259,15 +260,14 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
                         const uint32_t first = (uint32_t)c0;
                         // `out` collects one bit per candidate, shifted in from the right: candidate t ends up at bit n-1-t.
                         // The bit is the sign of h2 - r2 (set <=> r2 > h2; the rounded difference has the exact sign and is
-                        // +0 on equality), so a test costs the 8 separately rounded operations of the reference's
-                        // predicate (src/neighbors/Neighbors.cpp:433-435) plus one FADD and one funnel shift.
+                        // +0 on equality), so a test costs the separately rounded operations of the reference's
+                        // predicate (src/neighbors/Neighbors.cpp:433-435; x and y as a packed pair: dist2_exact) plus one FADD and one funnel shift.
                         uint32_t out = 0;
                         const uint32_t a = slot_addr(stage_addr, first);
 #pragma unroll 4
                         for (int t = 0; t < n; t++) {
                             const float4 pj = lds128(a + 16u * (uint32_t)t);
-                            const F3 dd = vsub<Exact>(xi, f3(pj));
-                            out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, vdot<Exact>(dd, dd))), out, 1);
+                            out = __funnelshift_l(__float_as_uint(__fsub_rn(g.h2, dist2_exact(xi_xy, xi.z, pj))), out, 1);
                         }
                         uint32_t m = ~out & (0xffffffffu >> (32 - n));  // hits; candidate t at bit n-1-t
                         const uint32_t top = first + (uint32_t)(n - 1);  // code of bit k = top - k

@@ -215,6 +215,37 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
     return r;
 }
+// Packed fp32 pairs (sm_100a FADD2 / FMUL2): both components are rounded to nearest like the scalar instructions,
+// so the Exact policy may use them.  (x, y) of a float4 loaded with one LDS.128 already is an aligned register pair.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// |xi - pj|^2 in the reference's operation order, every operation separately rounded (src/neighbors/Neighbors.cpp:433-435:
+// (dx*dx + dy*dy) + dz*dz), the x and y lanes computed as a pair: 6 instructions instead of 8
+__device__ __forceinline__ float dist2_exact(unsigned long long xi_xy, float xi_z, float4 pj) {
+    const unsigned long long d = sub2_rn(xi_xy, pack2(pj.x, pj.y));
+    const float2 sq = unpack2(mul2_rn(d, d));
+    const float dz = __fsub_rn(xi_z, pj.z);
+    return __fadd_rn(__fadd_rn(sq.x, sq.y), __fmul_rn(dz, dz));
+}
+
 // shared address of stage slot `code`: one IMAD (the compiler's own shift/mask/add sequence takes three)
 __device__ __forceinline__ uint32_t slot_addr(uint32_t stage_addr, uint32_t code) {
     uint32_t a;

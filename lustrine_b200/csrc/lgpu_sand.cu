@@ -121,15 +121,27 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
         F3 deltap = f3(0.0f, 0.0f, 0.0f);
         bool touched = false;
         if (!(word & LGPU_CNT_WALK) && mode == 0) {
-            // Looped replay (one group of four per iteration, the next group's codes loaded one ahead): the
-            // contact body is long, and unrolling it over the whole row made the kernel ~300 KB of code that
-            // missed the instruction cache a quarter of the time.  The old position of a sand neighbour in
-            // contact is read from the sorted storage at the slot its staged x* carries in the w lane.
+            // Two sweeps over the row.  Only a third of a list's entries are in contact (on a packing at rest: the 6
+            // nearest of 18 neighbours within h), but a warp runs the long contact body whenever ANY of its lanes needs
+            // it — i.e. for every entry.  So the first sweep only evaluates the contact predicate (the reference's,
+            // src/Simulate.cpp:235-240, Exact) into a bit mask, and the second runs the contact + friction body over the
+            // set bits: max-over-lanes(contacts) trips instead of the full row.  Same entries, same order, same
+            // arithmetic: entries that are not in contact never touched deltap.  The old position of a sand neighbour
+            // in contact is read from the sorted storage at the slot its staged x* carries in the w lane.
             const uint32_t solid_base = (uint32_t)ck.d->solid_base;
-            replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t code, int) {
+            uint32_t contact = 0;
+            const unsigned long long pi_xy = pack2(pi.x, pi.y);
+            replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t, int k) {
+                if (!(dist2_exact(pi_xy, pi.z, pj) > sp.d2_contact_max)) contact |= 1u << k;
+            });
+            while (contact) {
+                const int k = __ffs(contact) - 1;
+                contact &= contact - 1;
+                const uint32_t code = row_code(ck, k);
+                const float4 pj = lds128(slot_addr(stage_addr, code));
                 const bool is_sand = code < solid_base;
                 sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
-            });
+            }
             if ((word & LGPU_CNT_MASK) > 4 * LGPU_MG) {
                 const float4 r = sand_spill<P>(v, sp, ck, word & LGPU_CNT_MASK, pi, xi_old, deltap, touched);
                 deltap = f3(r.x, r.y, r.z); touched = r.w != 0.0f;
