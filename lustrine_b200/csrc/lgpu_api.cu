@@ -423,7 +423,7 @@ static int enqueue_step(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     st = mode == 1 ? lgpu_launch_predict_fluid(c, p) : lgpu_launch_predict_sand(c, p);
     if (st) return st;
     lgpu_mark(c, 2);
-    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C + 1, true);  // + the trash cell of slab mode
+    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C + 1, true, lgpu_pdl_enabled(c));  // + the trash cell of slab mode; chained to the predict kernel
     if (st) return st;
     lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, mode == 2);

@@ -209,8 +209,7 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
     const bool slab = lgpu_slab_active(c);
     // programmatic dependent launch between the passes and, in slab mode, through the refresh kernels (not with
     // per-launch event marks in between); LGPU_PDL=0 turns it off
-    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);
+    const bool pdl = lgpu_pdl_enabled(c) && lgpu_slab_pdl_ok(c);
     for (int it = 0; it < iterations; it++) {
         float4* next = bufs[it & 1];
         if (it > 0) {  // (the first density + lambda pass ran inside the table build)

@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_cells(int* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nb = gridDim.x;
     volatile unsigned long long* vs = state + 3;
+    pdl_trigger();
+    pdl_wait();  // (a no-op unless the launch is chained programmatically to its predecessor)
     if (tid == 0) {
         s_epoch = *(volatile unsigned long long*)(state + 2) & SCAN_EPOCH_MASK;
         s_tile = (int)atomicAdd(&state[0], 1ULL);  // ticket: a tile only ever waits for tiles that started before it
@@ -306,9 +308,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan_cells(int* __restrict_
     }
 }
 
-int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts) {
+int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts, bool pdl) {
     int nb = (num_cells + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_cells<<<nb, SCAN_THREADS, 0, c->stream>>>(counts, num_cells, starts, c->scan_state, zero_counts ? 1 : 0);
+    CUDA_TRY(launch_pdl(k_scan_cells, nb, SCAN_THREADS, 0, c->stream, pdl, counts, num_cells, starts, c->scan_state, zero_counts ? 1 : 0));
     c->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
@@ -322,6 +324,8 @@ int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells,
 // per mate, and needs no further look-up to find its cell.
 __global__ void __launch_bounds__(LGPU_BLOCK) k_scatter_ids(View v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (i >= v.n_in) return;
     const int key = v.key_in[i];
     v.sort_rec[v.cell_start[key] + v.rank_in[i]] = make_int4(v.orig_in[i], i, key, 0);
@@ -329,6 +333,8 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_scatter_ids(View v) {
 
 __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (s >= v.n_in) return;
     const int4 rec = v.sort_rec[s];
     const int mine = rec.x, i = rec.y, c = rec.z;
@@ -370,8 +376,11 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_reorder(View v, int reset_orig) 
 int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig) {
     if (c->n_in == 0) return LGPU_OK;
     View v = lgpu_make_view(c);
-    k_scatter_ids<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v);
-    k_reorder<<<lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream>>>(v, reset_orig ? 1 : 0);
+    // chained programmatically to the scan (and k_reorder to k_scatter_ids) on a single GPU; slab mode has plain
+    // launches in between
+    const bool pdl = lgpu_pdl_enabled(c) && !c->g.slab;
+    CUDA_TRY(launch_pdl(k_scatter_ids, lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream, pdl, v));
+    CUDA_TRY(launch_pdl(k_reorder, lgpu_blocks(c->n_in), LGPU_BLOCK, 0, c->stream, pdl, v, reset_orig ? 1 : 0));
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LGPU_OK;
@@ -425,7 +434,7 @@ int lgpu_sort_solids(lgpu_ctx* c) {
         int *ranks = keys + n4, *tmp = ranks + n4, *counts = tmp + n4;  // (counts is 16-byte aligned: the scan loads int4)
         CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * ((size_t)C + 2), c->stream));
         k_solid_keys<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->g, c->solid_pos_unsorted, n, keys, ranks, counts, c->counters);
-        int st = lgpu_launch_scan_cells(c, counts, c->solid_cell_start, C + 1, false);
+        int st = lgpu_launch_scan_cells(c, counts, c->solid_cell_start, C + 1, false, false);
         if (st) return st;
         k_solid_scatter<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(keys, ranks, c->solid_cell_start, n, tmp);
         k_solid_reorder<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->solid_pos_unsorted, keys, c->solid_cell_start, tmp, n, c->solid_pos, c->solid_orig, C);
@@ -480,7 +489,7 @@ int lgpu_counting_sort(const int* keys, int n, int num_cells, int* sorted, int d
     CUDA_TRY(cudaMemcpyAsync(d_keys, keys, sizeof(int) * n, cudaMemcpyHostToDevice, tmpctx.stream));
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(int) * ((size_t)num_cells + 1), tmpctx.stream));
     k_cs_hist<<<lgpu_blocks(n), LGPU_BLOCK, 0, tmpctx.stream>>>(d_keys, n, d_ranks, d_counts);
-    int st = lgpu_launch_scan_cells(&tmpctx, d_counts, d_starts, num_cells, false);
+    int st = lgpu_launch_scan_cells(&tmpctx, d_counts, d_starts, num_cells, false, false);
     if (st) return st;
     k_solid_scatter<<<lgpu_blocks(n), LGPU_BLOCK, 0, tmpctx.stream>>>(d_keys, d_ranks, d_starts, n, d_tmp);
     k_cs_rank<<<lgpu_blocks(n), LGPU_BLOCK, 0, tmpctx.stream>>>(d_keys, d_starts, d_tmp, n, d_sorted);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "lgpu.h"
 
@@ -281,7 +282,37 @@ int lgpu_put_sand(lgpu_ctx* c, int offset, int n, const float* pos, const float*
 // ---- launch wrappers, one per translation unit ----
 int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p);
 int lgpu_launch_predict_sand(lgpu_ctx* c, const lgpu_step_params& p);
-int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts);
+// Programmatic dependent launch between consecutive kernels of the substep: a kernel lets its successor start
+// launching as soon as all of its own blocks are resident (pdl_trigger at the top); the successor's blocks
+// become resident as this kernel's blocks retire and its producer warps wait for this kernel's memory
+// (pdl_wait) before they touch anything — launch latency and ramp-up overlap the previous kernel's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// programmatic dependent launch between the kernels of a captured substep (programmatic edges of the CUDA graph)
+static inline bool lgpu_pdl_in_graph() {
+    static const bool off = getenv("LGPU_PDL_GRAPH") && atoi(getenv("LGPU_PDL_GRAPH")) == 0;  // (LGPU_PDL_GRAPH=0: plain edges)
+    return !off;
+}
+// whether the launches of this substep are chained programmatically (not with per-launch event marks in between;
+// LGPU_PDL=0 turns it off everywhere)
+static inline bool lgpu_pdl_enabled(const lgpu_ctx* c) {
+    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
+    return pdl_env && !c->phase_timing && (!c->use_graph || lgpu_pdl_in_graph());
+}
+int lgpu_launch_scan_cells(lgpu_ctx* c, int* counts, int* starts, int num_cells, bool zero_counts, bool pdl);
 int lgpu_launch_reorder(lgpu_ctx* c, bool reset_orig);
 int lgpu_sort_solids(lgpu_ctx* c);
 int lgpu_begin_passes(lgpu_ctx* c);

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __gri
     __shared__ int ss32[LGPU_DESC_WARPS][LGPU_HCOLS][LGPU_HB];   // ... sorted solid slot
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int brick = blockIdx.x * LGPU_DESC_WARPS + wib;
+    pdl_trigger();
+    pdl_wait();  // the cell offsets are the sort's
     if (brick >= v.NB) return;
     const Geom& g = v.g;
     const int by = brick / (v.nbX * v.nbZ);
@@ -319,9 +321,9 @@ int lgpu_launch_build_table(lgpu_ctx* c, bool sand_order, const lgpu_step_params
     if (c->n == 0) return LGPU_OK;  // (slab mode: the solver drivers still run the refresh protocol)
     View v = lgpu_make_view(c);
     FluidParams fp = lgpu_make_fluid_params(c->g, p);
-    k_brick_desc<<<(c->NB + LGPU_DESC_WARPS - 1) / LGPU_DESC_WARPS, LGPU_DESC_WARPS * 32, 0, c->stream>>>(v);
-    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph;
+    const bool pdl = lgpu_pdl_enabled(c);
+    // (slab mode: the predecessor of k_brick_desc is a plain launch of the refresh-list kernels, not a kernel of this chain)
+    CUDA_TRY(launch_pdl(k_brick_desc, (c->NB + LGPU_DESC_WARPS - 1) / LGPU_DESC_WARPS, LGPU_DESC_WARPS * 32, 0, c->stream, pdl && !c->g.slab, v));
     int st;
     if (sand_order) st = launch_build<true, LM_NONE>(c, v, fp, pdl);
     else switch (lambda_mode) {

@@ -166,7 +166,7 @@ extern "C" int lgpu_remove_in_cells(lgpu_ctx* c, const int* cell_ids, int n_cell
     k_fill_int<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(keep, n, 1);
     int m = n_dead > n_moved ? n_dead : n_moved;
     if (m) k_apply_moves<<<lgpu_blocks(m), LGPU_BLOCK, 0, c->stream>>>(inv, d_dead, n_dead, d_moved, n_moved, keep, c->orig[0]);
-    int st = lgpu_launch_scan_cells(c, keep, dst, n, false);
+    int st = lgpu_launch_scan_cells(c, keep, dst, n, false, false);
     if (st) return st;
     k_compact<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(v, keep, dst, n);
     c->launches += 4;
@@ -216,7 +216,7 @@ extern "C" int lgpu_aabb_first_k(lgpu_ctx* c, const float center[3], const float
     F3 ha; ha.x = half[0]; ha.y = half[1]; ha.z = half[2];
     k_invert_orig<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(c->orig[0], n, inv);
     k_aabb_flags<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(v, n, ce, ha, flag);
-    int st = lgpu_launch_scan_cells(c, flag, rank, n, false);
+    int st = lgpu_launch_scan_cells(c, flag, rank, n, false, false);
     if (st) return st;
     float* d_out = c->d_stage;
     k_aabb_gather<<<lgpu_blocks(n), LGPU_BLOCK, 0, c->stream>>>(v, n, flag, rank, inv, k, d_out);

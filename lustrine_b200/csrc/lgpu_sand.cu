@@ -198,8 +198,7 @@ int lgpu_launch_sand_solver(lgpu_ctx* c, const lgpu_step_params& p) {
     const size_t smem = LGPU_BRICK_SMEM;
     const float4* cur = c->x0;
     float4* bufs[2] = {c->pa, c->pb};
-    static const bool pdl_env = !(getenv("LGPU_PDL") && atoi(getenv("LGPU_PDL")) == 0);
-    const bool pdl = pdl_env && !c->phase_timing && !c->use_graph && lgpu_slab_pdl_ok(c);  // see run_fluid
+    const bool pdl = lgpu_pdl_enabled(c) && lgpu_slab_pdl_ok(c);  // see run_fluid
     for (int it = 0; it < K; it++) {
         float4* next = bufs[it & 1];
         const bool last = it == K - 1;

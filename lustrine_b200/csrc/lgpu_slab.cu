@@ -403,7 +403,7 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     }
     int st;
     lgpu_mark(c, 2);
-    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C + 1, true);
+    st = lgpu_launch_scan_cells(c, c->cell_count, c->cell_start, c->g.C + 1, true, false);
     if (st) return st;
     lgpu_mark(c, 3);
     st = lgpu_launch_reorder(c, false);  // particle ids are global: never renumbered
