@@ -570,12 +570,17 @@ def wrapper_e2e(workload, steps, sync_mode):
     ms = (time.perf_counter() - t0) * 1e3 / steps
     checksum = float(out.double().sum())
     W.L.cleanup_simulation()
-    h2d = n * 28 if sync_mode == 0 else 0
-    d2h = n * (28 + 12) if sync_mode == 0 else n * 12
+    # per particle, SYNC_FULL: up positions 12 + velocities 12 (+ attracted 4 for a sand step: simulate_fluid never touches
+    # it); down the same plus positions_star 12 (the reference leaves it equal to positions) plus the 12 of
+    # simulation_bind_positions_copy — all by the copy engine, the Simulation's host arrays being page-locked
+    fl = 0 if kind == "fluid" else 4
+    h2d = n * (24 + fl) if sync_mode == 0 else 0
+    d2h = n * (24 + fl + 12 + 12) if sync_mode == 0 else n * 12
     return {"value": n / (ms * 1e-3), "unit": "particle-substeps/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": steps, "particles": int(n), "position_checksum": checksum,
             "path": "LustrineWrapper C API on liblustrine_b200.so: simulate(dt, attract, blow) + simulation_bind_positions_copy(pinned buffer), "
-                    + ("SYNC_FULL (host arrays authoritative: positions, velocities, attracted uploaded and downloaded every step)" if sync_mode == 0
+                    + ("SYNC_FULL (host arrays authoritative: positions, velocities (and attracted around a sand step) uploaded and downloaded "
+                       "every step, positions_star refreshed; the Simulation's host arrays are page-locked by the drop-in)" if sync_mode == 0
                        else "SYNC_LAZY (state resident on the device, positions copied out every step)")}
 
 

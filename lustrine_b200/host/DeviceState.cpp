@@ -107,20 +107,25 @@ void DeviceState::destroy(DeviceState* d) {
     delete d;
 }
 
-void DeviceState::upload(Simulation* s) {
+// with_flags = false: the step about to run is simulate_fluid, which neither reads nor writes Simulation::attracted
+// (src/Simulate.cpp:27-115): 4 bytes per particle less in either direction
+void DeviceState::upload(Simulation* s, bool with_flags) {
     const int n = s->ptr_sand_end - s->ptr_sand_start;
     ensure_capacity(s, n);
     LGPU_MUST(lgpu_upload_sand(ctx, n, reinterpret_cast<const float*>(s->positions + s->ptr_sand_start),
-                               reinterpret_cast<const float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
+                               reinterpret_cast<const float*>(s->velocities + s->ptr_sand_start),
+                               with_flags ? s->attracted + s->ptr_sand_start : nullptr));
     device_sand = n;
+    device_flags_valid = with_flags;
 }
 
-void DeviceState::download(Simulation* s) {
+void DeviceState::download(Simulation* s, bool with_flags) {
     // the reference leaves positions_star == positions after a step (src/Simulate.cpp:111,318): with page-locked host
     // arrays the copy engine delivers the positions to both (12 B per particle over PCIe instead of a host memcpy)
     float* star = reinterpret_cast<float*>(s->positions_star + s->ptr_sand_start);
     LGPU_MUST(lgpu_download_sand2(ctx, reinterpret_cast<float*>(s->positions + s->ptr_sand_start), host_pinned ? star : nullptr,
-                                  reinterpret_cast<float*>(s->velocities + s->ptr_sand_start), s->attracted + s->ptr_sand_start));
+                                  reinterpret_cast<float*>(s->velocities + s->ptr_sand_start),
+                                  with_flags && device_flags_valid ? s->attracted + s->ptr_sand_start : nullptr));
     if (!host_pinned) std::memcpy(star, s->positions + s->ptr_sand_start, sizeof(glm::vec3) * (size_t)lgpu_num_sand(ctx));
     device_matches_host = true;
 }
@@ -156,7 +161,13 @@ int DeviceState::cell_count(const int lo[3], const int hi[3], bool include_solid
 }
 
 void DeviceState::step(Simulation* s, float dt, int mode) {
-    if (sync_mode == SYNC_FULL) upload(s);
+    // (a fluid step leaves `attracted` alone: under SYNC_FULL it is not even uploaded; the device copy of the other
+    // modes stays what the last sand step or upload made it)
+    // (... unless a particle sink is configured: an eviction moves the last particle's `attracted` along with it,
+    // src/Lustrine.cpp:829, and the device does that move)
+    const bool with_flags = mode != 1 || (s->sink && s->sink->num_sinks > 0);
+    if (sync_mode == SYNC_FULL) upload(s, with_flags);
+    else if (with_flags && !device_flags_valid) upload(s, true);  // (a sand step after fluid steps that never brought the flags)
     lgpu_step_params p;
     lgpu_default_step_params(&p);
     p.dt = dt;
@@ -184,7 +195,7 @@ void DeviceState::step(Simulation* s, float dt, int mode) {
         prev_attract_flag = s->attract_flag;  // :323
         s->first_iteration = false;
     }
-    if (sync_mode != SYNC_LAZY) download(s);
+    if (sync_mode != SYNC_LAZY) download(s, with_flags);
     else { device_matches_host = false; LGPU_MUST(lgpu_sync(ctx)); }
     LGPU_MUST(lgpu_last_step_ms(ctx, 0, &last_ms));
     Profiling::record(2, last_ms * 1e-3);

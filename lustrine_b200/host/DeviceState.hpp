@@ -19,6 +19,7 @@ struct DeviceState {
     bool prev_attract_flag = false;    // the reference keeps this in a function-local static (src/Simulate.cpp:185)
     bool host_pinned = false;          // the live part of the host arrays is page-locked (pin_host)
     void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool device_flags_valid = true;    // the device holds Simulation::attracted (false after a flag-less upload for a fluid step)
     bool device_matches_host = false;  // the device positions equal the host arrays (set by download, cleared by host-side appends)
     float last_ms = 0.0f;
     int device_sand = 0;               // particles resident on the device
@@ -33,8 +34,8 @@ struct DeviceState {
     void ensure_capacity(Simulation* s, int needed);              // grows the context (x1.5) when the sources outgrow it
     void pin_host(Simulation* s);                                // page-locks the first `capacity` sand slots of the host arrays
     void unpin_host();
-    void upload(Simulation* s);                                  // host arrays -> device (positions, velocities, attracted)
-    void download(Simulation* s);                                // device -> host arrays
+    void upload(Simulation* s, bool with_flags = true);                                  // host arrays -> device (positions, velocities, attracted)
+    void download(Simulation* s, bool with_flags = true);                                // device -> host arrays
     void download_positions_into(float* dst);
     void append_from_host(Simulation* s, int first, int count);  // particle sources
     int remove_in_cells(Simulation* s, const std::vector<int>& cells);
