@@ -22,24 +22,24 @@
 #define LGPU_BY 4
 #define LGPU_BX 4
 #ifndef LGPU_BZ
-#define LGPU_BZ 7
+#define LGPU_BZ 8                                   // (4 x 4 x 8 cells hold ~476 particles of the unit lattice: 15 chunks of 32 for the 16 chunk slots of two rounds of 8 warps)
 #endif
 #define LGPU_HX (LGPU_BX + 2)
 #define LGPU_HCOLS ((LGPU_BY + 2) * (LGPU_BX + 2))  // 36 halo columns
 #define LGPU_HB (LGPU_BZ + 3)                       // cell boundaries of a halo column (BZ + 2 cells)
 #define LGPU_OWN_COLS (LGPU_BY * LGPU_BX)           // 16
 #ifndef LGPU_BRICK_WARPS
-#define LGPU_BRICK_WARPS 8                          // warps of a block of the staged kernels (a brick of the unit lattice has 14-17 chunks of 32 particles at BZ = 7)
+#define LGPU_BRICK_WARPS 8                          // warps of a block of the staged kernels (a brick of the unit lattice has 13-19 chunks of 32 particles at BZ = 8)
 #endif
 #define LGPU_BRICK_THREADS (LGPU_BRICK_WARPS * 32)
 #ifndef LGPU_CTAS_PER_SM
 #define LGPU_CTAS_PER_SM 3                          // blocks of the staged kernels per SM: while one waits for its copies the others gather
 #endif
 #ifndef LGPU_STAGE_SLOTS
-#define LGPU_STAGE_SLOTS 1600    // float4 slots of the staged neighbourhood of a block (unit lattice: <= 1408 at BZ = 7)
+#define LGPU_STAGE_SLOTS 1700    // float4 slots of the staged neighbourhood of a block (unit lattice: <= 1600 at BZ = 8)
 #endif
 #ifndef LGPU_ROW_CAP
-#define LGPU_ROW_CAP 576         // own particles of a brick whose table block fits the block's shared memory (unit lattice: <= 539 at BZ = 7)
+#define LGPU_ROW_CAP 608         // own particles of a brick whose table block fits the block's shared memory (unit lattice: <= 588 at BZ = 8 but for the 1.6 % of bricks that hold 7 x 7 x 13: those are cut)
 #endif
 #define LGPU_MG 8                // table groups (of four 16-bit codes) per row: M = 32
 #define LGPU_SPILL 32            // codes of a spill chunk: a list of 33 .. 64 entries keeps its tail in one (global memory)
