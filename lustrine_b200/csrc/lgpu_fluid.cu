@@ -74,7 +74,7 @@ __device__ __noinline__ float3 deltap_spill(const View& v, const FluidParams& fp
     const Geom& g = v.g;
     const bool literal = fp.literal_lambda_index != 0;
     F3 f = f3(f0.x, f0.y, f0.z);
-    replay_spill<false>(v, ck, cnt, [&](float4 pj, uint32_t, int t) {
+    replay_spill<false>(v, ck.i, ck.stage_addr, cnt, [&](float4 pj, uint32_t, int t) {
         const float lj = literal ? (t < LGPU_LAMBDA_HEAD ? v.lambda_head[t] : 0.0f) : pj.w;
         deltap_pair<P, POLY6>(g, fp, xi, f3(pj), li, lj, f);
     });

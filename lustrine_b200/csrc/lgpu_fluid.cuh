@@ -160,7 +160,7 @@ __device__ __noinline__ float2 lambda_walk(const View& v, const FluidParams& fp,
 template <class P, bool POLY6>
 __device__ __noinline__ LambdaAcc<P, POLY6> lambda_spill(const View& v, const FluidParams& fp, const Chunk& ck, int cnt, F3 xi, LambdaAcc<P, POLY6> acc) {
     const Geom& g = v.g;
-    replay_spill<false>(v, ck, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
+    replay_spill<false>(v, ck.i, ck.stage_addr, cnt, [&](float4 pj, uint32_t, int) { acc.pair(g, fp, xi, f3(pj)); });
     return acc;
 }
 

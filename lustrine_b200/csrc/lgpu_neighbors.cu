@@ -153,38 +153,46 @@ __global__ void __launch_bounds__(LGPU_DESC_WARPS * 32) k_brick_desc(const __gri
 // Collects the 16-bit codes of a table row in the lane's row of the slot's table block (shared memory, [group][own
 // particle]); the finished block goes to global memory with one bulk copy, and the row is still at hand for the first
 // density + lambda pass.
+// entry number cnt >= M of a row goes into the list's spill chunk (rare).  Out of line, and everything by value: an
+// object whose address is passed to an out-of-line function would have to live in local memory.  state = address of
+// the list's spill chunk (0: none yet) | bit 63: the list is lost (no chunk left, or more than M + LGPU_SPILL entries:
+// the solver passes re-walk).
+#define LGPU_ROW_LOST (1ULL << 63)
+__device__ __noinline__ unsigned long long row_put_spill(const View& v, int i, int cnt, uint32_t code, unsigned long long state) {
+    const int k = cnt - 4 * LGPU_MG;
+    if (k == 0) {
+        const int chunk = atomicAdd(&v.brick_ctl[3], 1);
+        if (chunk < v.spill_cap) { state = (unsigned long long)(uintptr_t)(v.nbr_spill + (size_t)chunk * (LGPU_SPILL / 4)); v.nbr_ovf[i] = chunk; }
+        else state = LGPU_ROW_LOST;
+    }
+    if (k >= LGPU_SPILL) state |= LGPU_ROW_LOST;
+    if (!(state & LGPU_ROW_LOST)) reinterpret_cast<unsigned short*>((uintptr_t)state)[k] = (unsigned short)code;
+    return state;
+}
 struct RowWriter {
     uint32_t base, stride;    // shared address of the lane's first group; bytes between groups
     int cnt;
-    unsigned short* spill;    // the list's spill chunk (entries M .. M + LGPU_SPILL - 1), once it has one
-    bool lost;                // no spill chunk left, or more than M + LGPU_SPILL entries: the solver passes re-walk
-    __device__ __forceinline__ void init(const Chunk& ck) {
-        base = ck.row_addr; stride = ck.row_stride;
-        cnt = 0; spill = nullptr; lost = false;
+    unsigned long long state; // see row_put_spill
+    __device__ __forceinline__ void init(uint32_t row_addr, uint32_t row_stride) {
+        base = row_addr; stride = row_stride;
+        cnt = 0; state = 0;
     }
+    __device__ __forceinline__ bool lost() const { return (state & LGPU_ROW_LOST) != 0; }
     __device__ __forceinline__ void put(int k, uint32_t code) {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)(k >> 2) * stride + (uint32_t)(k & 3) * 2u), "h"((unsigned short)code) : "memory");
     }
-    // entry number cnt >= M: into the spill chunk (rare)
-    __device__ __noinline__ void put_spill(const View& v, int i, uint32_t code) {
-        const int k = cnt - 4 * LGPU_MG;
-        if (k == 0) {
-            const int chunk = atomicAdd(&v.brick_ctl[3], 1);
-            if (chunk < v.spill_cap) { spill = reinterpret_cast<unsigned short*>(v.nbr_spill + (size_t)chunk * (LGPU_SPILL / 4)); v.nbr_ovf[i] = chunk; }
-            else lost = true;
-        }
-        if (k >= LGPU_SPILL) lost = true;
-        if (!lost) spill[k] = (unsigned short)code;
-    }
     __device__ __forceinline__ void emit(const View& v, int i, uint32_t code) {
         if (cnt < 4 * LGPU_MG) put(cnt, code);
-        else put_spill(v, i, code);
+        else state = row_put_spill(v, i, cnt, code, state);
         cnt++;
     }
     __device__ __forceinline__ void emit_unchecked(uint32_t code) { put(cnt, code); cnt++; }  // the caller has checked cnt + (codes to come) <= M
     __device__ __forceinline__ void finish(uint32_t pad) {  // completes the last group with the padding code
         if (cnt <= 4 * LGPU_MG) { for (int k = cnt; k & 3; k++) put(k, pad); }
-        else if (!lost) { for (int k = cnt - 4 * LGPU_MG; k & 3; k++) spill[k] = (unsigned short)pad; }
+        else if (!lost()) {
+            unsigned short* spill = reinterpret_cast<unsigned short*>((uintptr_t)state);
+            for (int k = cnt - 4 * LGPU_MG; k & 3; k++) spill[k] = (unsigned short)pad;
+        }
     }
 };
 
@@ -192,16 +200,16 @@ struct RowWriter {
 // stencil over the global storage in the reference's nested order (per cell: sand then solids in the fluid lists,
 // solids then sand in the sand lists) and translate what they find into stage slots of their brick.
 template <bool SAND>
-__device__ __noinline__ int build_row_walk(const View& v, const BrickDesc& d, const Chunk& ck, F3 xi, int ly, int lx, uint32_t pad) {
+__device__ __noinline__ int build_row_walk(const View& v, const BrickDesc& d, int i, uint32_t row_addr, uint32_t row_stride, F3 xi, int ly, int lx, uint32_t pad) {
     RowWriter w;
-    w.init(ck);
-    walk<SAND>(v, ck.i, xi, [&](int j, int r) {
+    w.init(row_addr, row_stride);
+    walk<SAND>(v, i, xi, [&](int j, int r) {
         const int hc = (ly + r / 3) * LGPU_HX + lx + r % 3;  // halo column of stencil column r = 3 (dy + 1) + (dx + 1)
-        if (j >= 0) w.emit(v, ck.i, (uint32_t)(d.col[hc].s0 + (j - d.col[hc].g0)));
-        else w.emit(v, ck.i, (uint32_t)(d.scol[hc].s0 + (~j - d.scol[hc].g0)));
+        if (j >= 0) w.emit(v, i, (uint32_t)(d.col[hc].s0 + (j - d.col[hc].g0)));
+        else w.emit(v, i, (uint32_t)(d.scol[hc].s0 + (~j - d.scol[hc].g0)));
     });
     w.finish(pad);
-    return w.lost ? -w.cnt : w.cnt;
+    return w.lost() ? -w.cnt : w.cnt;
 }
 
 template <bool SAND, int LM>
@@ -247,10 +255,10 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
             const uint32_t pad = SAND ? 0u : self_code;
             int cnt;
             if (slow) {
-                cnt = build_row_walk<SAND>(v, d, ck, xi, ly, lx, pad);
+                cnt = build_row_walk<SAND>(v, d, i, ck.row_addr, ck.row_stride, xi, ly, lx, pad);
             } else {
                 RowWriter w;
-                w.init(ck);
+                w.init(ck.row_addr, ck.row_stride);
                 const unsigned long long xi_xy = pack2(xi.x, xi.y);
                 // No solid near: the reference order is simply ascending sorted slot over the 9 columns (fluid: self
                 // included; sand: self skipped — SURVEY F7).  Per column, 32 candidates at a time (one round unless the
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
                     }
                 }
                 w.finish(pad);
-                cnt = w.lost ? -w.cnt : w.cnt;
+                cnt = w.lost() ? -w.cnt : w.cnt;
             }
             // (cnt < 0: the list did not fit the table row plus a spill chunk)
             word = cnt < 0 ? -cnt : cnt;

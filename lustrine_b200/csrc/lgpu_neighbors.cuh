@@ -460,8 +460,8 @@ __device__ __forceinline__ void replay_row(const Chunk& ck, int cnt, Body&& body
 // ... and the tail of a list longer than the table width from its spill chunk (global memory; a few particles per
 // thousand in a collapsing dam break): entries M .. cnt-1.  Called from out-of-line functions only (the hot loops stay small).
 template <bool PAD, class Body>
-__device__ __forceinline__ void replay_spill(const View& v, const Chunk& ck, int cnt, Body&& body) {
-    const uint2* sp = v.nbr_spill + (size_t)v.nbr_ovf[ck.i] * (LGPU_SPILL / 4);
+__device__ __forceinline__ void replay_spill(const View& v, int i, uint32_t stage_addr, int cnt, Body&& body) {
+    const uint2* sp = v.nbr_spill + (size_t)v.nbr_ovf[i] * (LGPU_SPILL / 4);
     const int ng = (cnt - 4 * LGPU_MG + 3) >> 2;
     for (int g = 0; g < ng; g++) {
         const uint2 w = sp[g];
@@ -470,7 +470,7 @@ __device__ __forceinline__ void replay_spill(const View& v, const Chunk& ck, int
         for (int q = 0; q < 4; q++) {
             const int k = 4 * (LGPU_MG + g) + q;
             if (!PAD && k >= cnt) break;
-            body(lds128(slot_addr(ck.stage_addr, code[q])), code[q], k);
+            body(lds128(slot_addr(stage_addr, code[q])), code[q], k);
         }
     }
 }

@@ -92,10 +92,11 @@ __device__ __forceinline__ void sand_pair(const SandParams& sp, F3 pi, F3 xi_old
 }
 
 // entries 32 .. cnt-1 of a list longer than the table width (spill chunk): returns the displacement, w != 0 if touched
+// (everything by value: a Chunk passed by reference to an out-of-line function would have to live in local memory)
 template <class P>
-__device__ __noinline__ float4 sand_spill(const View& v, const SandParams& sp, const Chunk& ck, int cnt, F3 pi, F3 xi_old, F3 deltap, bool touched) {
-    const uint32_t solid_base = (uint32_t)ck.d->solid_base;
-    replay_spill<true>(v, ck, cnt, [&](float4 pj, uint32_t code, int) {
+__device__ __noinline__ float4 sand_spill(const View& v, const SandParams& sp, int i, uint32_t stage_addr, uint32_t solid_base, int cnt, F3 pi, F3 xi_old,
+                                          F3 deltap, bool touched) {
+    replay_spill<true>(v, i, stage_addr, cnt, [&](float4 pj, uint32_t code, int) {
         const bool is_sand = code < solid_base;
         sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
     });
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
                 sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
             }
             if ((word & LGPU_CNT_MASK) > 4 * LGPU_MG) {
-                const float4 r = sand_spill<P>(v, sp, ck, word & LGPU_CNT_MASK, pi, xi_old, deltap, touched);
+                const float4 r = sand_spill<P>(v, sp, i, stage_addr, solid_base, word & LGPU_CNT_MASK, pi, xi_old, deltap, touched);
                 deltap = f3(r.x, r.y, r.z); touched = r.w != 0.0f;
             }
         } else {
