@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
                 while (far) {  // neighbours beyond q = 0.5: replace the inner-branch term by the true one
                     const int k = __ffs(far) - 1;
                     far &= far - 1;
-                    const float4 pj = lds128(slot_addr(stage_addr, row_code(ck, k)));
+                    const float4 pj = lds128(code_addr(stage_addr, row_code(ck, k)));
                     const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                     const float len = sqrt_approx(r2);

@@ -195,7 +195,7 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
             while (far) {  // neighbours beyond q = 0.5: replace the inner-branch terms by the true ones
                 const int k = __ffs(far) - 1;
                 far &= far - 1;
-                const float4 pj = lds128(slot_addr(stage_addr, row_code(ck, k)));
+                const float4 pj = lds128(code_addr(stage_addr, row_code(ck, k)));
                 const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 const float len = sqrt_approx(r2);

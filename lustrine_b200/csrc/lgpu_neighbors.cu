@@ -166,7 +166,7 @@ __device__ __noinline__ unsigned long long row_put_spill(const View& v, int i, i
         else state = LGPU_ROW_LOST;
     }
     if (k >= LGPU_SPILL) state |= LGPU_ROW_LOST;
-    if (!(state & LGPU_ROW_LOST)) reinterpret_cast<unsigned short*>((uintptr_t)state)[k] = (unsigned short)code;
+    if (!(state & LGPU_ROW_LOST)) reinterpret_cast<unsigned short*>((uintptr_t)state)[k] = (unsigned short)(code << 4);
     return state;
 }
 struct RowWriter {
@@ -178,8 +178,9 @@ struct RowWriter {
         cnt = 0; state = 0;
     }
     __device__ __forceinline__ bool lost() const { return (state & LGPU_ROW_LOST) != 0; }
+    // (a stored code is the stage slot x 16: the byte offset the solver passes add to the stage's address)
     __device__ __forceinline__ void put(int k, uint32_t code) {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)(k >> 2) * stride + (uint32_t)(k & 3) * 2u), "h"((unsigned short)code) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (uint32_t)(k >> 2) * stride + (uint32_t)(k & 3) * 2u), "h"((unsigned short)(code << 4)) : "memory");
     }
     __device__ __forceinline__ void emit(const View& v, int i, uint32_t code) {
         if (cnt < 4 * LGPU_MG) put(cnt, code);
@@ -191,7 +192,7 @@ struct RowWriter {
         if (cnt <= 4 * LGPU_MG) { for (int k = cnt; k & 3; k++) put(k, pad); }
         else if (!lost()) {
             unsigned short* spill = reinterpret_cast<unsigned short*>((uintptr_t)state);
-            for (int k = cnt - 4 * LGPU_MG; k & 3; k++) spill[k] = (unsigned short)pad;
+            for (int k = cnt - 4 * LGPU_MG; k & 3; k++) spill[k] = (unsigned short)(pad << 4);
         }
     }
 };

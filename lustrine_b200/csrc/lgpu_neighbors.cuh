@@ -228,6 +228,10 @@ __device__ __forceinline__ float dist2_exact(unsigned long long xi_xy, float xi_
 }
 
 // shared address of stage slot `code`: one IMAD (the compiler's own shift/mask/add sequence takes three)
+// shared address of a table CODE: codes are byte offsets into the stage (stage slot x 16 < 65536), so the address is a
+// plain add that folds into the load's address operand
+__device__ __forceinline__ uint32_t code_addr(uint32_t stage_addr, uint32_t code) { return stage_addr + code; }
+static_assert(LGPU_STAGE_SLOTS * 16 <= 65536, "a table code is a 16-bit byte offset into the stage");
 __device__ __forceinline__ uint32_t slot_addr(uint32_t stage_addr, uint32_t code) {
     uint32_t a;
     asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(a) : "r"(code), "r"(stage_addr));
@@ -451,7 +455,7 @@ __device__ __forceinline__ void replay_row(const Chunk& ck, int cnt, Body&& body
         for (int q = 0; q < 4; q++) {
             const int k = 4 * g + q;
             if (!PAD && k >= cnt) break;
-            body(lds128(slot_addr(ck.stage_addr, code[q])), code[q], k);
+            body(lds128(code_addr(ck.stage_addr, code[q])), code[q], k);
         }
         w = wn;
     }
@@ -470,7 +474,7 @@ __device__ __forceinline__ void replay_spill(const View& v, int i, uint32_t stag
         for (int q = 0; q < 4; q++) {
             const int k = 4 * (LGPU_MG + g) + q;
             if (!PAD && k >= cnt) break;
-            body(lds128(slot_addr(stage_addr, code[q])), code[q], k);
+            body(lds128(code_addr(stage_addr, code[q])), code[q], k);
         }
     }
 }
@@ -481,7 +485,8 @@ __device__ __forceinline__ uint32_t row_code(const Chunk& ck, int k) {
 }
 
 // sorted sand slot (>= 0) or ~(sorted solid slot) (< 0) of a table code of a brick (tests: lgpu_dump)
-__device__ __forceinline__ int decode_code(const BrickDesc& d, int code) {
+__device__ __forceinline__ int decode_code(const BrickDesc& d, int code16) {
+    const int code = code16 >> 4;  // codes are stage slots x 16
     for (int hc = 0; hc < LGPU_HCOLS; hc++) {
         if (code >= d.col[hc].s0 && code < d.col[hc].s0 + d.col[hc].len) return d.col[hc].g0 + (code - d.col[hc].s0);
         if (code >= d.scol[hc].s0 && code < d.scol[hc].s0 + d.scol[hc].len) return ~(d.scol[hc].g0 + (code - d.scol[hc].s0));

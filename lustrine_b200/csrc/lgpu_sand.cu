@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
             // set bits: max-over-lanes(contacts) trips instead of the full row.  Same entries, same order, same
             // arithmetic: entries that are not in contact never touched deltap.  The old position of a sand neighbour
             // in contact is read from the sorted storage at the slot its staged x* carries in the w lane.
-            const uint32_t solid_base = (uint32_t)ck.d->solid_base;
+            const uint32_t solid_base = (uint32_t)ck.d->solid_base << 4;  // (table codes are stage slots x 16)
             uint32_t contact = 0;
             const unsigned long long pi_xy = pack2(pi.x, pi.y);
             replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t, int k) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
                 const int k = __ffs(contact) - 1;
                 contact &= contact - 1;
                 const uint32_t code = row_code(ck, k);
-                const float4 pj = lds128(slot_addr(stage_addr, code));
+                const float4 pj = lds128(code_addr(stage_addr, code));
                 const bool is_sand = code < solid_base;
                 sand_pair<P>(sp, pi, xi_old, f3(pj), is_sand, [&]() { return f3(v.pos[__float_as_int(pj.w)]); }, deltap, touched);
             }
