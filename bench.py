@@ -261,7 +261,10 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
         t1 = torch.tensor([r1["ms_per_step"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t1, op=dist.ReduceOp.MAX)
         single = {"workload": name1, "particles": s1 ** 3, "ms_per_step": float(t1.item()), "value": s1 ** 3 / (float(t1.item()) * 1e-3)}
-    S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank)
+    # fluid: a two-column ghost layer (the inner ghosts' lambdas are computed locally: K - 1 ghost refreshes per substep
+    # instead of 2K - 1); LGPU_GHOST_COLUMNS=1 for the one-column layer
+    gw = int(os.environ.get("LGPU_GHOST_COLUMNS", "2" if kind == "fluid" else "1"))
+    S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank, ghost_columns=gw)
     G = S.G
     mode = 1 if kind == "fluid" else 2
     params = lgpu.default_step_params(**step_kwargs(kind, K, dt, args.exact, 0))
@@ -391,7 +394,7 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
                                       "line is the 1M scene of BASELINE configs[1], the N-GPU lines (N > 1) the 16M scene of configs[3] (%d particles per GPU "
                                       "here); weak_efficiency below compares like with like" % (n_total // world),
                       "particles_per_gpu": [int(g[1].item()) for g in gathered],
-                      "partition": "x-slabs of whole cell columns, one-column ghost layer, migration + ghost refresh written peer-to-peer over NVLink",
+                      "partition": "x-slabs of whole cell columns, %d-column ghost layer, migration + ghost refresh written peer-to-peer over NVLink" % gw,
                       "slabs": [list(x) for x in plan], "collective": "none on the data path",
                       "arithmetic": "exact (reference op order)" if args.exact else "fast (FMA + approx rsqrt, parity-tested to 1e-5)",
                       "l2": "flushed between substeps (256 MiB write, outside the event bracket)",

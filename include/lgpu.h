@@ -72,6 +72,10 @@ typedef struct lgpu_config {
     void* stream;              /* cudaStream_t to launch on, NULL = a private non-blocking stream */
     int halo_capacity;         /* slab mode: max particles per neighbour and substep in flight (migrants, ghost
                                   copies); 0 = max(65536, capacity_sand / 4).  Must be equal on all slabs. */
+    int slab_ghost_columns;    /* slab mode: width of the ghost layer in cell columns, 1 (0 = default) or 2.  With 2 the
+                                  lambdas of the inner ghost column are computed locally (their neighbours are all
+                                  present), so a fluid substep needs K - 1 ghost refreshes instead of 2K - 1.  Must be
+                                  equal on all slabs; every slab must own at least that many columns. */
 } lgpu_config;
 
 /* Per-step scalars.  The reference re-reads them from the public Simulation struct on

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
     brick_loop<false>(v, cur, cursor, smem_raw, [&](const Chunk& ck) -> int {
         const int i = ck.i, word = ck.word, slot = ck.slot;
         const int mode = ck.d->mode;
-        if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+        if (word & (LGPU_CNT_GHOST | LGPU_CNT_GHOST_INNER)) {  // a neighbouring slab's particle: its owner sends the new position
             if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
             return 0;
         }
@@ -219,7 +219,8 @@ static int run_fluid(lgpu_ctx* c, const View& v, const FluidParams& fp, int iter
         }
         // slab mode: after each pass a small kernel copies the boundary particles' lambda (.w of cur) / corrected x*
         // (next) into the neighbours' ghost slots and waits for the neighbours' stores of the same pass
-        if (slab && !fp.literal_lambda_index) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
+        // (with a two-column ghost layer the ghosts whose lambda the owned particles read have computed it themselves)
+        if (slab && !fp.literal_lambda_index && c->g.gw < 2) { lgpu_mark(c, 8); int st = lgpu_slab_refresh(c, cur, true); if (st) return st; }
         lgpu_mark(c, 7);
         if (it == iterations - 1) CUDA_TRY(launch_pdl(k_fluid_deltap<LM, true>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));
         else CUDA_TRY(launch_pdl(k_fluid_deltap<LM, false>, grid, LGPU_BRICK_THREADS, smem, c->stream, pdl, v, fp, (const float4*)cur, next, c->brick_ctl + 8 + c->pass));

@@ -19,28 +19,35 @@
 // Slab mode, end of the predict kernels: a particle whose predicted cell column left [x_lo, x_hi)
 // emigrates to the neighbouring slab (record to the outbox); it now sits in this slab's ghost column,
 // so its slot lives on as a ghost copy that the new owner refreshes like any other ghost.  A particle
-// in the first / last owned column is sent as a ghost copy.  Returns true if the particle emigrated.
+// in the first / last gw owned columns is sent as a ghost copy.  Returns true if the particle emigrated.
 __device__ __forceinline__ bool slab_classify(const View& v, int i, F3 x, F3 vel, F3 xs, int flags) {
     const int cxg = cell_x_global(v.g, xs.x);
     const int side = cxg < v.g.x_lo ? 0 : (cxg >= v.g.x_hi ? 1 : -1);
     HaloRec rec;
     rec.pos = f4(x); rec.vel = f4(vel); rec.pstar = f4(xs); rec.flags = flags; rec.orig = v.orig_in[i]; rec.pad0 = rec.pad1 = 0;
-    if (side >= 0 && v.has_nbr[side]) {
-        int slot = atomicAdd(&v.out_cnt[side], 1);
-        if (slot < v.halo_cap) { v.out_mig[side][slot] = rec; v.mig_src[side][slot] = i; }
-        else atomicAdd(&v.out_cnt[4], 1);
-        return true;
+    // (outbox slots are handed out per warp, see warp_agg_inc; the order of the records is the message order both ends use)
+    bool emigrated = false;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const bool mig = side == s && v.has_nbr[s];
+        const int slot = warp_agg_inc(&v.out_cnt[s], mig);
+        if (mig) {
+            if (slot < v.halo_cap) { v.out_mig[s][slot] = rec; v.mig_src[s][slot] = i; }
+            else atomicAdd(&v.out_cnt[4], 1);
+            emigrated = true;
+        }
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const bool edge = s == 0 ? cxg <= v.g.x_lo : cxg >= v.g.x_hi - 1;
-        if (edge && v.has_nbr[s]) {
-            int slot = atomicAdd(&v.out_cnt[2 + s], 1);
+        const bool edge = s == 0 ? cxg < v.g.x_lo + v.g.gw : cxg >= v.g.x_hi - v.g.gw;  // the first / last gw owned columns
+        const bool gho = !emigrated && edge && v.has_nbr[s];
+        const int slot = warp_agg_inc(&v.out_cnt[2 + s], gho);
+        if (gho) {
             if (slot < v.halo_cap) { v.out_gho[s][slot] = rec; v.gho_src[s][slot] = i; }
             else atomicAdd(&v.out_cnt[4], 1);
         }
     }
-    return false;
+    return emigrated;
 }
 
 __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_fluid(View v, float dt, F3 gm /* gravity*mass */) {
@@ -64,7 +71,9 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_fluid(View v, float dt, 
         key = cell_id_checked(v.g, xs, v.counters);
     }
     v.key_in[i] = key;
-    v.rank_in[i] = atomicAdd(&v.cell_count[key], 1);
+    // (the dead slots of a slab — last step's ghosts, the emigrants — all land in the trash cell: one atomic per warp)
+    const int r_dead = v.g.slab ? warp_agg_inc(&v.cell_count[v.g.C], key == v.g.C) : -1;
+    v.rank_in[i] = key == v.g.C ? r_dead : atomicAdd(&v.cell_count[key], 1);
 }
 
 struct SandPredict {
@@ -123,7 +132,9 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_predict_sand(View v, SandPredict
         key = cell_id_checked(v.g, xs, v.counters);
     }
     v.key_in[i] = key;
-    v.rank_in[i] = atomicAdd(&v.cell_count[key], 1);
+    // (the dead slots of a slab — last step's ghosts, the emigrants — all land in the trash cell: one atomic per warp)
+    const int r_dead = v.g.slab ? warp_agg_inc(&v.cell_count[v.g.C], key == v.g.C) : -1;
+    v.rank_in[i] = key == v.g.C ? r_dead : atomicAdd(&v.cell_count[key], 1);
 }
 
 int lgpu_launch_predict_fluid(lgpu_ctx* c, const lgpu_step_params& p) {

@@ -48,6 +48,8 @@
 #define LGPU_SOLID_WINDOW 2048
 #define LGPU_CNT_WALK (1 << 30)   // nbr_cnt flag: the table row is not usable, re-walk the stencil
 #define LGPU_CNT_GHOST (1 << 29)  // nbr_cnt flag: ghost particle of a neighbouring slab (not updated here)
+#define LGPU_CNT_GHOST_INNER (1 << 28)  // nbr_cnt flag: ghost in the column next to the owned ones of a two-column ghost layer: its list is built and its
+                                        // lambda computed here (all its neighbours are present); its position still comes from its owner
 #define LGPU_CNT_MASK 0x0fffffff
 #define LGPU_CNT_SLOT_SHIFT 16    // meta word of a table block: list length (<= M) | stage slot << 16 | flags
 #define LGPU_CNT_SLOT_MASK 0x0fff0000
@@ -96,9 +98,10 @@ struct Geom {
     float cell_size, kernel_factor;
     float cubic_k, cubic_l;
     int gX, gY, gZ, gXZ, C;           // LOCAL grid of this context (== the reference's grid on a single GPU)
-    int x_off;                        // global cell x of local column 0 (slabs: x_lo - 1; single GPU: 0)
+    int x_off;                        // global cell x of local column 0 (slabs: x_lo - gw; single GPU: 0)
     int slab;                         // 1 = this context owns the cell columns [x_lo, x_hi) of a larger grid
     int x_lo, x_hi;                   // owned global cell columns (slab mode)
+    int gw;                           // ghost columns on either side of the owned ones (slab mode: 1 or 2)
 };
 
 // particle flag bits above the reference's `attracted` bits (slab mode only)
@@ -363,6 +366,20 @@ template <class P> __device__ __forceinline__ float vdot(F3 a, F3 b) {
 template <class P> __device__ __forceinline__ float vlen(F3 a) { return P::sqrt(vdot<P>(a, a)); }
 template <class P> __device__ __forceinline__ F3 vnormalize(F3 a) { return vscale<P>(a, P::div(1.0f, P::sqrt(vdot<P>(a, a)))); }
 __device__ __forceinline__ F3 vneg(F3 a) { return f3(-a.x, -a.y, -a.z); }
+
+// Warp-aggregated `atomicAdd(ctr, 1)` for the lanes with `pred`: ONE atomic per warp instead of one per lane (hundreds of
+// thousands of lanes incrementing the same counter serialise in L2: 0.1 ms per 200 k at one atomic per clock).  Called by
+// all currently active lanes of the warp; returns the lane's slot, or -1 without `pred`.
+__device__ __forceinline__ int warp_agg_inc(int* ctr, bool pred) {
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, pred);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(ctr, __popc(m));
+    base = __shfl_sync(act, base, leader);
+    return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
 
 // get_cell_id, src/neighbors/Utils.hpp:24-33: IEEE division, truncation toward zero, no clamp.
 // Ids outside [0, C) (undefined behaviour in the reference) are clamped and counted.

@@ -225,13 +225,24 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
         const F3 xi = f3(x0i);
         int word, ng = 0;
         const int flags = g.slab ? v.flags[i] : 0;
-        if (flags & LGPU_FLAG_GHOST) {  // ghost of a neighbouring slab: read by others, never updated here
+        // Ghost of a neighbouring slab: read by others, its position never updated here.  With a two-column ghost layer
+        // the ghosts of the column next to the owned ones still get a list: all their neighbours are present, so their
+        // lambda is computed locally instead of being sent by the owner after every lambda pass.
+        int ghost_word = 0;
+        if (flags & LGPU_FLAG_GHOST) {
+            ghost_word = LGPU_CNT_GHOST;
+            if (g.gw == 2 && !SAND) {
+                const int gx = __float2int_rz(__fdiv_rn(xi.x, g.cell_size));  // global cell column (get_cell_id's arithmetic)
+                if (gx == g.x_lo - 1 || gx == g.x_hi) ghost_word = LGPU_CNT_GHOST_INNER;
+            }
+        }
+        if (ghost_word == LGPU_CNT_GHOST) {
             word = LGPU_CNT_GHOST;
         } else if (d.mode != 0) {
             // neighbourhood larger than a ring slot: count only, the solver passes re-walk the stencil
             int cnt = 0;
             walk<SAND>(v, i, f3(v.x0[i]), [&](int, int) { cnt++; });
-            word = cnt | LGPU_CNT_WALK;
+            word = cnt | LGPU_CNT_WALK | ghost_word;
             atomicAdd(&v.counters[1], 1ULL);
         } else {
             const int ly = q / LGPU_BX, lx = q % LGPU_BX;
@@ -305,6 +316,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_build_
             word = cnt < 0 ? -cnt : cnt;
             if (cnt < 0 || (v.M < 4 * LGPU_MG && cnt > v.M)) { word |= LGPU_CNT_WALK; atomicAdd(&v.counters[1], 1ULL); }
             else ng = (min(cnt, 4 * LGPU_MG) + 3) >> 2;
+            word |= ghost_word;  // (LGPU_CNT_GHOST_INNER or nothing)
         }
         v.nbr_cnt[i] = word;
         const int mword = (word & LGPU_CNT_WALK) ? (word & ~LGPU_CNT_MASK) : word;  // (a re-walked row's length is not needed)

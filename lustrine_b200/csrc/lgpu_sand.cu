@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
     brick_loop<false>(v, cur, cursor, smem_raw, [&](const Chunk& ck) -> int {
         const int i = ck.i, word = ck.word;
         const int mode = ck.d->mode;
-        if (word & LGPU_CNT_GHOST) {  // a neighbouring slab's particle: its owner sends the new value
+        if (word & (LGPU_CNT_GHOST | LGPU_CNT_GHOST_INNER)) {  // a neighbouring slab's particle: its owner sends the new value
             if (LAST) v.flags_in[i] = LGPU_FLAG_DEAD;
             return 0;
         }

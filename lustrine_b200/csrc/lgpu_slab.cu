@@ -504,8 +504,9 @@ __global__ void __launch_bounds__(LGPU_BLOCK) k_compact_owned(View v, int n_stor
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_store) return;
     const int a = v.flags_in[i];
-    if (a & (LGPU_FLAG_DEAD | LGPU_FLAG_GHOST)) return;
-    const int o = atomicAdd(counter, 1);
+    const bool live = !(a & (LGPU_FLAG_DEAD | LGPU_FLAG_GHOST));
+    const int o = warp_agg_inc(counter, live);  // (one atomic per warp: millions of lanes on one counter serialise)
+    if (!live) return;
     const float4 x = v.pos_in[i], u = v.vel_in[i];
     pos[3 * o] = x.x; pos[3 * o + 1] = x.y; pos[3 * o + 2] = x.z;
     vel[3 * o] = u.x; vel[3 * o + 1] = u.y; vel[3 * o + 2] = u.z;

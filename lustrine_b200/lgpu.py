@@ -23,7 +23,7 @@ class Config(C.Structure):
     _fields_ = [("domain", c_i * 3), ("particle_radius", c_f), ("particle_diameter", c_f),
                 ("kernel_radius_scale", c_f), ("capacity_sand", c_i), ("capacity_solid", c_i),
                 ("max_neighbors", c_i), ("device", c_i), ("slab_x_lo", c_i), ("slab_x_hi", c_i),
-                ("stream", C.c_void_p), ("halo_capacity", c_i)]
+                ("stream", C.c_void_p), ("halo_capacity", c_i), ("slab_ghost_columns", c_i)]
 
 
 class StepParams(C.Structure):
@@ -148,7 +148,7 @@ class Context:
     """One device context = one Lustrine simulation's particle state on one GPU."""
 
     def __init__(self, domain, radius=0.5, diameter=1.0, capacity_sand=0, capacity_solid=0,
-                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None, slab=None, halo_capacity=0):
+                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None, slab=None, halo_capacity=0, ghost_columns=0):
         L = lib()
         cfg = Config()
         for a in range(3):
@@ -164,6 +164,7 @@ class Context:
         if slab is not None:
             cfg.slab_x_lo, cfg.slab_x_hi = int(slab[0]), int(slab[1])
         cfg.halo_capacity = int(halo_capacity)
+        cfg.slab_ghost_columns = int(ghost_columns)
         self._h = C.c_void_p()
         _check(L.lgpu_create(C.byref(cfg), C.byref(self._h)), "lgpu_create")
         self.L = L

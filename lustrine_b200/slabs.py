@@ -1,7 +1,9 @@
 """Spatial slabs: the particle domain partitioned across the GPUs of one box.
 
 Each rank (one process per GPU) owns the cell columns [x_lo, x_hi) of the reference's uniform grid
-and runs the same substep as the single-GPU path on its particles plus a one-column ghost layer.
+and runs the same substep as the single-GPU path on its particles plus a ghost layer of one or two cell
+columns (`ghost_columns`; with two, the lambdas of the inner ghost column are computed locally and a fluid substep needs
+K - 1 ghost refreshes instead of 2K - 1).
 Per substep the neighbouring slabs exchange, with no collective on the data path:
   * after predict: migrants (particles whose predicted cell column left the slab) and ghost copies
     of the particles in the first / last owned column;
@@ -35,12 +37,12 @@ def cell_x(pos, cs):
     return (np.ascontiguousarray(pos[:, 0], np.float32) / cs).astype(np.int32)
 
 
-def plan_slabs(columns, grid_x, world):
+def plan_slabs(columns, grid_x, world, min_columns=1):
     """Slab boundaries [x_lo, x_hi) per rank, whole cell columns, covering [0, grid_x), chosen from the
     per-column particle histogram so that the ranks hold (nearly) equal particle counts.
     `columns` = cell column of every particle (any order)."""
-    if world < 1 or grid_x < world:
-        raise ValueError("need at least one cell column per rank (grid_x=%d, world=%d)" % (grid_x, world))
+    if world < 1 or grid_x < world * min_columns:
+        raise ValueError("need at least %d cell column(s) per rank (grid_x=%d, world=%d)" % (min_columns, grid_x, world))
     hist = np.bincount(np.clip(columns, 0, grid_x - 1), minlength=grid_x).astype(np.int64)
     cum = np.concatenate([[0], np.cumsum(hist)])
     total = int(cum[-1])
@@ -51,8 +53,8 @@ def plan_slabs(columns, grid_x, world):
         # choose the closer of x-1 / x, keep at least one column per rank on both sides
         if x > 0 and abs(cum[x - 1] - target) <= abs(cum[min(x, grid_x)] - target):
             x -= 1
-        x = max(x, bounds[-1] + 1)
-        x = min(x, grid_x - (world - k))
+        x = max(x, bounds[-1] + min_columns)        # (a slab owns at least as many columns as the ghost layer is wide)
+        x = min(x, grid_x - (world - k) * min_columns)
         bounds.append(x)
     bounds.append(grid_x)
     return [(bounds[k], bounds[k + 1]) for k in range(world)]
@@ -69,7 +71,7 @@ def deal(pos, slabs, cs):
     return out
 
 
-def slab_capacity(pos, slabs, owned, cs, grid_x, factor=1.5):
+def slab_capacity(pos, slabs, owned, cs, grid_x, factor=1.5, ghost_columns=1):
     """Particle capacity of every slab context (equal on all ranks).  The storage of a substep holds the
     previous substep's slots (owned + ghost copies, the latter dead by then) plus the incoming ghost copies
     and migrants, so the ghost columns on both sides count twice; `factor` is the head room for
@@ -77,7 +79,7 @@ def slab_capacity(pos, slabs, owned, cs, grid_x, factor=1.5):
     hist = np.bincount(np.clip(cell_x(pos, cs), 0, grid_x - 1), minlength=grid_x).astype(np.int64)
     need = 0
     for (lo, hi), o in zip(slabs, owned):
-        ghosts = (int(hist[lo - 1]) if lo > 0 else 0) + (int(hist[hi]) if hi < grid_x else 0)
+        ghosts = int(hist[max(lo - ghost_columns, 0):lo].sum()) + int(hist[hi:min(hi + ghost_columns, grid_x)].sum())
         need = max(need, len(o) + 2 * ghosts)
     return int(need * factor) + 4096
 
@@ -152,9 +154,10 @@ class VirtualSlabs:
     def _build(self, pos, vel, flags, ids, slabs=None):
         domain, solids, device, capacity_factor, halo_capacity, ctx_kw = self._args
         cs = cell_size()
-        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
+        gw = max(int(ctx_kw.get("ghost_columns", 0)), 1)
+        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw)
         owned = deal(pos, self.slabs, cs)
-        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
+        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor, gw)
         self.ctx = [SlabContext(domain, s, self.capacity, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
         exports = [c.G.slab_export() for c in self.ctx]
         for k, c in enumerate(self.ctx):
@@ -226,9 +229,10 @@ class DistributedSlab:
         through CUDA IPC handles and uploads this rank's particles.  Returns the indices this rank owns."""
         domain, solids, device, capacity_factor, halo_capacity, factory, ctx_kw = self._args
         cs = cell_size()
-        self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world)
+        gw = max(int(ctx_kw.get("ghost_columns", 0)), 1)
+        self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw)
         owned = deal(pos, self.slabs, cs)
-        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor)
+        self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor, gw)
         self.ctx = factory(domain, self.slabs[self.rank], self.capacity, solids, device, halo_capacity, **ctx_kw)
         handle, _, _ = self.ctx.G.slab_export()
         handles = [None] * self.world

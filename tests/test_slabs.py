@@ -173,9 +173,11 @@ def close(a, b, what, rtol=REL_TOL, atol=ABS_TOL):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
-def test_fluid_slabs_match_single_context(world):
-    """P slabs == 1 slab == no slabs, same tolerances as the oracle parity (summation order only)."""
+@pytest.mark.parametrize("world,gw", [(2, 1), (3, 1), (2, 2), (3, 2)])
+def test_fluid_slabs_match_single_context(world, gw):
+    """P slabs == 1 slab == no slabs, same tolerances as the oracle parity (summation order only).  gw = width of the
+    ghost layer in cell columns: with 2 the inner ghosts' lambdas are computed locally (their lists are the owners'
+    lists, their neighbours all present) and no lambda travels between the slabs."""
     domain, pos = scenes.dam_break(16)
     solids = scenes.floor_plate(30, 20)
     vel0 = np.zeros_like(pos)
@@ -184,7 +186,7 @@ def test_fluid_slabs_match_single_context(world):
     with lgpu.Context(domain, capacity_sand=len(pos), capacity_solid=len(solids)) as G:
         G.upload_sand(pos, vel0)
         G.upload_solids(solids)
-        V = slabs.VirtualSlabs(domain, pos, world, solids=solids, vel=vel0)
+        V = slabs.VirtualSlabs(domain, pos, world, solids=solids, vel=vel0, ghost_columns=gw)
         moved = 0
         for step in range(6):
             G.step_fluid(**kw)
@@ -202,7 +204,8 @@ def test_fluid_slabs_match_single_context(world):
 
 
 @pytest.mark.gpu
-def test_sand_slabs_match_single_context():
+@pytest.mark.parametrize("gw", [1, 2])
+def test_sand_slabs_match_single_context(gw):
     domain, sand, solids = scenes.sand_pile(12, drop=1.0)
     vel0 = np.zeros_like(sand)
     vel0[:, 0] = 6.0 * np.cos(sand[:, 1])
@@ -210,7 +213,7 @@ def test_sand_slabs_match_single_context():
     with lgpu.Context(domain, capacity_sand=len(sand), capacity_solid=len(solids)) as G:
         G.upload_sand(sand, vel0)
         G.upload_solids(solids)
-        V = slabs.VirtualSlabs(domain, sand, 3, solids=solids, vel=vel0)
+        V = slabs.VirtualSlabs(domain, sand, 3, solids=solids, vel=vel0, ghost_columns=gw)
         ids = np.arange(len(sand))
         for step in range(5):
             G.step_sand(**kw)
@@ -225,7 +228,8 @@ def test_sand_slabs_match_single_context():
 
 
 @pytest.mark.gpu
-def test_slab_keys_and_neighbour_counts_are_the_single_gpu_ones():
+@pytest.mark.parametrize("gw", [1, 2])
+def test_slab_keys_and_neighbour_counts_are_the_single_gpu_ones(gw):
     domain, pos = scenes.dam_break(12)
     kw = dict(dt=0.01, iterations=1, literal_lambda_index=0, exact_math=1)
     with lgpu.Context(domain, capacity_sand=len(pos)) as G:
@@ -234,7 +238,7 @@ def test_slab_keys_and_neighbour_counts_are_the_single_gpu_ones():
         keys = G.dump(lgpu.DUMP_KEYS); orig = G.dump(lgpu.DUMP_ORIG); cnt = G.dump(lgpu.DUMP_NBR_COUNT)
         ref_key = np.zeros(len(pos), np.int64); ref_key[orig] = keys
         ref_cnt = np.zeros(len(pos), np.int64); ref_cnt[orig] = cnt
-    V = slabs.VirtualSlabs(domain, pos, 2)
+    V = slabs.VirtualSlabs(domain, pos, 2, ghost_columns=gw)
     V.step(1, **kw)
     seen = 0
     for c in V.ctx:
@@ -265,7 +269,8 @@ def test_literal_lambda_index_is_refused_on_slabs():
 
 
 @pytest.mark.gpu
-def test_free_running_slabs_replan_instead_of_overflowing():
+@pytest.mark.parametrize("gw", [1, 2])
+def test_free_running_slabs_replan_instead_of_overflowing(gw):
     """A free-running dam break drains the slabs on the left into the slab on the right.  With the boundaries planned
     once the right slab outgrows its capacity (LGPU_ERR_CAPACITY); re-planning from the current per-column histogram
      keeps the run going, and the particles stay those of the single-context run."""
@@ -274,8 +279,8 @@ def test_free_running_slabs_replan_instead_of_overflowing():
     steps, every = 240, 10
     with lgpu.Context(domain, capacity_sand=len(pos)) as G:
         G.upload_sand(pos)
-        fixed = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1)
-        V = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1)
+        fixed = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1, ghost_columns=gw)
+        V = slabs.VirtualSlabs(domain, pos, 4, capacity_factor=1.1, ghost_columns=gw)
         overflowed = None
         for step in range(steps):
             G.step_fluid(**kw)
@@ -304,3 +309,23 @@ def test_free_running_slabs_replan_instead_of_overflowing():
         close(sp, rp, "position")
         close(sv, rv, "velocity", atol=1e-3)
         V.close()
+
+
+def test_plan_keeps_slabs_as_wide_as_the_ghost_layer():
+    """With a two-column ghost layer every slab owns at least two columns (a narrower slab could not fill its
+    neighbours' outer ghost column), and the capacity estimate counts both ghost columns."""
+    rng = np.random.default_rng(3)
+    cols = np.concatenate([np.full(5000, 7), rng.integers(0, 40, 300)])  # nearly everything in one column
+    for world in (2, 4, 8):
+        plan = slabs.plan_slabs(cols, 40, world, min_columns=2)
+        assert plan[0][0] == 0 and plan[-1][1] == 40
+        assert all(hi - lo >= 2 for lo, hi in plan), plan
+        assert all(plan[k][1] == plan[k + 1][0] for k in range(world - 1))
+    with pytest.raises(ValueError):
+        slabs.plan_slabs(cols, 7, 4, min_columns=2)
+    domain, pos = scenes.dam_break(16)
+    cs = slabs.cell_size()
+    grid = slabs.grid_dims(domain, cs)
+    plan = slabs.plan_slabs(slabs.cell_x(pos, cs), grid[0], 3, min_columns=2)
+    owned = slabs.deal(pos, plan, cs)
+    assert slabs.slab_capacity(pos, plan, owned, cs, grid[0], ghost_columns=2) > slabs.slab_capacity(pos, plan, owned, cs, grid[0], ghost_columns=1)

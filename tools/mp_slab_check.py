@@ -60,7 +60,8 @@ def main():
         mode = 2
     params = lgpu.default_step_params(**kw)
 
-    S = slabs.DistributedSlab(domain, pos, solids=solids, vel=vel0, device=local_rank, capacity_factor=args.capacity_factor)
+    gw = int(os.environ.get("LGPU_GHOST_COLUMNS", "2" if mode == 1 else "1"))
+    S = slabs.DistributedSlab(domain, pos, solids=solids, vel=vel0, device=local_rank, capacity_factor=args.capacity_factor, ghost_columns=gw)
     worst_imbalance = 1.0
     for k in range(args.steps):
         S.step(mode, params)
