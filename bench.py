@@ -261,10 +261,15 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
         t1 = torch.tensor([r1["ms_per_step"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t1, op=dist.ReduceOp.MAX)
         single = {"workload": name1, "particles": s1 ** 3, "ms_per_step": float(t1.item()), "value": s1 ** 3 / (float(t1.item()) * 1e-3)}
-    # fluid: a two-column ghost layer (the inner ghosts' lambdas are computed locally: K - 1 ghost refreshes per substep
-    # instead of 2K - 1); LGPU_GHOST_COLUMNS=1 for the one-column layer
-    gw = int(os.environ.get("LGPU_GHOST_COLUMNS", "2" if kind == "fluid" else "1"))
-    S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank, ghost_columns=gw)
+    # one-column ghost layer.  (LGPU_GHOST_COLUMNS=2, fluid: the inner ghosts' lambdas are computed locally, K - 1 ghost
+    # refreshes per substep instead of 2K - 1 — measured 1.3 % SLOWER on 2 and 8 B200s: the second ghost column's work
+    # costs what the four saved handshakes gain.)
+    gw = int(os.environ.get("LGPU_GHOST_COLUMNS", "1"))
+    # the plan is cropped to the occupied cell columns + a margin (LGPU_SLAB_MARGIN=none: the whole grid, whose empty two
+    # thirds then land on the last rank)
+    m_env = os.environ.get("LGPU_SLAB_MARGIN", str(slabs.DEFAULT_MARGIN))
+    margin = None if m_env.lower() == "none" else int(m_env)
+    S = slabs.DistributedSlab(domain, sand, solids=solids, device=local_rank, ghost_columns=gw, margin=margin)
     G = S.G
     mode = 1 if kind == "fluid" else 2
     params = lgpu.default_step_params(**step_kwargs(kind, K, dt, args.exact, 0))
@@ -328,6 +333,11 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
     phase /= PH
     G.set_phase_timing(False)
     info = G.slab_info()
+    # every rank's phases and grid size (rank 0 is an edge slab: one neighbour, and without the crop not the critical path)
+    pr = torch.tensor(list(phase) + [float(info["local_cells"]), float(info["owned"]), float(info["ghosts"])], dtype=torch.float64, device="cuda")
+    pr_all = [torch.zeros_like(pr) for _ in range(world)]
+    dist.all_gather(pr_all, pr)
+    pr_all = np.array([x.cpu().numpy() for x in pr_all])
     n_local = info["owned"]
     cells_per_particle = info["local_cells"] / max(n_local, 1)
     step_bytes = fluid_bytes_per_particle(K, cells_per_particle) if kind == "fluid" else sand_bytes_per_particle(K, cells_per_particle)
@@ -347,7 +357,12 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
     roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": step_achieved / hbm_gbs,
                      "algorithmic_bytes_per_particle_substep": step_bytes, "per": "GPU",
                      "phases_ms_rank0": {"predict_key_hist_halo": phase[1], "scan": phase[2], "scatter_reorder": phase[3], "neighbour_table": phase[4],
-                                         "lambda_total": phase[6], "deltap_or_contact_total": phase[7], "halo_refresh_total": phase[8]}}
+                                         "lambda_total": phase[6], "deltap_or_contact_total": phase[7], "halo_refresh_total": phase[8]},
+                     "phases_ms_per_rank": {"predict_key_hist_halo": pr_all[:, 1].tolist(), "scan": pr_all[:, 2].tolist(), "scatter_reorder": pr_all[:, 3].tolist(),
+                                            "neighbour_table": pr_all[:, 4].tolist(), "lambda_total": pr_all[:, 6].tolist(),
+                                            "deltap_or_contact_total": pr_all[:, 7].tolist(), "halo_refresh_total": pr_all[:, 8].tolist()},
+                     "local_cells_per_rank": [int(x) for x in pr_all[:, 9]], "owned_per_rank": [int(x) for x in pr_all[:, 10]],
+                     "ghosts_per_rank": [int(x) for x in pr_all[:, 11]]}
 
     # e2e: host buffers in, host buffers out, every substep, on every rank
     e2e = None

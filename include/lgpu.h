@@ -76,6 +76,11 @@ typedef struct lgpu_config {
                                   lambdas of the inner ghost column are computed locally (their neighbours are all
                                   present), so a fluid substep needs K - 1 ghost refreshes instead of 2K - 1.  Must be
                                   equal on all slabs; every slab must own at least that many columns. */
+    int slab_guard_columns;    /* slab mode, a plan CROPPED to the occupied columns (the first slab starts at x_lo > 0 or the
+                                  last one ends at x_hi < grid x: the empty part of the domain costs no cells): the particles
+                                  in the outer `slab_guard_columns` owned columns of such an open side are counted every
+                                  substep (lgpu_slab_edge) so that the host re-plans before any particle leaves the planned
+                                  columns (which fails the step with LGPU_ERR_CAPACITY).  0 = not counted. */
 } lgpu_config;
 
 /* Per-step scalars.  The reference re-reads them from the public Simulation struct on
@@ -184,6 +189,9 @@ LGPU_API int lgpu_slab_export(lgpu_ctx* ctx, unsigned char handle[64], void** lo
 LGPU_API int lgpu_slab_connect(lgpu_ctx* ctx, int side, const unsigned char handle[64], void* same_process_ptr);
 /* out: x_lo, x_hi, local grid X, local cells, owned particles, ghost particles, halo capacity, x offset */
 LGPU_API int lgpu_slab_info(const lgpu_ctx* ctx, int out[8]);
+/* out[0] = particles of the last substep inside the guard columns of an open side of a cropped plan (see
+ * lgpu_config::slab_guard_columns; > 0: time to re-plan), out[1] = 1 if this slab has an open side */
+LGPU_API int lgpu_slab_edge(const lgpu_ctx* ctx, int out[2]);
 LGPU_API int lgpu_slab_upload(lgpu_ctx* ctx, int n, const float* pos, const float* vel, const int* flags, const int* ids);
 LGPU_API int lgpu_slab_download(lgpu_ctx* ctx, float* pos, float* vel, int* flags, int* ids, int* n_out);
 LGPU_API int lgpu_slab_step_begin(lgpu_ctx* ctx, const lgpu_step_params* p, int mode /* 1 fluid, 2 sand */);

@@ -50,6 +50,7 @@ static void make_geom(const lgpu_config& cfg, Geom* g) {
     g->gY = (int)(g->domainY / g->cell_size) + 1;
     g->gZ = (int)(g->domainZ / g->cell_size) + 1;
     g->x_off = 0; g->slab = 0; g->x_lo = 0; g->x_hi = g->gX; g->gw = 0;
+    g->gXg = g->gX; g->guard = cfg.slab_guard_columns > 0 ? cfg.slab_guard_columns : 0;
     if (cfg.slab_x_hi > cfg.slab_x_lo) {
         // spatial slab: local grid = owned columns [x_lo, x_hi) plus gw ghost columns on either side
         g->slab = 1;
@@ -84,7 +85,7 @@ extern "C" int lgpu_create(const lgpu_config* cfg, lgpu_ctx** out) {
     *out = nullptr;
     if (cfg->domain[0] <= 0 || cfg->domain[1] <= 0 || cfg->domain[2] <= 0 || cfg->particle_radius <= 0.0f ||
         cfg->capacity_sand < 0 || cfg->capacity_solid < 0 || cfg->kernel_radius_scale <= 0.0f || cfg->slab_ghost_columns < 0 ||
-        cfg->slab_ghost_columns > 2 || (cfg->slab_x_hi > cfg->slab_x_lo && cfg->slab_x_hi - cfg->slab_x_lo < cfg->slab_ghost_columns)) {
+        cfg->slab_ghost_columns > 2 || cfg->slab_guard_columns < 0 || (cfg->slab_x_hi > cfg->slab_x_lo && cfg->slab_x_hi - cfg->slab_x_lo < cfg->slab_ghost_columns)) {
         lgpu_set_error("lgpu_create: bad configuration");
         return LGPU_ERR_ARG;
     }

@@ -47,6 +47,17 @@ __device__ __forceinline__ bool slab_classify(const View& v, int i, F3 x, F3 vel
             else atomicAdd(&v.out_cnt[4], 1);
         }
     }
+    // An open side (no neighbour, and the plan stops short of the domain wall: the boundaries were cropped to the occupied
+    // columns so that the empty part of the domain costs no cells): count the particles that approach the end of the
+    // planned columns (the host re-plans) and those that have left them (the step fails).
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        if (v.has_nbr[s] || (s == 0 ? v.g.x_lo <= 0 : v.g.x_hi >= v.g.gXg)) continue;  // (uniform)
+        const bool left = s == 0 ? cxg < v.g.x_lo : cxg >= v.g.x_hi;
+        const bool near = left || (s == 0 ? cxg < v.g.x_lo + v.g.guard : cxg >= v.g.x_hi - v.g.guard);
+        warp_agg_inc(&v.out_cnt[5], near);
+        warp_agg_inc(&v.out_cnt[6], left);
+    }
     return emigrated;
 }
 

@@ -102,6 +102,8 @@ struct Geom {
     int slab;                         // 1 = this context owns the cell columns [x_lo, x_hi) of a larger grid
     int x_lo, x_hi;                   // owned global cell columns (slab mode)
     int gw;                           // ghost columns on either side of the owned ones (slab mode: 1 or 2)
+    int gXg;                          // x extent of the reference's (global) grid
+    int guard;                        // slab mode: guard columns of an open side of a cropped plan (lgpu_config::slab_guard_columns)
 };
 
 // particle flag bits above the reference's `attracted` bits (slab mode only)

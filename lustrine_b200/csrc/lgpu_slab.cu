@@ -45,6 +45,7 @@ struct SlabState {
     int halo_turn;        // which of the two halo inbox sets this substep uses
     unsigned int* push_ticket;
     bool begun;
+    int near_edge;        // particles inside the guard columns of an open side in the last substep (cropped plans)
     int n_store;
     void* d_xfer;         // device side of lgpu_slab_download (allocated once)
 };
@@ -156,6 +157,14 @@ extern "C" int lgpu_slab_info(const lgpu_ctx* c, int out[8]) {
     if (!c || !out) return LGPU_ERR_ARG;
     out[0] = c->g.x_lo; out[1] = c->g.x_hi; out[2] = c->g.gX; out[3] = c->g.C;
     out[4] = c->n_owned; out[5] = c->n_ghost; out[6] = c->slab ? c->slab->halo_cap : 0; out[7] = c->g.x_off;
+    return LGPU_OK;
+}
+
+extern "C" int lgpu_slab_edge(const lgpu_ctx* c, int out[2]) {
+    if (!c || !out) return LGPU_ERR_ARG;
+    const SlabState* S = c->slab;
+    out[0] = S ? S->near_edge : 0;
+    out[1] = S && ((!S->has_nbr[0] && c->g.x_lo > 0) || (!S->has_nbr[1] && c->g.x_hi < c->g.gXg)) ? 1 : 0;
     return LGPU_OK;
 }
 
@@ -375,6 +384,12 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
     const SlabHeader* H = (const SlabHeader*)(S->h_counts + 8);
     if (H->error) { lgpu_set_error("slab: timed out waiting for a neighbouring slab's halo message"); return LGPU_ERR_CUDA; }
     if (S->h_counts[4]) { lgpu_set_error("slab: halo capacity %d exceeded (%d records dropped)", S->halo_cap, S->h_counts[4]); return LGPU_ERR_CAPACITY; }
+    S->near_edge = S->h_counts[5];
+    if (S->h_counts[6]) {
+        lgpu_set_error("slab: %d particle(s) left the planned cell columns [%d, %d) on a side that has no neighbouring slab (a plan cropped to the "
+                       "occupied columns): re-plan earlier (lgpu_slab_edge / replan_if_needed) or plan with a wider margin", S->h_counts[6], c->g.x_lo, c->g.x_hi);
+        return LGPU_ERR_CAPACITY;
+    }
     int m[2] = {0, 0}, g[2] = {0, 0};
     const int ht = S->halo_turn;
     S->halo_turn ^= 1;
@@ -496,6 +511,7 @@ extern "C" int lgpu_slab_upload(lgpu_ctx* c, int n, const float* pos, const floa
     c->n = c->n_owned = c->n_in = n;
     c->n_ghost = 0;
     c->grid_valid = false;
+    c->slab->near_edge = 0;
     return lgpu_put_sand(c, 0, n, pos, vel, flags, ids);
 }
 

@@ -23,7 +23,7 @@ class Config(C.Structure):
     _fields_ = [("domain", c_i * 3), ("particle_radius", c_f), ("particle_diameter", c_f),
                 ("kernel_radius_scale", c_f), ("capacity_sand", c_i), ("capacity_solid", c_i),
                 ("max_neighbors", c_i), ("device", c_i), ("slab_x_lo", c_i), ("slab_x_hi", c_i),
-                ("stream", C.c_void_p), ("halo_capacity", c_i), ("slab_ghost_columns", c_i)]
+                ("stream", C.c_void_p), ("halo_capacity", c_i), ("slab_ghost_columns", c_i), ("slab_guard_columns", c_i)]
 
 
 class StepParams(C.Structure):
@@ -54,7 +54,7 @@ SYMBOLS = [
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
     "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_graph_stats", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
-    "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_upload", "lgpu_slab_download",
+    "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_edge", "lgpu_slab_upload", "lgpu_slab_download",
     "lgpu_slab_step_begin", "lgpu_slab_step_end",
 ]
 
@@ -106,6 +106,7 @@ def lib():
         L.lgpu_slab_export.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.lgpu_slab_connect.argtypes = [vp, c_i, vp, vp]
         L.lgpu_slab_info.argtypes = [vp, C.POINTER(c_i * 8)]
+        L.lgpu_slab_edge.argtypes = [vp, C.POINTER(c_i * 2)]
         L.lgpu_slab_upload.argtypes = [vp, c_i, vp, vp, vp, vp]
         L.lgpu_slab_download.argtypes = [vp, vp, vp, vp, vp, C.POINTER(c_i)]
         L.lgpu_slab_step_begin.argtypes = [vp, C.POINTER(StepParams), c_i]
@@ -148,7 +149,8 @@ class Context:
     """One device context = one Lustrine simulation's particle state on one GPU."""
 
     def __init__(self, domain, radius=0.5, diameter=1.0, capacity_sand=0, capacity_solid=0,
-                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None, slab=None, halo_capacity=0, ghost_columns=0):
+                 kernel_radius_scale=3.1, max_neighbors=0, device=-1, stream=None, slab=None, halo_capacity=0, ghost_columns=0,
+                 guard_columns=0):
         L = lib()
         cfg = Config()
         for a in range(3):
@@ -165,6 +167,7 @@ class Context:
             cfg.slab_x_lo, cfg.slab_x_hi = int(slab[0]), int(slab[1])
         cfg.halo_capacity = int(halo_capacity)
         cfg.slab_ghost_columns = int(ghost_columns)
+        cfg.slab_guard_columns = int(guard_columns)
         self._h = C.c_void_p()
         _check(L.lgpu_create(C.byref(cfg), C.byref(self._h)), "lgpu_create")
         self.L = L
@@ -287,6 +290,12 @@ class Context:
         out = (c_i * 8)()
         _check(self.L.lgpu_slab_info(self._h, C.byref(out)), "lgpu_slab_info")
         return dict(zip(("x_lo", "x_hi", "local_grid_x", "local_cells", "owned", "ghosts", "halo_capacity", "x_off"), list(out)))
+
+    def slab_edge(self):
+        """(particles of the last substep inside the guard columns of an open side of a cropped plan, slab has an open side)"""
+        out = (c_i * 2)()
+        _check(self.L.lgpu_slab_edge(self._h, C.byref(out)), "lgpu_slab_edge")
+        return int(out[0]), bool(out[1])
 
     def slab_upload(self, pos, ids, vel=None, flags=None):
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)

@@ -37,16 +37,34 @@ def cell_x(pos, cs):
     return (np.ascontiguousarray(pos[:, 0], np.float32) / cs).astype(np.int32)
 
 
-def plan_slabs(columns, grid_x, world, min_columns=1):
-    """Slab boundaries [x_lo, x_hi) per rank, whole cell columns, covering [0, grid_x), chosen from the
-    per-column particle histogram so that the ranks hold (nearly) equal particle counts.
-    `columns` = cell column of every particle (any order)."""
+DEFAULT_MARGIN = 32   # cell columns a cropped plan keeps free beyond the outermost occupied column on either side
+
+
+def plan_slabs(columns, grid_x, world, min_columns=1, margin=None):
+    """Slab boundaries [x_lo, x_hi) per rank, whole cell columns, chosen from the per-column particle histogram so
+    that the ranks hold (nearly) equal particle counts.  `columns` = cell column of every particle (any order).
+
+    margin=None: the slabs cover the whole grid [0, grid_x).  margin=m: the plan is CROPPED to the occupied columns
+    plus m free columns on either side (never beyond the grid).  A slab's scan, brick descriptors and histogram cost
+    per CELL, and the empty part of the domain used to land on the last rank: 36.7 M cells against 2.3 M on the
+    others for the 16 M dam break on 8 ranks (the fluid fills the first third of the domain), which made that rank
+    the critical path of every substep.  A cropped plan must be re-planned before the particles reach its end:
+    guard_columns(margin) is the width of the warning zone a slab context counts (lgpu_slab_edge)."""
     if world < 1 or grid_x < world * min_columns:
         raise ValueError("need at least %d cell column(s) per rank (grid_x=%d, world=%d)" % (min_columns, grid_x, world))
     hist = np.bincount(np.clip(columns, 0, grid_x - 1), minlength=grid_x).astype(np.int64)
     cum = np.concatenate([[0], np.cumsum(hist)])
     total = int(cum[-1])
-    bounds = [0]
+    first, last = 0, grid_x
+    if margin is not None and total > 0:
+        occ = np.nonzero(hist)[0]
+        first = max(int(occ[0]) - int(margin), 0)
+        last = min(int(occ[-1]) + 1 + int(margin), grid_x)
+        short = world * min_columns - (last - first)   # (every rank still owns min_columns columns)
+        if short > 0:
+            first = max(first - short, 0)
+            last = min(first + world * min_columns, grid_x)
+    bounds = [first]
     for k in range(1, world):
         target = total * k / world
         x = int(np.searchsorted(cum, target, side="left"))  # first boundary with cum >= target
@@ -54,10 +72,16 @@ def plan_slabs(columns, grid_x, world, min_columns=1):
         if x > 0 and abs(cum[x - 1] - target) <= abs(cum[min(x, grid_x)] - target):
             x -= 1
         x = max(x, bounds[-1] + min_columns)        # (a slab owns at least as many columns as the ghost layer is wide)
-        x = min(x, grid_x - (world - k) * min_columns)
+        x = min(x, last - (world - k) * min_columns)
         bounds.append(x)
-    bounds.append(grid_x)
+    bounds.append(last)
     return [(bounds[k], bounds[k + 1]) for k in range(world)]
+
+
+def guard_columns(margin):
+    """Width of the warning zone at the open end of a cropped plan: half the margin (the plan is renewed when the front
+    has covered half of the free columns; the other half is what the particles may cover until the next check)."""
+    return 0 if margin is None else max(int(margin) // 2, 1)
 
 
 def deal(pos, slabs, cs):
@@ -90,10 +114,11 @@ def imbalance(owned_counts):
     return float(c.max() / max(c.mean(), 1.0))
 
 
-def needs_replan(owned_counts, live_counts, capacity, max_imbalance=1.25, fill=0.8):
-    """Re-plan when a slab holds `max_imbalance` times the mean, or when a slab's storage (owned + ghosts, counted
-    twice like slab_capacity does) approaches its capacity — whichever comes first."""
-    return imbalance(owned_counts) > max_imbalance or max(live_counts) > fill * capacity
+def needs_replan(owned_counts, live_counts, capacity, max_imbalance=1.25, fill=0.8, near_edge=0):
+    """Re-plan when a slab holds `max_imbalance` times the mean, when a slab's storage (owned + ghosts, counted
+    twice like slab_capacity does) approaches its capacity, or when particles have entered the guard columns at the
+    open end of a cropped plan — whichever comes first."""
+    return imbalance(owned_counts) > max_imbalance or max(live_counts) > fill * capacity or near_edge > 0
 
 
 def merge_by_id(parts, n_total):
@@ -141,10 +166,12 @@ class VirtualSlabs:
     same messages, neighbours' arenas addressed by plain device pointers instead of IPC handles."""
 
     def __init__(self, domain, pos, world, solids=None, vel=None, flags=None, device=-1, capacity_factor=1.5, halo_capacity=0,
-                 slabs=None, **ctx_kw):
+                 slabs=None, margin=DEFAULT_MARGIN, **ctx_kw):
         pos = np.ascontiguousarray(pos, np.float32)
         self.n_total = len(pos)
         self.world = world
+        self.margin = margin
+        ctx_kw = dict(ctx_kw, guard_columns=guard_columns(margin))
         self._args = (domain, solids, device, capacity_factor, halo_capacity, ctx_kw)
         self.grid = grid_dims(domain, cell_size())
         self.ctx = []
@@ -155,7 +182,7 @@ class VirtualSlabs:
         domain, solids, device, capacity_factor, halo_capacity, ctx_kw = self._args
         cs = cell_size()
         gw = max(int(ctx_kw.get("ghost_columns", 0)), 1)
-        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw)
+        self.slabs = slabs or plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw, self.margin)
         owned = deal(pos, self.slabs, cs)
         self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor, gw)
         self.ctx = [SlabContext(domain, s, self.capacity, solids, device, halo_capacity, **ctx_kw) for s in self.slabs]
@@ -179,12 +206,17 @@ class VirtualSlabs:
         info = [c.G.slab_info() for c in self.ctx]
         return [i["owned"] for i in info], [i["owned"] + 2 * i["ghosts"] for i in info]
 
+    def near_edge(self):
+        """Particles inside the guard columns at the open ends of a cropped plan (last substep)."""
+        return sum(c.G.slab_edge()[0] for c in self.ctx)
+
     def replan_if_needed(self, max_imbalance=1.25, fill=0.8):
         """Re-plans the slab boundaries from the current per-column histogram when the particles have gathered in a few
-        slabs: all particles are collected, dealt again and uploaded into new contexts.  A rare, slow step
-        (the boundaries are fixed between re-plans); returns True if it happened."""
+        slabs or approach the open end of a cropped plan: all particles are collected, dealt again and
+        uploaded into new contexts.  A rare, slow step (the boundaries are fixed between re-plans); returns True if it
+        happened."""
         owned, live = self.counts()
-        if not needs_replan(owned, live, self.capacity, max_imbalance, fill):
+        if not needs_replan(owned, live, self.capacity, max_imbalance, fill, self.near_edge()):
             return False
         pos, vel, flags = self.gather()
         for c in self.ctx:
@@ -209,12 +241,14 @@ class DistributedSlab:
     """This rank's slab of a torch.distributed job (one process per GPU, NCCL or gloo for the plumbing)."""
 
     def __init__(self, domain, pos, solids=None, vel=None, flags=None, device=0, capacity_factor=1.5, halo_capacity=0,
-                 context_factory=None, **ctx_kw):
+                 context_factory=None, margin=DEFAULT_MARGIN, **ctx_kw):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         pos = np.ascontiguousarray(pos, np.float32)
         self.n_total = len(pos)
+        self.margin = margin
+        ctx_kw = dict(ctx_kw, guard_columns=guard_columns(margin))
         self._args = (domain, solids, device, capacity_factor, halo_capacity, context_factory or SlabContext, ctx_kw)
         self.grid = grid_dims(domain, cell_size())
         self.ctx = None
@@ -230,7 +264,7 @@ class DistributedSlab:
         domain, solids, device, capacity_factor, halo_capacity, factory, ctx_kw = self._args
         cs = cell_size()
         gw = max(int(ctx_kw.get("ghost_columns", 0)), 1)
-        self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw)
+        self.slabs = plan_slabs(cell_x(pos, cs), self.grid[0], self.world, gw, self.margin)
         owned = deal(pos, self.slabs, cs)
         self.capacity = slab_capacity(pos, self.slabs, owned, cs, self.grid[0], capacity_factor, gw)
         self.ctx = factory(domain, self.slabs[self.rank], self.capacity, solids, device, halo_capacity, **ctx_kw)
@@ -259,13 +293,15 @@ class DistributedSlab:
         else:
             self.ctx.G.step_sand(params)
 
-    def counts(self):
-        """(owned, storage need) of every rank — one small all_gather, no device data."""
+    def counts(self, with_edge=False):
+        """(owned, storage need[, particles near the open end of a cropped plan]) of every rank — one small all_gather,
+        no device data."""
         info = self.ctx.G.slab_info()
-        mine = (int(info["owned"]), int(info["owned"] + 2 * info["ghosts"]))
+        mine = (int(info["owned"]), int(info["owned"] + 2 * info["ghosts"]), int(self.ctx.G.slab_edge()[0]))
         allc = [None] * self.world
         self.dist.all_gather_object(allc, mine)
-        return [c[0] for c in allc], [c[1] for c in allc]
+        out = [c[0] for c in allc], [c[1] for c in allc]
+        return out + (sum(c[2] for c in allc),) if with_edge else out
 
     def replan_if_needed(self, max_imbalance=1.25, fill=0.8):
         """Collective: re-plans the slab boundaries from the current particle columns when the load has drifted
@@ -273,8 +309,8 @@ class DistributedSlab:
         (all_gather over the process group), derives the same new plan, re-creates its context and re-wires its
         neighbours.  Rare and slow by design: between re-plans the boundaries are fixed and the data path has no
         collective.  Returns True if it happened."""
-        owned, live = self.counts()
-        if not needs_replan(owned, live, self.capacity, max_imbalance, fill):
+        owned, live, edge = self.counts(with_edge=True)
+        if not needs_replan(owned, live, self.capacity, max_imbalance, fill, edge):
             return False
         pos, vel, flags = self.gather()
         self.dist.barrier()        # nobody re-maps a neighbour's arena while it is still being read

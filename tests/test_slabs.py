@@ -47,6 +47,34 @@ def test_plan_edge_cases():
     assert sorted(np.concatenate(owned).tolist()) == [0, 1, 2]
 
 
+def test_cropped_plan_leaves_the_empty_part_of_the_domain_out():
+    """The 16 M dam break fills the first third of its domain: planned over the whole grid, the last of 8 ranks owns
+    two thirds of the cell columns (and their scan / brick descriptors / histogram); a cropped plan stops `margin`
+    columns past the outermost occupied column."""
+    grid_x = 488
+    cols = np.repeat(np.arange(0, 164), 1000)  # columns 0..163 occupied (252 lattice planes of spacing 1 in cells of 1.55)
+    full = slabs.plan_slabs(cols, grid_x, 8)
+    assert full[0][0] == 0 and full[-1][1] == grid_x and full[-1][1] - full[-1][0] > 300
+    plan = slabs.plan_slabs(cols, grid_x, 8, margin=32)
+    assert plan[0][0] == 0 and plan[-1][1] == 164 + 32
+    assert all(a[1] == b[0] for a, b in zip(plan, plan[1:])) and all(hi > lo for lo, hi in plan)
+    assert [p[0] for p in plan[1:]] == [p[0] for p in full[1:]]          # the inner boundaries are the balanced ones
+    assert max(hi - lo for lo, hi in plan) <= 21 + 32
+    # the occupied block in the middle of the grid: cropped on both sides; never beyond the grid
+    mid = slabs.plan_slabs(cols + 100, grid_x, 4, margin=16)
+    assert mid[0][0] == 100 - 16 and mid[-1][1] == 264 + 16
+    assert slabs.plan_slabs(cols + 100, 270, 4, margin=16)[-1][1] == 270
+    # a block narrower than the ranks need: the plan is widened to min_columns per rank
+    thin = slabs.plan_slabs(np.full(50, 7), 40, 4, min_columns=2, margin=0)
+    assert all(hi - lo >= 2 for lo, hi in thin) and thin[0][0] >= 0 and thin[-1][1] <= 40
+    owned = slabs.deal(np.array([[7 * 1.55 + 0.1, 1, 1]] * 50, np.float32), thin, slabs.cell_size())
+    assert sum(len(o) for o in owned) == 50
+    assert slabs.guard_columns(None) == 0 and slabs.guard_columns(32) == 16 and slabs.guard_columns(1) == 1
+    # particles in the guard columns of an open end ask for a new plan
+    assert not slabs.needs_replan([100, 100], [120, 120], 1000)
+    assert slabs.needs_replan([100, 100], [120, 120], 1000, near_edge=3)
+
+
 def test_merge_by_id_detects_loss_and_duplicates():
     a = (np.ones((2, 3), np.float32), np.zeros((2, 3), np.float32), np.zeros(2, np.int32), np.array([0, 2], np.int32))
     b = (np.ones((1, 3), np.float32) * 2, np.zeros((1, 3), np.float32), np.ones(1, np.int32), np.array([1], np.int32))
@@ -84,6 +112,7 @@ class FakeG:
         pos, ids = self.state
         return pos, np.zeros_like(pos), np.zeros(len(ids), np.int32), ids
     def slab_info(self): return {{"owned": len(self.state[1]), "ghosts": 0}}
+    def slab_edge(self): return (0, False)
     def close(self): pass
 
 class FakeCtx:
@@ -95,7 +124,7 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 domain, pos = scenes.dam_break(16)
 S = slabs.DistributedSlab(domain, pos, context_factory=FakeCtx)
-assert S.slabs == slabs.plan_slabs(slabs.cell_x(pos, slabs.cell_size()), S.grid[0], world)
+assert S.slabs == slabs.plan_slabs(slabs.cell_x(pos, slabs.cell_size()), S.grid[0], world, 1, slabs.DEFAULT_MARGIN)
 # neighbours wired left/right with the right handles
 want = {{}}
 if rank > 0: want[0] = rank - 1
@@ -116,7 +145,7 @@ before = list(S.slabs)
 owned, live = S.counts()
 assert sum(owned) == len(pos) and slabs.imbalance(owned) > 1.25, owned
 assert S.replan_if_needed() and S.replans == 1
-assert S.slabs != before and S.slabs == slabs.plan_slabs(slabs.cell_x(moved, slabs.cell_size()), S.grid[0], world)
+assert S.slabs != before and S.slabs == slabs.plan_slabs(slabs.cell_x(moved, slabs.cell_size()), S.grid[0], world, 1, slabs.DEFAULT_MARGIN)
 assert S.G.connected == want, "neighbours re-wired after the re-plan"
 owned2, _ = S.counts()
 assert sum(owned2) == len(pos) and slabs.imbalance(owned2) < 1.1, owned2
@@ -309,6 +338,43 @@ def test_free_running_slabs_replan_instead_of_overflowing(gw):
         close(sp, rp, "position")
         close(sv, rv, "velocity", atol=1e-3)
         V.close()
+
+
+@pytest.mark.gpu
+def test_cropped_plan_is_renewed_before_the_front_reaches_its_end():
+    """A plan cropped to the occupied columns (+ a small margin here) on a free-running dam break: the contexts count
+    the particles that enter the guard columns at the open end, replan_if_needed renews the plan, and the run stays the
+    single-context run.  Without re-planning the step fails loudly instead of binning particles into the wrong cells."""
+    domain, pos = scenes.dam_break(20)
+    kw = dict(dt=0.01, iterations=2, literal_lambda_index=0, exact_math=1)
+    grid_x = slabs.grid_dims(domain, slabs.cell_size())[0]
+    with lgpu.Context(domain, capacity_sand=len(pos)) as G:
+        G.upload_sand(pos)
+        V = slabs.VirtualSlabs(domain, pos, 3, capacity_factor=1.3, margin=6)
+        first_plan = list(V.slabs)
+        assert first_plan[-1][1] < grid_x and V.ctx[-1].G.slab_edge() == (0, True) and V.ctx[0].G.slab_edge() == (0, False)
+        cells_cropped = sum(c.G.slab_info()["local_cells"] for c in V.ctx)
+        full = slabs.VirtualSlabs(domain, pos, 3, capacity_factor=1.3, margin=None)
+        assert sum(c.G.slab_info()["local_cells"] for c in full.ctx) > cells_cropped
+        full.close()
+        for step in range(120):
+            G.step_fluid(**kw)
+            V.step(1, **kw)
+            if (step + 1) % 4 == 0 and V.replan_if_needed():
+                print("step", step + 1, "re-planned:", V.slabs, "near edge", V.near_edge())
+        assert V.replans >= 1 and V.slabs[-1][1] > first_plan[-1][1]
+        rp, rv, _ = G.download()
+        sp, sv, _ = V.gather()
+        close(sp, rp, "position")
+        close(sv, rv, "velocity", atol=1e-3)
+        V.close()
+    # never re-planned: the front runs out of the planned columns and the step says so
+    V = slabs.VirtualSlabs(domain, pos, 2, capacity_factor=2.0, margin=2)
+    with pytest.raises(lgpu.LgpuError, match="left the planned cell columns"):
+        for step in range(400):
+            V.step(1, **kw)
+            V.sync()
+    V.close()
 
 
 def test_plan_keeps_slabs_as_wide_as_the_ghost_layer():
