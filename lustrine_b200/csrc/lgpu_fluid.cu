@@ -122,11 +122,13 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_fluid_
                     const float x2 = x * x;
                     const float w = fmaf(-fp.s_corr_k, x2 * x2, li + pj.w) * fmaf(len, fp.fcA, fp.cB);
                     fx = fmaf(w, dx, fx); fy = fmaf(w, dy, fy); fz = fmaf(w, dz, fz);
-                    if (r2 > fp.thr2) far |= 1u << k;
+                    far = far_push(far, fp.thr2, r2);
                 });
+                const int k_top = 4 * ((min(cnt, 4 * LGPU_MG) + 3) >> 2) - 1;  // entry k sits at bit k_top - k of `far`
                 while (far) {  // neighbours beyond q = 0.5: replace the inner-branch term by the true one
-                    const int k = __ffs(far) - 1;
-                    far &= far - 1;
+                    const int b = 31 - __clz(far);
+                    far ^= 1u << b;
+                    const int k = k_top - b;
                     const float4 pj = lds128(code_addr(stage_addr, row_code(ck, k)));
                     const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));

@@ -29,6 +29,14 @@ struct FluidParams {
     int literal_lambda_index;
 };
 
+// Bit mask of the row entries that have drifted past q = 0.5, one bit per entry shifted in from the right: the bit is
+// the sign of thr2 - r2 (set <=> r2 > thr2; the rounded difference has the exact sign and is +0 on equality), moved in
+// by a funnel shift — FADD + SHF per neighbour instead of FSETP + SHF + SEL + LOP3 for `far |= (r2 > thr2) << k`.
+// After a whole row of n entries (padded to groups of four), entry k sits at bit n - 1 - k.
+__device__ __forceinline__ uint32_t far_push(uint32_t far, float thr2, float r2) {
+    return __funnelshift_l(__float_as_uint(thr2 - r2), far, 1);
+}
+
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -190,11 +198,13 @@ __device__ __forceinline__ void fluid_lambda_particle(const View& v, const Fluid
                 const float gs = fmaf(len, fp.fgA, fp.gB);
                 sum = fmaf(gs * gs, r2, sum);
                 gx = fmaf(-gs, dx, gx); gy = fmaf(-gs, dy, gy); gz = fmaf(-gs, dz, gz);
-                if (r2 > fp.thr2) far |= 1u << k;
+                far = far_push(far, fp.thr2, r2);
             });
+            const int k_top = 4 * ((min(cnt, 4 * LGPU_MG) + 3) >> 2) - 1;  // entry k sits at bit k_top - k of `far`
             while (far) {  // neighbours beyond q = 0.5: replace the inner-branch terms by the true ones
-                const int k = __ffs(far) - 1;
-                far &= far - 1;
+                const int b = 31 - __clz(far);
+                far ^= 1u << b;
+                const int k = k_top - b;
                 const float4 pj = lds128(code_addr(stage_addr, row_code(ck, k)));
                 const float dx = xi.x - pj.x, dy = xi.y - pj.y, dz = xi.z - pj.z;
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));

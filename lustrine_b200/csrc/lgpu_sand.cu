@@ -132,12 +132,18 @@ __global__ void __launch_bounds__(LGPU_BRICK_THREADS, LGPU_CTAS_PER_SM) k_sand_i
             const uint32_t solid_base = (uint32_t)ck.d->solid_base << 4;  // (table codes are stage slots x 16)
             uint32_t contact = 0;
             const unsigned long long pi_xy = pack2(pi.x, pi.y);
-            replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t, int k) {
-                if (!(dist2_exact(pi_xy, pi.z, pj) > sp.d2_contact_max)) contact |= 1u << k;
+            // (`apart` collects the sign of d2_contact_max - d2 per entry, shifted in from the right by a funnel shift: set
+            // <=> d2 > d2_contact_max, exactly — FADD + SHF per entry; entry k ends up at bit k_top - k)
+            uint32_t apart = 0;
+            replay_row<true>(ck, word & LGPU_CNT_MASK, [&](float4 pj, uint32_t, int) {
+                apart = __funnelshift_l(__float_as_uint(__fsub_rn(sp.d2_contact_max, dist2_exact(pi_xy, pi.z, pj))), apart, 1);
             });
-            while (contact) {
-                const int k = __ffs(contact) - 1;
-                contact &= contact - 1;
+            const int n_row = 4 * ((min(word & LGPU_CNT_MASK, 4 * LGPU_MG) + 3) >> 2), k_top = n_row - 1;
+            contact = ~apart & (n_row ? 0xffffffffu >> (32 - n_row) : 0u);
+            while (contact) {  // ascending entry = descending bit: the reference's list order
+                const int b = 31 - __clz(contact);
+                contact ^= 1u << b;
+                const int k = k_top - b;
                 const uint32_t code = row_code(ck, k);
                 const float4 pj = lds128(code_addr(stage_addr, code));
                 const bool is_sand = code < solid_base;
