@@ -362,7 +362,11 @@ def run_slabs(args, workload, kind, side, K, dt, steps, warmup, hbm_gbs, peak_sr
                                             "neighbour_table": pr_all[:, 4].tolist(), "lambda_total": pr_all[:, 6].tolist(),
                                             "deltap_or_contact_total": pr_all[:, 7].tolist(), "halo_refresh_total": pr_all[:, 8].tolist()},
                      "local_cells_per_rank": [int(x) for x in pr_all[:, 9]], "owned_per_rank": [int(x) for x in pr_all[:, 10]],
-                     "ghosts_per_rank": [int(x) for x in pr_all[:, 11]]}
+                     "ghosts_per_rank": [int(x) for x in pr_all[:, 11]],
+                     # what a rank receives per substep over NVLink (its neighbours send the same amounts): 64-byte halo records
+                     # for its ghosts after predict, then 4 bytes (lambda) / 16 bytes (x*) per ghost after every pass but the last
+                     "nvlink_bytes_in_per_substep_per_rank": [int(g) * (64 + (4 * K + 16 * (K - 1) if kind == "fluid" and gw < 2 else 16 * (K - 1)))
+                                                              for g in pr_all[:, 11]]}
 
     # e2e: host buffers in, host buffers out, every substep, on every rank
     e2e = None
