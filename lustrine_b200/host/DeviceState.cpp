@@ -34,7 +34,9 @@ void DeviceState::make_context(Simulation* s, int capacity_sand) {
     cfg.device = -1;
     LGPU_MUST(lgpu_create(&cfg, &ctx));
     capacity = capacity_sand;
+#ifndef LUSTRINE_B200_BULLET_HEADER
     s->bullet_physics_simulation.gpu = ctx;  // (the rigid-body side borrows the context for the player-AABB compaction)
+#endif
     lgpu_grid_info gi;
     LGPU_MUST(lgpu_get_grid(ctx, &gi));
     if (gi.grid[0] != s->gridX || gi.grid[1] != s->gridY || gi.grid[2] != s->gridZ || gi.kernel_radius != s->kernelRadius ||

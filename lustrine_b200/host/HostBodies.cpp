@@ -9,6 +9,7 @@
 
 #include "lgpu.h"
 #include "lustrine/BulletPhysics.hpp"
+#include "lustrine/RigidBodyHooks.hpp"
 
 namespace Lustrine {
 namespace Bullet {
@@ -94,6 +95,27 @@ glm::vec3 get_body_velocity(Simulation* s, int body) { return (body >= 0 && body
 void set_body_position(Simulation* s, int body, glm::vec3 p) { if (body >= 0 && body < s->num_bodies) s->bodies[body].position = p; }
 void set_body_velocity(Simulation* s, int body, glm::vec3 v) { if (body >= 0 && body < s->num_bodies) s->bodies[body].velocity = v; }
 void add_body_velocity(Simulation* s, int body, glm::vec3 v) { if (body >= 0 && body < s->num_bodies) s->bodies[body].velocity += v; }
+static Body* body_at(Simulation* s, int id) { return (id >= 0 && id < s->num_bodies) ? &s->bodies[id] : nullptr; }
+void set_body_frixion(Simulation* s, int body, float f) { if (Body* b = body_at(s, body)) b->friction = f; }
+float get_body_frixion(Simulation* s, int body) { Body* b = body_at(s, body); return b ? b->friction : 0.0f; }
+void set_body_damping(Simulation* s, int body, float linear, float angular) { if (Body* b = body_at(s, body)) { b->linear_damping = linear; b->angular_damping = angular; } }
+float get_body_lin_damping(Simulation* s, int body) { Body* b = body_at(s, body); return b ? b->linear_damping : 0.0f; }
+void set_body_no_rotation(Simulation*, int) {}  // (the stand-in's boxes never rotate)
+void check_collisions(Simulation* s, int body, int* indices, int* size) {
+    int n = 0;
+    for (int i = 0; i < s->num_bodies; i++) if (i != body && check_collision(s, body, i)) indices[n++] = i;
+    *size = n;
+}
+bool do_collide_except_for(Simulation* s, int body, int exception_id) {
+    for (int i = 0; i < s->num_bodies; i++) if (i != body && i != exception_id && check_collision(s, body, i)) return true;
+    return false;
+}
+void hook_set_body_gravity(Simulation* s, int body, glm::vec3 gravity) { if (Body* b = body_at(s, body)) b->gravity = gravity; }
+void hook_set_body_no_collision_response(Simulation* s, int body) { if (Body* b = body_at(s, body)) b->collision_response = false; }
+int hook_is_grounded(Simulation* s, int body) {
+    Body* b = body_at(s, body);
+    return b ? (int)(b->position.y - b->half_extents.y <= 0.55f) : 0;
+}
 void print_resume(const Simulation* s) { std::cout << "host bodies: " << s->num_bodies << std::endl; }
 
 }  // namespace Bullet

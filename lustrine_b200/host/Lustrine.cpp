@@ -155,7 +155,9 @@ void init_common(const SimulationParameters* parameters, Simulation* s, const st
     // device state: constants, solids once, sand
     B200::DeviceState* d = B200::DeviceState::create(s, kernel_radius_scale);
     s->gpu = d;
+#ifndef LUSTRINE_B200_BULLET_HEADER
     s->bullet_physics_simulation.gpu = d ? d->ctx : nullptr;
+#endif
 
     std::cout << "registered " << s->num_sand_particles << " sand particles and " << s->num_solid_particles
               << " solid particles (B200 device state: " << (d ? "ok" : "FAILED") << ")\n";

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "lustrine/RigidBodyHooks.hpp"
 #include "lustrine/Simulate.hpp"
 
 namespace Lustrine {
@@ -149,17 +150,8 @@ int add_detector_block(Vec3 position, Vec3 half) {
 }
 int check_collision(int a, int b) { return (int)Bullet::check_collision(&simulation->bullet_physics_simulation, a, b); }
 int do_collide(int body) { return (int)Bullet::do_collide(&simulation->bullet_physics_simulation, body); }
-int do_collide_except_for(int body, int exception_id) {
-    Bullet::Simulation* b = &simulation->bullet_physics_simulation;
-    for (int i = 0; i < b->num_bodies; i++) if (i != body && i != exception_id && Bullet::check_collision(b, body, i)) return 1;
-    return 0;
-}
-void check_collisions(int body, int* indices, int* size) {
-    Bullet::Simulation* b = &simulation->bullet_physics_simulation;
-    int n = 0;
-    for (int i = 0; i < b->num_bodies; i++) if (i != body && Bullet::check_collision(b, body, i)) indices[n++] = i;
-    *size = n;
-}
+int do_collide_except_for(int body, int exception_id) { return (int)Bullet::do_collide_except_for(&simulation->bullet_physics_simulation, body, exception_id); }
+void check_collisions(int body, int* indices, int* size) { Bullet::check_collisions(&simulation->bullet_physics_simulation, body, indices, size); }
 int get_num_bodies() { return Bullet::get_num_bodies(&simulation->bullet_physics_simulation); }
 void apply_impulse(int body, Vec3 impulse, Vec3 rel) { Bullet::apply_impulse(&simulation->bullet_physics_simulation, body, to_glm(impulse), to_glm(rel)); }
 Vec3 get_position(int body) { return from_glm(Bullet::get_body_position(&simulation->bullet_physics_simulation, body)); }
@@ -167,21 +159,14 @@ glm::vec3 get_velocity(int body) { return Bullet::get_body_velocity(&simulation-
 void set_velocity(int body, Vec3 v) { Bullet::set_body_velocity(&simulation->bullet_physics_simulation, body, to_glm(v)); }
 void set_position(int body, Vec3 p) { Bullet::set_body_position(&simulation->bullet_physics_simulation, body, to_glm(p)); }
 void add_velocity(int body, Vec3 v) { Bullet::add_body_velocity(&simulation->bullet_physics_simulation, body, to_glm(v)); }
-void set_body_no_rotation(int) {}
-static Bullet::Body* body_at(int id) {
-    Bullet::Simulation* b = &simulation->bullet_physics_simulation;
-    return (id >= 0 && id < b->num_bodies) ? &b->bodies[id] : nullptr;
-}
-void set_body_frixion(int body, float f) { if (Bullet::Body* b = body_at(body)) b->friction = f; }
-float get_body_frixion(int body) { Bullet::Body* b = body_at(body); return b ? b->friction : 0.0f; }
-void set_body_damping(int body, float linear, float angular) { if (Bullet::Body* b = body_at(body)) { b->linear_damping = linear; b->angular_damping = angular; } }
-float get_body_damping(int body) { Bullet::Body* b = body_at(body); return b ? b->linear_damping : 0.0f; }
+void set_body_no_rotation(int body) { Bullet::set_body_no_rotation(&simulation->bullet_physics_simulation, body); }
+void set_body_frixion(int body, float f) { Bullet::set_body_frixion(&simulation->bullet_physics_simulation, body, f); }
+float get_body_frixion(int body) { return Bullet::get_body_frixion(&simulation->bullet_physics_simulation, body); }
+void set_body_damping(int body, float linear, float angular) { Bullet::set_body_damping(&simulation->bullet_physics_simulation, body, linear, angular); }
+float get_body_damping(int body) { return Bullet::get_body_lin_damping(&simulation->bullet_physics_simulation, body); }
 void set_player_id(int id) { simulation->bullet_physics_simulation.player_id = id; }
 void set_player_box_scale(Vec3 scale) { simulation->bullet_physics_simulation.player_box_scale = to_glm(scale); }
-int is_grounded(int id) {
-    Bullet::Body* b = body_at(id);
-    return b ? (int)(b->position.y - b->half_extents.y <= 0.55f) : 0;
-}
+int is_grounded(int id) { return Bullet::hook_is_grounded(&simulation->bullet_physics_simulation, id); }
 void set_attract_blow_parameters(float attract_radius, float blow_radius, float attract_coeff, float blow_coeff) {  // :505-511
     simulation->attract_radius = attract_radius; simulation->blow_radius = blow_radius;
     simulation->attract_coeff = attract_coeff; simulation->blow_coeff = blow_coeff;
@@ -211,8 +196,8 @@ void set_simulate_function(int index) {  // :666-677
     }
 }
 
-void set_body_gravity(int id, Vec3 gravity) { if (Bullet::Body* b = body_at(id)) b->gravity = to_glm(gravity); }
-void set_body_no_collision_response(int id) { if (Bullet::Body* b = body_at(id)) b->collision_response = false; }
+void set_body_gravity(int id, Vec3 gravity) { Bullet::hook_set_body_gravity(&simulation->bullet_physics_simulation, id, to_glm(gravity)); }
+void set_body_no_collision_response(int id) { Bullet::hook_set_body_no_collision_response(&simulation->bullet_physics_simulation, id); }
 int collide_with_player(int id) { return check_collision(id, simulation->bullet_physics_simulation.player_id); }
 void enable_particles_bounding_boxes() { simulation->bullet_physics_simulation.particles_bounding_box_requested_state = true; }
 void disable_particles_bounding_boxes() { simulation->bullet_physics_simulation.particles_bounding_box_requested_state = false; }

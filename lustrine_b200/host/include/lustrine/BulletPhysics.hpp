@@ -12,9 +12,10 @@
 // that the particle step and the C wrapper touch and the same function names; the bodies are
 // stored in a small host-side table (kinematic: gravity + explicit Euler for dynamic bodies,
 // no contact solver).  The O(N) host scan is replaced by the device compaction
-// lgpu_aabb_first_k.  To couple a real Bullet world, compile the reference's own
-// BulletPhysics.cpp against its Simulation.hpp and use the plugin in plugin/simulate_b200.cpp
-// (INTEGRATION.md §2), where the reference's Bullet code runs unmodified.
+// lgpu_aabb_first_k.  To couple a real Bullet world, build the host library with
+// -DLUSTRINE_B200_BULLET_HEADER='"<reference>/src/BulletPhysics.hpp"': Simulation.hpp then embeds the reference's
+// Bullet::Simulation, HostBodies.cpp is left out and the reference's own BulletPhysics.cpp + Bullet are linked instead
+// (tests/cpp/Makefile builds exactly that for the parity test of the mixed scene).
 #pragma once
 
 #include <vector>
@@ -83,6 +84,13 @@ glm::vec3 get_body_velocity(Simulation* simulation, int body);
 void set_body_position(Simulation* simulation, int body, glm::vec3 position);
 void set_body_velocity(Simulation* simulation, int body, glm::vec3 velocity);
 void add_body_velocity(Simulation* simulation, int body, glm::vec3 velocity);
+void set_body_frixion(Simulation* simulation, int body, float frixion);           // (sic) src/BulletPhysics.hpp:59-63
+float get_body_frixion(Simulation* simulation, int body);
+void set_body_damping(Simulation* simulation, int body, float linear, float angular);
+float get_body_lin_damping(Simulation* simulation, int body);
+void set_body_no_rotation(Simulation* simulation, int body_index);
+void check_collisions(Simulation* simulation, int body, int* indices, int* size);  // :72-74
+bool do_collide_except_for(Simulation* simulation, int body, int exception_id);
 void print_resume(const Simulation* simulation);
 
 }  // namespace Bullet

@@ -10,7 +10,11 @@
 #include <utility>
 #include <vector>
 
+#ifdef LUSTRINE_B200_BULLET_HEADER
+#include LUSTRINE_B200_BULLET_HEADER   // the reference's BulletPhysics.hpp: a real Bullet world on the host (see BulletPhysics.hpp)
+#else
 #include "BulletPhysics.hpp"
+#endif
 #include "glm_compat.hpp"
 
 namespace Lustrine {

@@ -13,6 +13,9 @@ from wrapper_driver import WRAPPER_SYMBOLS, Wrapper
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OURS = os.path.join(ROOT, "lustrine_b200", "lib", "liblustrine_b200.so")
+# the drop-in built against the reference's BulletPhysics.hpp and linked with the reference's own BulletPhysics.cpp + Bullet 3.21
+# (tests/cpp/Makefile; test infrastructure, only where /root/reference was available at build time)
+OURS_REAL_BULLET = os.path.join(ROOT, "tests", "cpp", "_build", "liblustrine_b200_realbullet.so")
 
 
 def test_wrapper_symbols_exported():
@@ -114,4 +117,95 @@ def test_host_arrays_pageable_or_page_locked(pin_host, pinned_out, monkeypatch):
     got = run_scenario(Wrapper(OURS), pinned_out=pinned_out, **kw)
     assert got["n"] == ref["n"] and got["q"] == ref["q"]
     worst = max(float(np.abs(a - b).max()) for a, b in zip(got["pos"], ref["pos"]))
+    assert worst <= 1e-5
+
+
+def run_rigid_body_scenario(w, steps):
+    """The mixed scene of experiments/bullet/bullet.cpp:71-121 through the C wrapper: sand on a voxel floor, a capsule
+    player that drops into it, dynamic boxes, a static ground box, a detector block; the <= 100 proxy boxes around the
+    player switched on; attract and blow windows.  Returns what a game would read back every frame."""
+    from wrapper_driver import Vec3
+    L = w.L
+    data = w.init((30, 25, 30), 0.5, sand=[((9, 7, 9), (10.0, 2.0, 10.0))], solids=[((24, 1, 24), (0.0, 0.0, 0.0), 2)], subdivision=1)
+    player = L.add_capsule(Vec3(15.0, 11.0, 15.0), 2.0, 3.0)
+    boxes = [L.add_box(Vec3(16.0, 15.0, 16.0), True, Vec3(0.5, 0.5, 0.5)), L.add_box(Vec3(14.0, 15.0, 14.0), True, Vec3(0.5, 0.5, 0.5)),
+             L.add_box(Vec3(6.0, 2.0, 6.0), True, Vec3(3.0, 1.0, 1.0))]
+    ground = L.add_box(Vec3(15.0, -0.5, 15.0), False, Vec3(15.0, 1.0, 15.0))
+    detector = L.add_detector_block(Vec3(15.0, 6.0, 15.0), Vec3(2.0, 2.0, 2.0))
+    L.set_body_no_rotation(player)
+    L.set_body_frixion(player, 0.4)
+    L.set_body_damping(boxes[2], 0.1, 0.2)
+    L.set_player_id(player)
+    L.set_player_box_scale(Vec3(4.0, 7.0, 4.0))
+    L.enable_particles_bounding_boxes()
+    L.set_attract_blow_parameters(12.0, 9.0, 1000.0, 500.0)
+    trace = {"n0": (data.num_sand_particles, data.num_solid_particles), "bodies": L.get_num_bodies(), "pos": [], "body_pos": [], "flags": [],
+             "props": (L.get_body_damping(boxes[2]), L.get_body_damping(player))}
+    for s in range(steps):
+        if s == 30:
+            L.apply_impulse(boxes[2], Vec3(0.0, 12.0, 3.0), Vec3(0.0, 0.0, 0.0))
+        L.simulate(0.016, 18 <= s < 30, 38 <= s < 44)
+        trace["pos"].append(w.positions())
+        bp = []
+        for b in [player] + boxes + [ground, detector]:
+            v = L.get_position(b)
+            bp.append((v.x, v.y, v.z))
+        trace["body_pos"].append(bp)
+        trace["flags"].append((L.is_grounded(player), L.check_collision(detector, player), L.do_collide(player), L.collide_with_player(boxes[2]),
+                               L.do_collide_except_for(player, ground)))
+    L.cleanup_simulation()
+    return trace
+
+
+@pytest.mark.gpu
+def test_mixed_scene_with_the_real_bullet_world_matches_the_reference():
+    """BASELINE config 5 in small: the drop-in with a REAL Bullet world on the host (the reference's own BulletPhysics.cpp
+    and Bullet 3.21 linked in, north_star keeps them there) against the unmodified reference, frame by frame: particles,
+    every rigid body's position, the ground / detector / collision answers.  The particle step runs on the GPU; the proxy
+    boxes the reference parks on the <= 100 particles around the player come from the host arrays the step hands back."""
+    if not O.have_ref() or not os.path.exists(OURS_REAL_BULLET):
+        pytest.skip("oracle/_ref or tests/cpp/_build/liblustrine_b200_realbullet.so not built")
+    steps = 70
+    ref = run_rigid_body_scenario(Wrapper(O.REF_LIT_SO), steps)
+    got = run_rigid_body_scenario(Wrapper(OURS_REAL_BULLET), steps)
+    assert got["n0"] == ref["n0"] and got["bodies"] == ref["bodies"] and got["props"] == ref["props"]
+    worst_p = max(float(np.abs(a - b).max()) for a, b in zip(got["pos"], ref["pos"]))
+    worst_b = max(float(np.abs(np.array(a) - np.array(b)).max()) for a, b in zip(got["body_pos"], ref["body_pos"]))
+    moved = float(np.abs(np.array(ref["body_pos"][-1]) - np.array(ref["body_pos"][0])).max())
+    grounded = [f[0] for f in ref["flags"]]
+    print("  particles max|dx| %.3e, rigid bodies max|dx| %.3e over %d frames (bodies moved up to %.2f; player grounded in %d frames, "
+          "in the detector in %d)" % (worst_p, worst_b, steps, moved, sum(grounded), sum(f[1] for f in ref["flags"])))
+    assert worst_p <= 1e-5 and worst_b <= 1e-4
+    assert got["flags"] == ref["flags"], "is_grounded / check_collision / do_collide per frame"
+    assert moved > 3.0 and 0 < sum(grounded) < steps, "the scene must exercise the rigid bodies"
+
+
+@pytest.mark.gpu
+def test_stand_in_bodies_keep_the_wrapper_api_alive():
+    """The default build answers the ~30 rigid-body pass-throughs from host/HostBodies.cpp (a stand-in): the
+    particle side of the mixed scene must not depend on which engine moves the player — with the player pinned by
+    set_position every frame, the particles are those of the reference."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from wrapper_driver import Vec3
+
+    def run(w):
+        L = w.L
+        w.init((30, 25, 30), 0.5, sand=[((9, 7, 9), (10.0, 2.0, 10.0))], solids=[((24, 1, 24), (0.0, 0.0, 0.0), 2)], subdivision=1)
+        player = L.add_capsule(Vec3(15.0, 6.0, 15.0), 2.0, 3.0)
+        L.set_body_gravity(player, Vec3(0.0, 0.0, 0.0))
+        L.set_player_id(player)
+        L.set_player_box_scale(Vec3(4.0, 7.0, 4.0))
+        L.set_attract_blow_parameters(12.0, 9.0, 1000.0, 500.0)
+        out = []
+        for s in range(30):
+            L.set_position(player, Vec3(15.0 + 0.1 * s, 6.0, 15.0))
+            L.set_velocity(player, Vec3(0.0, 0.0, 0.0))
+            L.simulate(0.016, 8 <= s < 16, 20 <= s < 24)
+            out.append(w.positions())
+        L.cleanup_simulation()
+        return out
+    ref, got = run(Wrapper(O.REF_LIT_SO)), run(Wrapper(OURS))
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(got, ref))
+    print("  particles max|dx| %.3e over 30 frames with the player moved by the caller" % worst)
     assert worst <= 1e-5

@@ -65,6 +65,26 @@ class Wrapper:
         L.get_position.restype = Vec3
         L.get_duration.argtypes = [C.c_int]
         L.get_duration.restype = C.c_double
+        # rigid bodies (host side; src/LustrineWrapper.hpp:108-160)
+        L.add_box.argtypes = [Vec3, C.c_bool, Vec3]
+        L.add_capsule.argtypes = [Vec3, C.c_float, C.c_float]
+        L.add_detector_block.argtypes = [Vec3, Vec3]
+        L.set_player_box_scale.argtypes = [Vec3]
+        L.set_velocity.argtypes = [C.c_int, Vec3]
+        L.add_velocity.argtypes = [C.c_int, Vec3]
+        L.apply_impulse.argtypes = [C.c_int, Vec3, Vec3]
+        L.set_body_gravity.argtypes = [C.c_int, Vec3]
+        L.set_body_frixion.argtypes = [C.c_int, C.c_float]
+        if hasattr(L, "get_body_frixion"):  # (declared by the reference's header, defined only by the drop-in)
+            L.get_body_frixion.argtypes = [C.c_int]
+            L.get_body_frixion.restype = C.c_float
+        L.set_body_damping.argtypes = [C.c_int, C.c_float, C.c_float]
+        L.get_body_damping.argtypes = [C.c_int]
+        L.get_body_damping.restype = C.c_float
+        for f in (L.is_grounded, L.do_collide, L.set_body_no_rotation, L.set_body_no_collision_response, L.collide_with_player):
+            f.argtypes = [C.c_int]
+        L.check_collision.argtypes = [C.c_int, C.c_int]
+        L.do_collide_except_for.argtypes = [C.c_int, C.c_int]
         self.params = None
 
     def grid_box(self, params, dims, position, gtype, cell_value=1):
