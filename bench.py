@@ -65,6 +65,16 @@ def load_traffic(workload, kernel):
         return None, None
 
 
+def load_pipes(kernel):
+    """Utilisation of the fp32 (FMA) pipe, the shared-memory data pipe and the issue slots of `kernel` from the same committed ncu
+    capture (SURVEY §8d asks for the fp32 pipe beside the HBM figure), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["pipes"][kernel]
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -498,6 +508,8 @@ def rooflines(kind, K, n, num_cells, phase, ms_per_step, hbm_gbs, peak_src, work
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                 "frac": achieved / hbm_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                # % of peak of the fp32 (FMA) pipe, the shared-memory data pipe and the issue slots, from the same ncu capture
+                "pipes_ncu": load_pipes("k_" + dom),
                 "note": "sparse stencil: ~19 neighbour interactions per particle per launch are gathered from a shared-memory stage of the "
                         "particle's brick; the kernel is bound by that gather (LDS wavefronts + issue slots), not by HBM (DESIGN.md §5)"}
     step_achieved = step_bytes * n / (ms_per_step * 1e-3) / 1e9

@@ -45,6 +45,7 @@ ncu -i $G/${TAG}_prof.ncu-rep --page raw --csv > /tmp/${TAG}_raw.csv 2>/dev/null
 python - "$TAG" <<'PY'
 import csv, json, sys
 tag = sys.argv[1]
+pipes = {}
 out = {"source": "ncu --set full --clock-control none, profiles ncu summary of this round (dram__bytes_read.sum + dram__bytes_write.sum of one launch)"}
 def grab(path, names):
     rows = list(csv.reader(open(path)))
@@ -58,11 +59,19 @@ def grab(path, names):
                     v = float(r[idx[m]].replace(",", "")); u = rows[1][idx[m]]
                     return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
                 res[key] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+                def pct(m):
+                    try: return float(r[idx[m]].replace(",", ""))
+                    except Exception: return None
+                # the fp32 pipe beside the HBM figure; plus the two units that are busiest in these kernels
+                pipes.setdefault(key, {"fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                                       "shared_memory_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                                       "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active")})
     return res
 try:
     out["dam_break_1m"] = grab("/tmp/%s_raw.csv" % tag, {"k_fluid_lambda": "k_fluid_lambda", "k_fluid_deltap": "k_fluid_deltap"})
     try: out["sand_pile_4m"] = grab("/tmp/%s_sand_raw.csv" % tag, {"k_sand_iteration": "k_sand_iteration"})
     except Exception: pass
+    out["pipes"] = pipes
     json.dump(out, open("profiles/traffic.json", "w"), indent=1)
     print(out)
 except Exception as e:
