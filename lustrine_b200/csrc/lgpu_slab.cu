@@ -447,12 +447,13 @@ int lgpu_slab_end(lgpu_ctx* c, const lgpu_step_params& p, int mode) {
 // Programmatic dependent launch keeps the next solver kernel's blocks resident while k_refresh waits for the
 // neighbours.  That is only safe when every neighbour runs on ANOTHER GPU: slabs that share a device (the
 // virtual ranks of the single-GPU tests) would starve each other of SM resources and dead-lock.
-// Measured on 2 B200s: 1.5 % per substep.  Off unless LGPU_PDL_SLAB=1 until it has been run on 4 and 8 GPUs.
+// Measured: 1.5 % per substep on 2 B200s, 2 % on 8 (1.27 -> 1.24 ms, 16 M dam break); bit-identical to the single-context
+// run.  On whenever every neighbour is another process's GPU; LGPU_PDL_SLAB=0 turns it off.
 bool lgpu_slab_pdl_ok(const lgpu_ctx* c) {
     const SlabState* S = c->slab;
     if (!S || (!S->has_nbr[0] && !S->has_nbr[1])) return true;
-    static const bool on = getenv("LGPU_PDL_SLAB") && atoi(getenv("LGPU_PDL_SLAB")) != 0;
-    if (!on) return false;
+    static const bool off = getenv("LGPU_PDL_SLAB") && atoi(getenv("LGPU_PDL_SLAB")) == 0;
+    if (off) return false;
     for (int s = 0; s < 2; s++) if (S->has_nbr[s] && !S->peer_ipc[s]) return false;
     return true;
 }
