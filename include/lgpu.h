@@ -185,6 +185,21 @@ LGPU_API int lgpu_set_generic_kernels(lgpu_ctx* ctx, int on);
  * Particles carry caller-given global ids (lgpu_slab_upload / lgpu_slab_download).
  * lgpu_slab_step_begin/_end split a substep so that ONE host thread can drive several contexts
  * (tests on a single GPU): call _begin on all of them, then _end on all of them. */
+/* Host-side planning for a C / C++ host (lustrine_b200/slabs.py holds the same logic for the Python host of the tests and
+ * of bench.py; tests/test_slabs.py checks the two against each other).  No device is touched.
+ *   column_hist[grid_x]  particles per global cell column (x / cell_size, truncated) — what the ranks obtain with one
+ *                        all-reduce of an int array
+ *   lgpu_plan_slabs      boundaries bounds[0..world]: rank k owns the columns [bounds[k], bounds[k + 1]), equal particle
+ *                        counts as far as whole columns allow, every rank at least min_columns wide (>= the ghost layer).
+ *                        margin < 0: the plan covers [0, grid_x); margin >= 0: it is cropped to the occupied columns plus
+ *                        `margin` free columns on either side (create the contexts with slab_guard_columns =
+ *                        lgpu_slab_guard_columns(margin) and re-plan when lgpu_slab_edge reports particles near the end).
+ *   lgpu_slab_capacity   capacity_sand for every context of the plan (equal on all ranks): owned + twice the ghost
+ *                        columns of the fullest slab, times `factor` (head room until the next re-plan), + 4096.
+ * Returns LGPU_ERR_ARG if grid_x cannot give every rank min_columns columns. */
+LGPU_API int lgpu_plan_slabs(const long long* column_hist, int grid_x, int world, int min_columns, int margin, int* bounds);
+LGPU_API int lgpu_slab_guard_columns(int margin);
+LGPU_API long long lgpu_slab_capacity(const long long* column_hist, int grid_x, const int* bounds, int world, int ghost_columns, double factor);
 LGPU_API int lgpu_slab_export(lgpu_ctx* ctx, unsigned char handle[64], void** local_ptr, size_t* bytes);
 LGPU_API int lgpu_slab_connect(lgpu_ctx* ctx, int side, const unsigned char handle[64], void* same_process_ptr);
 /* out: x_lo, x_hi, local grid X, local cells, owned particles, ghost particles, halo capacity, x offset */

@@ -54,7 +54,7 @@ SYMBOLS = [
     "lgpu_num_solids", "lgpu_step_fluid", "lgpu_step_sand", "lgpu_sync", "lgpu_last_step_ms",
     "lgpu_launch_count", "lgpu_set_phase_timing", "lgpu_set_use_graph", "lgpu_graph_stats", "lgpu_set_stage_slots", "lgpu_set_generic_kernels", "lgpu_cell_count",
     "lgpu_remove_in_cells", "lgpu_aabb_first_k", "lgpu_dump", "lgpu_eval_kernel", "lgpu_counting_sort",
-    "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_edge", "lgpu_slab_upload", "lgpu_slab_download",
+    "lgpu_plan_slabs", "lgpu_slab_guard_columns", "lgpu_slab_capacity", "lgpu_slab_export", "lgpu_slab_connect", "lgpu_slab_info", "lgpu_slab_edge", "lgpu_slab_upload", "lgpu_slab_download",
     "lgpu_slab_step_begin", "lgpu_slab_step_end",
 ]
 
@@ -103,6 +103,10 @@ def lib():
         L.lgpu_dump.argtypes = [vp, c_i, vp, C.c_size_t]
         L.lgpu_eval_kernel.argtypes = [vp, C.POINTER(StepParams), c_i, vp, c_i, vp]
         L.lgpu_counting_sort.argtypes = [vp, c_i, c_i, vp, c_i]
+        L.lgpu_plan_slabs.argtypes = [vp, c_i, c_i, c_i, c_i, vp]
+        L.lgpu_slab_guard_columns.argtypes = [c_i]
+        L.lgpu_slab_capacity.argtypes = [vp, c_i, vp, c_i, c_i, C.c_double]
+        L.lgpu_slab_capacity.restype = C.c_longlong
         L.lgpu_slab_export.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.lgpu_slab_connect.argtypes = [vp, c_i, vp, vp]
         L.lgpu_slab_info.argtypes = [vp, C.POINTER(c_i * 8)]
@@ -118,6 +122,20 @@ def lib():
 def _check(status, what):
     if status != 0:
         raise LgpuError("%s failed with status %d: %s" % (what, status, lib().lgpu_last_error().decode()))
+
+
+def plan_slabs_c(column_hist, world, min_columns=1, margin=None):
+    """lgpu_plan_slabs (the C host's planner): [(x_lo, x_hi)] per rank from the per-column particle histogram."""
+    hist = np.ascontiguousarray(column_hist, np.int64)
+    bounds = np.zeros(world + 1, np.int32)
+    _check(lib().lgpu_plan_slabs(_ptr(hist), len(hist), int(world), int(min_columns), -1 if margin is None else int(margin), _ptr(bounds)), "lgpu_plan_slabs")
+    return [(int(bounds[k]), int(bounds[k + 1])) for k in range(world)]
+
+
+def slab_capacity_c(column_hist, slabs_plan, ghost_columns=1, factor=1.5):
+    hist = np.ascontiguousarray(column_hist, np.int64)
+    bounds = np.ascontiguousarray([s[0] for s in slabs_plan] + [slabs_plan[-1][1]], np.int32)
+    return int(lib().lgpu_slab_capacity(_ptr(hist), len(hist), _ptr(bounds), len(slabs_plan), int(ghost_columns), float(factor)))
 
 
 def default_step_params(**overrides):

@@ -75,6 +75,50 @@ def test_cropped_plan_leaves_the_empty_part_of_the_domain_out():
     assert slabs.needs_replan([100, 100], [120, 120], 1000, near_edge=3)
 
 
+def test_c_planner_equals_the_python_planner():
+    """include/lgpu.h offers the planning to a C / C++ host (lgpu_plan_slabs, lgpu_slab_capacity, lgpu_slab_guard_columns);
+    it must decide exactly what lustrine_b200/slabs.py decides, on the BASELINE layouts and on random histograms."""
+    rng = np.random.default_rng(7)
+    cs = slabs.cell_size()
+    cases = []
+    domain, pos = scenes.dam_break(20)
+    grid = slabs.grid_dims(domain, cs)
+    cases.append((slabs.cell_x(pos, cs), grid[0]))
+    cases.append((np.repeat(np.arange(0, 164), 50), 488))                       # the 16 M dam break's column layout
+    cases.append((np.repeat(np.arange(0, 164), 50) + 100, 488))
+    for _ in range(60):
+        gx = int(rng.integers(8, 300))
+        lo = int(rng.integers(0, gx)); hi = int(rng.integers(lo, gx))
+        n = int(rng.integers(1, 4000))
+        cols = rng.integers(lo, hi + 1, n)
+        if rng.random() < 0.3:
+            cols = np.concatenate([cols, np.full(int(rng.integers(1, 3000)), int(rng.integers(lo, hi + 1)))])  # one crowded column
+        cases.append((cols, gx))
+    checked = 0
+    for cols, gx in cases:
+        hist = np.bincount(np.clip(cols, 0, gx - 1), minlength=gx)
+        for world in (1, 2, 3, 4, 8):
+            for min_columns in (1, 2):
+                if gx < world * min_columns:
+                    continue
+                for margin in (None, 0, 3, 32):
+                    want = slabs.plan_slabs(cols, gx, world, min_columns, margin)
+                    got = lgpu.plan_slabs_c(hist, world, min_columns, margin)
+                    assert got == want, (gx, world, min_columns, margin, got, want)
+                    checked += 1
+                    # capacity: the Python helper works from positions, the C one from the histogram
+                    owned = [int(hist[(0 if k == 0 else lo):(gx if k == world - 1 else hi)].sum()) for k, (lo, hi) in enumerate(want)]
+                    need = 0
+                    for (lo, hi), o in zip(want, owned):
+                        g = int(hist[max(lo - min_columns, 0):lo].sum()) + int(hist[hi:min(hi + min_columns, gx)].sum())
+                        need = max(need, o + 2 * g)
+                    assert lgpu.slab_capacity_c(hist, want, min_columns, 1.5) == int(need * 1.5) + 4096
+    assert checked > 1000
+    assert [lgpu.lib().lgpu_slab_guard_columns(m) for m in (-1, 0, 1, 2, 32)] == [slabs.guard_columns(m) for m in (None, 0, 1, 2, 32)]
+    with pytest.raises(lgpu.LgpuError):
+        lgpu.plan_slabs_c(np.ones(3, np.int64), 4)
+
+
 def test_merge_by_id_detects_loss_and_duplicates():
     a = (np.ones((2, 3), np.float32), np.zeros((2, 3), np.float32), np.zeros(2, np.int32), np.array([0, 2], np.int32))
     b = (np.ones((1, 3), np.float32) * 2, np.zeros((1, 3), np.float32), np.ones(1, np.int32), np.array([1], np.int32))
